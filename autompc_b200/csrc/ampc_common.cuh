@@ -1,0 +1,218 @@
+// Shared device/host helpers for libampc_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/ampc_b200.h"
+
+// ------------------------------------------------------------------ errors ---
+void ampc_set_error(const char *fmt, ...);
+void ampc_count_launch(int n = 1);
+
+#define AMPC_CUDA_CHECK(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      ampc_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                     cudaGetErrorString(_e));                                              \
+      return AMPC_ERR_CUDA;                                                                \
+    }                                                                                      \
+  } while (0)
+
+#define AMPC_REQUIRE(cond, code, ...) \
+  do {                                \
+    if (!(cond)) {                    \
+      ampc_set_error(__VA_ARGS__);    \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+// ----------------------------------------------------------------- Philox ---
+// Philox4x32-10 (Salmon et al. 2011).  Counter = (global sample, step | block<<16,
+// solve counter lo, hi); key = (seed lo, seed hi).  One call yields four N(0,1)
+// draws (two Box-Muller pairs) for control dims [4*block, 4*block+4).
+__host__ __device__ __forceinline__ void ampc_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                            uint32_t c3, uint32_t k0, uint32_t k1,
+                                                            uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), hi1 = __umulhi(0xCD9E8D57u, c2);
+#else
+    const uint32_t hi0 = (uint32_t)(((uint64_t)0xD2511F53u * c0) >> 32);
+    const uint32_t hi1 = (uint32_t)(((uint64_t)0xCD9E8D57u * c2) >> 32);
+#endif
+    const uint32_t lo0 = 0xD2511F53u * c0, lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Four unit normals for (sample kg, step h, 4-wide control block blk).
+__device__ __forceinline__ void ampc_normal4(uint64_t seed, uint64_t ctr, uint32_t kg, uint32_t h,
+                                             uint32_t blk, float n[4]) {
+  uint32_t r[4];
+  ampc_philox4x32_10(kg, h | (blk << 16), (uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)seed,
+                     (uint32_t)(seed >> 32), r);
+  const float inv24 = 5.9604644775390625e-8f;  // 2^-24
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const float u1 = (float)((r[2 * q] >> 8) + 1u) * inv24;  // (0,1]
+    const float u2 = (float)(r[2 * q + 1] >> 8) * inv24;     // [0,1)
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    n[2 * q] = rad * c;
+    n[2 * q + 1] = rad * s;
+  }
+}
+
+// ------------------------------------------------------------ activations ---
+template <typename T>
+__device__ __forceinline__ T ampc_act(int act, T y) {
+  switch (act) {
+    case AMPC_ACT_RELU: return y > T(0) ? y : T(0);
+    case AMPC_ACT_TANH: return tanh(y);
+    case AMPC_ACT_SIGMOID: return T(1) / (T(1) + exp(-y));
+    default: {  // SELU, torch.nn.SELU constants
+      const T alpha = T(1.6732632423543772848170429916717), scale = T(1.0507009873554804934193349852946);
+      return scale * (y > T(0) ? y : alpha * expm1(y));
+    }
+  }
+}
+template <typename T>
+__device__ __forceinline__ T ampc_act_grad(int act, T y) {
+  switch (act) {
+    case AMPC_ACT_RELU: return y > T(0) ? T(1) : T(0);
+    case AMPC_ACT_TANH: { T t = tanh(y); return T(1) - t * t; }
+    case AMPC_ACT_SIGMOID: { T s = T(1) / (T(1) + exp(-y)); return s * (T(1) - s); }
+    default: {
+      const T alpha = T(1.6732632423543772848170429916717), scale = T(1.0507009873554804934193349852946);
+      return scale * (y > T(0) ? T(1) : alpha * exp(y));
+    }
+  }
+}
+
+// --------------------------------------------------------------- reductions ---
+__device__ __forceinline__ float ampc_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float ampc_warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ----------------------------------------------------- MPPI kernel params ---
+// Layout of the fp32 constant block both rollout kernels stage into shared memory.
+struct AmpcConstLayout {
+  int xu_mean, xu_inv, dy_mean, dy_std, goal, Q, R, F, lo, hi, scale, total;
+  __host__ __device__ AmpcConstLayout(int nx, int nu) {
+    int o = 0;
+    xu_mean = o; o += nx + nu;
+    xu_inv = o; o += nx + nu;
+    dy_mean = o; o += nx;
+    dy_std = o; o += nx;
+    goal = o; o += nx;
+    Q = o; o += nx * nx;
+    R = o; o += nu * nu;
+    F = o; o += nx * nx;
+    lo = o; o += nu;
+    hi = o; o += nu;
+    scale = o; o += nu;
+    total = (o + 3) & ~3;
+  }
+};
+
+struct AmpcMppiParams {
+  int K, H, nx, nu;
+  int k_offset, K_global;
+  int terminal_mode, q_diag, f_diag, act;
+  int n_layers;
+  int dims[AMPC_MAX_LAYERS + 1];
+  int npt[AMPC_MAX_LAYERS];   // fp32 kernel: outputs per thread of each layer
+  int woff[AMPC_MAX_LAYERS];  // float offsets into wpack
+  int boff[AMPC_MAX_LAYERS];
+  int wpack_floats;
+  int max_width;              // widest activation (incl. input)
+  float inv_lmda, sqrt_sigma, lam_over_sigma;
+  uint64_t seed, ctr;
+  const float *wpack;     // packed weights + biases (layout is kernel-specific)
+  const float *consts;    // AmpcConstLayout
+  const float *x0;        // (nx,)
+  const float *eps;       // NULL or (H,K,nu) unclipped noise
+  float *act_seq;         // (H,nu) in/out
+  float *costs;           // (K,)
+  float *term_out;        // scalar (terminal_mode 0)
+  float *partials;        // (gridDim.x, 2 + H*nu)
+  unsigned int *ticket;   // grid completion counter
+  float *record_out;      // NULL: update act_seq in-kernel;  else write [m, s, W] here
+  float *u_out;           // (nu,)
+};
+
+// Merge softmax partial records [m, s, W(HN)] (block level or rank level) and either
+// apply the update (mppi.py:115-118) or emit the merged record.  Called by one CTA.
+// `s_act_shift` = shifted action sequence (mppi.py:122-123) in shared memory.
+// s_scratch: >= 64 + AMPC_MERGE_CACHE floats of shared memory.
+#define AMPC_MERGE_CACHE 1024
+__device__ __forceinline__ void ampc_merge_records(const float *recs, int n_recs, int rec_stride, int HN,
+                                                   int nu, float inv_lmda, const float *s_act_shift,
+                                                   const float *scale, float *act_seq, float *u_out,
+                                                   float *record_out, float *s_scratch) {
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  float *s_rs = s_scratch + 64;  // per-record rescale exp(-(m_b - m)/lmda), cached when it fits
+  const bool cached = n_recs <= AMPC_MERGE_CACHE;
+  float m = INFINITY;
+  for (int b = tid; b < n_recs; b += nthr) m = fminf(m, __ldcg(recs + (size_t)b * rec_stride));
+  m = ampc_warp_min(m);
+  if (lane == 0) s_scratch[warp] = m;
+  __syncthreads();
+  m = s_scratch[0];
+  for (int w = 1; w < nwarp; ++w) m = fminf(m, s_scratch[w]);
+  float s = 0.f;
+  for (int b = tid; b < n_recs; b += nthr) {
+    const float mb = __ldcg(recs + (size_t)b * rec_stride);
+    const float rs = expf(-(mb - m) * inv_lmda);
+    if (cached) s_rs[b] = rs;
+    s += __ldcg(recs + (size_t)b * rec_stride + 1) * rs;
+  }
+  s = ampc_warp_sum(s);
+  if (lane == 0) s_scratch[32 + warp] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int w = 0; w < nwarp; ++w) s += s_scratch[32 + w];
+  for (int e = tid; e < HN; e += nthr) {
+    float acc = 0.f;
+    if (cached) {
+      for (int b = 0; b < n_recs; ++b)
+        acc = fmaf(__ldcg(recs + (size_t)b * rec_stride + 2 + e), s_rs[b], acc);
+    } else {
+      for (int b = 0; b < n_recs; ++b) {
+        const float mb = __ldcg(recs + (size_t)b * rec_stride);
+        acc = fmaf(__ldcg(recs + (size_t)b * rec_stride + 2 + e), expf(-(mb - m) * inv_lmda), acc);
+      }
+    }
+    if (record_out) {
+      record_out[2 + e] = acc;
+    } else {
+      const float v = s_act_shift[e] + acc / s;
+      act_seq[e] = v;
+      if (e < nu) u_out[e] = v * scale[e];
+    }
+  }
+  if (record_out && tid == 0) {
+    record_out[0] = m;
+    record_out[1] = s;
+  }
+}

@@ -1,0 +1,111 @@
+// float64 MLP device routines shared by mlp_ops.cu and ilqr.cu.
+// Semantics: autompc/sysid/mlp.py:55-59 (ForwardNet.forward) and the closed form
+// of the Jacobian back-propagation in mlp.py:238-305.
+#pragma once
+#include "ampc_common.cuh"
+
+struct AmpcMlpF64 {
+  int n_layers, act, nx, nu, max_width;
+  int dims[AMPC_MAX_LAYERS + 1];
+  const double *Wt[AMPC_MAX_LAYERS];  // [in][out] (transposed torch.nn.Linear.weight)
+  const double *b[AMPC_MAX_LAYERS];
+  const double *xu_mean, *xu_std, *dy_mean, *dy_std;
+};
+
+int ampc_mlp_f64_upload(const ampc_mlp_desc *mlp, int nx, int nu, AmpcMlpF64 *net, double **blob_out);
+
+// dot(Wt[:, j], h) with four independent partial sums (hides fp64 FMA latency)
+__device__ __forceinline__ double ampc_dot_col(const double *__restrict__ Wt, int N, int j, const double *h, int Kin) {
+  double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+  int k = 0;
+  for (; k + 4 <= Kin; k += 4) {
+    p0 = fma(__ldg(Wt + (size_t)(k + 0) * N + j), h[k + 0], p0);
+    p1 = fma(__ldg(Wt + (size_t)(k + 1) * N + j), h[k + 1], p1);
+    p2 = fma(__ldg(Wt + (size_t)(k + 2) * N + j), h[k + 2], p2);
+    p3 = fma(__ldg(Wt + (size_t)(k + 3) * N + j), h[k + 3], p3);
+  }
+  for (; k < Kin; ++k) p0 = fma(__ldg(Wt + (size_t)k * N + j), h[k], p0);
+  return (p0 + p1) + (p2 + p3);
+}
+
+// Batched forward.  `hA` holds B z-scored inputs, sample s at hA + s*stride; hA/hB ping-pong.
+// Must be called by all `nthr` threads of the CTA (contains __syncthreads).  Returns the
+// buffer base holding the raw network outputs (sample s at ret + s*stride).
+__device__ __forceinline__ const double *ampc_mlp_f64_forward_batch(const AmpcMlpF64 &net, int B, double *hA,
+                                                                    double *hB, int stride, int tid, int nthr) {
+  double *hin = hA, *hout = hB;
+  for (int l = 0; l < net.n_layers; ++l) {
+    const int Kin = net.dims[l], N = net.dims[l + 1];
+    const bool last = (l == net.n_layers - 1);
+    for (int t = tid; t < B * N; t += nthr) {
+      const int s = t / N, j = t - s * N;
+      const double y = __ldg(net.b[l] + j) + ampc_dot_col(net.Wt[l], N, j, hin + (size_t)s * stride, Kin);
+      hout[(size_t)s * stride + j] = last ? y : ampc_act<double>(net.act, y);
+    }
+    __syncthreads();
+    double *t2 = hin; hin = hout; hout = t2;
+  }
+  return hin;
+}
+
+__device__ __forceinline__ const double *ampc_mlp_f64_forward(const AmpcMlpF64 &net, double *h0, double *h1,
+                                                              double *, int tid, int nthr) {
+  return ampc_mlp_f64_forward_batch(net, 1, h0, h1, net.max_width, tid, nthr);
+}
+
+// Batched forward + input Jacobian of the raw network output w.r.t. the RAW
+// (un-normalised) input, for m samples processed together by one CTA.
+// Sample s uses  h0/h1/g at  +s*hstride  and Jacobian panels J0/J1 at +s*jstride
+// (each panel max_width*nin).  On return *Jout (+s*jstride) is the panel
+// [n_out][nin] = W_L D_{L-1} ... D_1 W_1 diag(1/xu_std) and the returned buffer
+// (+s*hstride) holds the raw outputs.
+__device__ __forceinline__ const double *ampc_mlp_f64_forward_jac_batch(const AmpcMlpF64 &net, int m, double *h0,
+                                                                        double *h1, double *g, int hstride,
+                                                                        double *J0, double *J1, int jstride,
+                                                                        const double **Jout, int tid, int nthr) {
+  const int nin = net.dims[0];
+  double *hin = h0, *hout = h1, *Jp = J0, *Jn = J1;
+  for (int l = 0; l < net.n_layers; ++l) {
+    const int Kin = net.dims[l], N = net.dims[l + 1];
+    const bool last = (l == net.n_layers - 1);
+    for (int t = tid; t < m * N; t += nthr) {
+      const int s = t / N, j = t - s * N;
+      const double y = __ldg(net.b[l] + j) + ampc_dot_col(net.Wt[l], N, j, hin + (size_t)s * hstride, Kin);
+      hout[(size_t)s * hstride + j] = last ? y : ampc_act<double>(net.act, y);
+      g[(size_t)s * hstride + j] = last ? 1.0 : ampc_act_grad<double>(net.act, y);
+    }
+    __syncthreads();
+    const int per = N * nin;
+    for (int t = tid; t < m * per; t += nthr) {
+      const int s = t / per, r = t - s * per;
+      const int c = r / N, j = r - c * N;   // j fastest: coalesced weight reads
+      const double *jp = Jp + (size_t)s * jstride;
+      double v;
+      if (l == 0) {
+        v = __ldg(net.Wt[0] + (size_t)c * N + j) / __ldg(net.xu_std + c);
+      } else {
+        double p0 = 0.0, p1 = 0.0;
+        int k = 0;
+        for (; k + 2 <= Kin; k += 2) {
+          p0 = fma(__ldg(net.Wt[l] + (size_t)k * N + j), jp[(size_t)k * nin + c], p0);
+          p1 = fma(__ldg(net.Wt[l] + (size_t)(k + 1) * N + j), jp[(size_t)(k + 1) * nin + c], p1);
+        }
+        if (k < Kin) p0 = fma(__ldg(net.Wt[l] + (size_t)k * N + j), jp[(size_t)k * nin + c], p0);
+        v = p0 + p1;
+      }
+      Jn[(size_t)s * jstride + (size_t)j * nin + c] = v * g[(size_t)s * hstride + j];
+    }
+    __syncthreads();
+    double *t2 = hin; hin = hout; hout = t2;
+    double *t3 = Jp; Jp = Jn; Jn = t3;
+  }
+  *Jout = Jp;
+  return hin;
+}
+
+__device__ __forceinline__ const double *ampc_mlp_f64_forward_jac(const AmpcMlpF64 &net, double *h0, double *h1,
+                                                                  double *g, double *J0, double *J1,
+                                                                  const double **Jout, int tid, int nthr) {
+  return ampc_mlp_f64_forward_jac_batch(net, 1, h0, h1, g, net.max_width, J0, J1, net.max_width * net.dims[0], Jout,
+                                        tid, nthr);
+}

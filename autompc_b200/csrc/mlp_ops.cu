@@ -1,0 +1,191 @@
+// float64 MLP inference and batched Jacobians on the device.
+//
+// Replaces autompc.sysid.mlp.MLP.pred/pred_batch (autompc/sysid/mlp.py:219-236) and
+// pred_diff/pred_diff_batch (:238-305).  The reference network is float64
+// (mlp.py:165); these kernels keep float64 so results agree to rounding.  The
+// Jacobian is propagated forward through the layer stack,
+//   J_0 = W_0 diag(1/xu_std),  J_l = W_l (act'(pre_{l-1}) * J_{l-1}),  J = diag(dy_std) J_L,
+// which is the closed form of the reference's eye(nx) back-propagation.
+//
+// One CTA per sample; activations and the two Jacobian panels live in shared
+// memory; weights are stored in-major ([in][out]) so neighbouring threads read
+// neighbouring outputs.  The same device routines are reused by the iLQR kernel.
+#include <vector>
+
+#include "ampc_common.cuh"
+#include "mlp_f64.cuh"
+
+struct ampc_mlp {
+  AmpcMlpF64 net;
+  int device = 0;
+  double *d_blob = nullptr;
+  size_t smem_pred = 0, smem_diff = 0;
+};
+
+namespace {
+
+constexpr int NT = 128;
+
+__global__ void __launch_bounds__(NT) pred_batch_kernel(const AmpcMlpF64 net, int batch, const double *X,
+                                                        const double *U, double *Xn) {
+  extern __shared__ double sm_d[];
+  const int s = blockIdx.x;
+  if (s >= batch) return;
+  double *h0 = sm_d, *h1 = sm_d + net.max_width;
+  const int nx = net.nx, nu = net.nu;
+  for (int j = threadIdx.x; j < nx + nu; j += NT) {
+    const double v = j < nx ? X[(size_t)s * nx + j] : U[(size_t)s * nu + (j - nx)];
+    h0[j] = (v - net.xu_mean[j]) / net.xu_std[j];
+  }
+  __syncthreads();
+  const double *out = ampc_mlp_f64_forward(net, h0, h1, nullptr, threadIdx.x, NT);
+  for (int j = threadIdx.x; j < nx; j += NT)
+    Xn[(size_t)s * nx + j] = X[(size_t)s * nx + j] + (out[j] * net.dy_std[j] + net.dy_mean[j]);
+}
+
+__global__ void __launch_bounds__(NT) pred_diff_kernel(const AmpcMlpF64 net, int batch, const double *X,
+                                                       const double *U, double *Xn, double *Jx, double *Ju) {
+  extern __shared__ double sm_d[];
+  const int s = blockIdx.x;
+  if (s >= batch) return;
+  const int nx = net.nx, nu = net.nu, nin = nx + nu;
+  double *h0 = sm_d, *h1 = h0 + net.max_width, *g = h1 + net.max_width;
+  double *J0 = g + net.max_width, *J1 = J0 + (size_t)net.max_width * nin;
+  for (int j = threadIdx.x; j < nin; j += NT) {
+    const double v = j < nx ? X[(size_t)s * nx + j] : U[(size_t)s * nu + (j - nx)];
+    h0[j] = (v - net.xu_mean[j]) / net.xu_std[j];
+  }
+  __syncthreads();
+  const double *J;
+  const double *out = ampc_mlp_f64_forward_jac(net, h0, h1, g, J0, J1, &J, threadIdx.x, NT);
+  for (int j = threadIdx.x; j < nx; j += NT)
+    Xn[(size_t)s * nx + j] = X[(size_t)s * nx + j] + (out[j] * net.dy_std[j] + net.dy_mean[j]);
+  for (int t = threadIdx.x; t < nx * nin; t += NT) {
+    const int r = t / nin, c = t - r * nin;
+    const double v = J[t] * net.dy_std[r];                     // mlp.py:298
+    if (c < nx) Jx[((size_t)s * nx + r) * nx + c] = v + (r == c ? 1.0 : 0.0);   // mlp.py:303
+    else Ju[((size_t)s * nx + r) * nu + (c - nx)] = v;
+  }
+}
+
+}  // namespace
+
+int ampc_mlp_f64_upload(const ampc_mlp_desc *mlp, int nx, int nu, AmpcMlpF64 *net, double **blob_out) {
+  AMPC_REQUIRE(mlp && mlp->n_layers >= 2 && mlp->n_layers <= AMPC_MAX_LAYERS, AMPC_ERR_UNSUPPORTED,
+               "MLP must have 1..%d hidden layers", AMPC_MAX_LAYERS - 1);
+  AMPC_REQUIRE(mlp->dims[0] == nx + nu && mlp->dims[mlp->n_layers] == nx, AMPC_ERR_INVALID,
+               "MLP dims do not match nx+nu -> nx");
+  AMPC_REQUIRE(mlp->act >= 0 && mlp->act <= 3, AMPC_ERR_UNSUPPORTED, "unknown activation %d", mlp->act);
+  memset(net, 0, sizeof(*net));
+  net->n_layers = mlp->n_layers;
+  net->act = mlp->act;
+  net->nx = nx;
+  net->nu = nu;
+  size_t off = 0;
+  size_t woff[AMPC_MAX_LAYERS], boff[AMPC_MAX_LAYERS];
+  for (int l = 0; l <= mlp->n_layers; ++l) {
+    net->dims[l] = mlp->dims[l];
+    AMPC_REQUIRE(mlp->dims[l] >= 1 && mlp->dims[l] <= AMPC_MAX_WIDTH, AMPC_ERR_UNSUPPORTED, "layer width %d",
+                 mlp->dims[l]);
+    if (mlp->dims[l] > net->max_width) net->max_width = mlp->dims[l];
+  }
+  for (int l = 0; l < mlp->n_layers; ++l) {
+    woff[l] = off; off += (size_t)mlp->dims[l] * mlp->dims[l + 1];
+    boff[l] = off; off += mlp->dims[l + 1];
+  }
+  const size_t o_xm = off; off += nx + nu;
+  const size_t o_xs = off; off += nx + nu;
+  const size_t o_dm = off; off += nx;
+  const size_t o_ds = off; off += nx;
+  std::vector<double> hb(off);
+  for (int l = 0; l < mlp->n_layers; ++l) {
+    const int Kin = mlp->dims[l], N = mlp->dims[l + 1];
+    for (int k = 0; k < Kin; ++k)
+      for (int j = 0; j < N; ++j) hb[woff[l] + (size_t)k * N + j] = mlp->W[l][(size_t)j * Kin + k];
+    for (int j = 0; j < N; ++j) hb[boff[l] + j] = mlp->b[l][j];
+  }
+  for (int j = 0; j < nx + nu; ++j) {
+    AMPC_REQUIRE(mlp->xu_std[j] != 0.0, AMPC_ERR_INVALID, "xu_std[%d] == 0", j);
+    hb[o_xm + j] = mlp->xu_mean[j];
+    hb[o_xs + j] = mlp->xu_std[j];
+  }
+  for (int j = 0; j < nx; ++j) { hb[o_dm + j] = mlp->dy_mean[j]; hb[o_ds + j] = mlp->dy_std[j]; }
+  double *d = nullptr;
+  AMPC_CUDA_CHECK(cudaMalloc(&d, off * sizeof(double)));
+  cudaError_t e = cudaMemcpy(d, hb.data(), off * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d); AMPC_CUDA_CHECK(e); }
+  for (int l = 0; l < mlp->n_layers; ++l) { net->Wt[l] = d + woff[l]; net->b[l] = d + boff[l]; }
+  net->xu_mean = d + o_xm; net->xu_std = d + o_xs; net->dy_mean = d + o_dm; net->dy_std = d + o_ds;
+  *blob_out = d;
+  return AMPC_OK;
+}
+
+extern "C" int ampc_mlp_create(ampc_mlp **out, const ampc_mlp_desc *mlp, int32_t nx, int32_t nu, int32_t device) {
+  AMPC_REQUIRE(out, AMPC_ERR_INVALID, "null out");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  AMPC_REQUIRE(ce == cudaSuccess && ndev > 0, AMPC_ERR_CUDA, "no CUDA device: libampc_b200 has no CPU fallback (%s)",
+               cudaGetErrorString(ce));
+  AMPC_REQUIRE(device >= 0 && device < ndev, AMPC_ERR_INVALID, "device %d of %d", device, ndev);
+  AMPC_CUDA_CHECK(cudaSetDevice(device));
+  ampc_mlp *m = new ampc_mlp();
+  m->device = device;
+  int rc = ampc_mlp_f64_upload(mlp, nx, nu, &m->net, &m->d_blob);
+  if (rc) { delete m; return rc; }
+  m->smem_pred = 2 * (size_t)m->net.max_width * sizeof(double);
+  m->smem_diff = (3 * (size_t)m->net.max_width + 2 * (size_t)m->net.max_width * (nx + nu)) * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(pred_diff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_diff);
+  if (e != cudaSuccess) {
+    ampc_set_error("pred_diff kernel needs %zu B shared memory: %s", m->smem_diff, cudaGetErrorString(e));
+    cudaFree(m->d_blob);
+    delete m;
+    return AMPC_ERR_UNSUPPORTED;
+  }
+  *out = m;
+  return AMPC_OK;
+}
+
+extern "C" int ampc_mlp_destroy(ampc_mlp *m) {
+  if (!m) return AMPC_OK;
+  cudaSetDevice(m->device);
+  cudaFree(m->d_blob);
+  delete m;
+  return AMPC_OK;
+}
+
+static int run_mlp(ampc_mlp *m, int batch, const double *X, const double *U, double *Xn, double *Jx, double *Ju) {
+  AMPC_REQUIRE(m && X && U && Xn && batch >= 0, AMPC_ERR_INVALID, "bad argument");
+  if (batch == 0) return AMPC_OK;
+  AMPC_CUDA_CHECK(cudaSetDevice(m->device));
+  const int nx = m->net.nx, nu = m->net.nu;
+  const size_t nX = (size_t)batch * nx, nU = (size_t)batch * nu;
+  const size_t nJx = Jx ? nX * nx : 0, nJu = Jx ? nX * nu : 0;
+  double *d = nullptr;
+  AMPC_CUDA_CHECK(cudaMalloc(&d, (2 * nX + nU + nJx + nJu) * sizeof(double)));
+  double *dX = d, *dU = dX + nX, *dXn = dU + nU, *dJx = dXn + nX, *dJu = dJx + nJx;
+  cudaError_t e = cudaMemcpy(dX, X, nX * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dU, U, nU * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    if (Jx) pred_diff_kernel<<<batch, NT, m->smem_diff>>>(m->net, batch, dX, dU, dXn, dJx, dJu);
+    else pred_batch_kernel<<<batch, NT, m->smem_pred>>>(m->net, batch, dX, dU, dXn);
+    ampc_count_launch();
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(Xn, dXn, nX * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && Jx) e = cudaMemcpy(Jx, dJx, nJx * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && Jx) e = cudaMemcpy(Ju, dJu, nJu * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  AMPC_CUDA_CHECK(e);
+  return AMPC_OK;
+}
+
+extern "C" int ampc_mlp_pred_batch(ampc_mlp *m, int32_t batch, const double *X, const double *U, double *Xn) {
+  return run_mlp(m, batch, X, U, Xn, nullptr, nullptr);
+}
+
+extern "C" int ampc_mlp_pred_diff_batch(ampc_mlp *m, int32_t batch, const double *X, const double *U, double *Xn,
+                                        double *Jx, double *Ju) {
+  AMPC_REQUIRE(Jx && Ju, AMPC_ERR_INVALID, "null Jacobian output");
+  return run_mlp(m, batch, X, U, Xn, Jx, Ju);
+}

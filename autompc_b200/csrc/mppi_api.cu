@@ -1,0 +1,419 @@
+// C ABI for the MPPI solve: handle, weight packing, solve / merge / parity taps.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "ampc_common.cuh"
+
+// ------------------------------------------------------------ error plumbing ---
+static thread_local char g_err[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void ampc_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void ampc_count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+extern "C" const char *ampc_last_error(void) { return g_err; }
+extern "C" const char *ampc_version(void) { return "ampc_b200 0.1 (sm_100a)"; }
+extern "C" uint64_t ampc_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------ kernels implemented elsewhere ---
+int ampc_mppi_fp32_configure(const AmpcMppiParams &p, bool *resident_out, size_t *smem_out);
+int ampc_mppi_fp32_launch(const AmpcMppiParams &p, bool resident, size_t smem, cudaStream_t stream);
+int ampc_mppi_fp32_grid(const AmpcMppiParams &p);
+
+struct AmpcTcPlan;  // tcgen05 path (mppi_tc.cu)
+int ampc_mppi_tc_supported(const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp, const char **why);
+int ampc_mppi_tc_create(AmpcTcPlan **plan, const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp);
+void ampc_mppi_tc_destroy(AmpcTcPlan *plan);
+int ampc_mppi_tc_grid(const AmpcTcPlan *plan);
+int ampc_mppi_tc_launch(AmpcTcPlan *plan, const AmpcMppiParams &p, cudaStream_t stream);
+
+// ------------------------------------------------------------------- handle ---
+struct ampc_mppi {
+  ampc_mppi_cfg cfg;
+  AmpcMppiParams p;         // template, per-solve fields filled at launch
+  int device = 0;
+  int HN = 0;
+  int n_partials = 0;
+  bool resident = false;
+  size_t smem = 0;
+  AmpcTcPlan *tc = nullptr;
+  cudaStream_t stream = nullptr;   // used by the *_host entry points
+  float *d_wpack = nullptr, *d_consts = nullptr, *d_act = nullptr, *d_costs = nullptr, *d_term = nullptr;
+  float *d_partials = nullptr, *d_x0 = nullptr, *d_u = nullptr, *d_eps = nullptr;
+  unsigned int *d_ticket = nullptr;
+  float *h_pin = nullptr;          // pinned staging: x0 (nx) | u (nu)
+  float *h_eps = nullptr;          // pinned staging for external eps (lazily)
+  size_t eps_elems = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+int pow2ceil(int v) {
+  int r = 1;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+bool is_diag(const double *M, int n) {
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j)
+      if (i != j && M[i * n + j] != 0.0) return false;
+  return true;
+}
+
+__global__ void merge_kernel(const float *recs, int n_recs, int H, int nu, float inv_lmda, const float *scale,
+                             float *act_seq, float *u_out) {
+  extern __shared__ float sm[];
+  float *s_act = sm;                                   // H*nu shifted
+  float *s_scratch = sm + ((H * nu + 3) & ~3);
+  const int HN = H * nu;
+  for (int e = threadIdx.x; e < HN; e += blockDim.x) {
+    const int i = e / nu, j = e - i * nu;
+    const int src = (i + 1 < H) ? i + 1 : H - 1;
+    s_act[e] = act_seq[src * nu + j];
+  }
+  __syncthreads();
+  ampc_merge_records(recs, n_recs, 2 + HN, HN, nu, inv_lmda, s_act, scale, act_seq, u_out, nullptr, s_scratch);
+}
+
+__global__ void noise_kernel(float *eps, int H, int K, int nu, int k_offset, float sqrt_sigma, uint64_t seed,
+                             uint64_t ctr) {
+  const int nblk = (nu + 3) >> 2;
+  const long long total = (long long)H * K * nblk;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int blk = (int)(t % nblk);
+    const long long r = t / nblk;
+    const int k = (int)(r % K), i = (int)(r / K);
+    float n4[4];
+    ampc_normal4(seed, ctr, (uint32_t)(k_offset + k), (uint32_t)i, (uint32_t)blk, n4);
+    for (int q = 0; q < 4; ++q) {
+      const int j = blk * 4 + q;
+      if (j < nu) eps[((size_t)i * K + k) * nu + j] = n4[q] * sqrt_sigma;
+    }
+  }
+}
+
+int validate(const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp, const ampc_quad_cost *cost) {
+  AMPC_REQUIRE(cfg && mlp && cost, AMPC_ERR_INVALID, "null argument");
+  AMPC_REQUIRE(cfg->K >= 1 && cfg->H >= 2 && cfg->H < 65536, AMPC_ERR_INVALID,
+               "need num_path >= 1 and 2 <= horizon < 65536 (got K=%d H=%d)", cfg->K, cfg->H);
+  AMPC_REQUIRE(cfg->nx >= 1 && cfg->nu >= 1 && cfg->nx + cfg->nu <= AMPC_MAX_WIDTH, AMPC_ERR_INVALID,
+               "bad dims nx=%d nu=%d", cfg->nx, cfg->nu);
+  AMPC_REQUIRE(cfg->sigma > 0 && cfg->lmda > 0, AMPC_ERR_INVALID, "sigma and lmda must be > 0");
+  AMPC_REQUIRE(cfg->terminal_mode == 0 || cfg->terminal_mode == 1, AMPC_ERR_INVALID, "terminal_mode");
+  AMPC_REQUIRE(cfg->k_offset >= 0 && cfg->K_global >= cfg->k_offset + cfg->K, AMPC_ERR_INVALID,
+               "shard [%d,%d) outside K_global=%d", cfg->k_offset, cfg->k_offset + cfg->K, cfg->K_global);
+  AMPC_REQUIRE(mlp->n_layers >= 2 && mlp->n_layers <= AMPC_MAX_LAYERS, AMPC_ERR_UNSUPPORTED,
+               "MLP must have 1..%d hidden layers (got n_layers=%d)", AMPC_MAX_LAYERS - 1, mlp->n_layers);
+  AMPC_REQUIRE(mlp->dims[0] == cfg->nx + cfg->nu && mlp->dims[mlp->n_layers] == cfg->nx, AMPC_ERR_INVALID,
+               "MLP dims do not match nx+nu -> nx");
+  for (int l = 1; l < mlp->n_layers; ++l)
+    AMPC_REQUIRE(mlp->dims[l] >= 1 && mlp->dims[l] <= AMPC_MAX_WIDTH, AMPC_ERR_UNSUPPORTED,
+                 "hidden width %d outside 1..%d", mlp->dims[l], AMPC_MAX_WIDTH);
+  AMPC_REQUIRE(mlp->act >= 0 && mlp->act <= 3, AMPC_ERR_UNSUPPORTED, "unknown activation %d", mlp->act);
+  for (int j = 0; j < cfg->nu; ++j)
+    AMPC_REQUIRE(isfinite(cost->umin[j]) && isfinite(cost->umax[j]) && cost->umax[j] > 0 &&
+                     cost->umin[j] <= cost->umax[j],
+                 AMPC_ERR_INVALID,
+                 "control %d: MPPI needs finite bounds with umax > 0 (controls are normalised by umax, "
+                 "mppi.py:100-102); got [%g, %g]", j, cost->umin[j], cost->umax[j]);
+  for (int j = 0; j < cfg->nx + cfg->nu; ++j)
+    AMPC_REQUIRE(mlp->xu_std[j] != 0.0, AMPC_ERR_INVALID, "xu_std[%d] == 0", j);
+  return AMPC_OK;
+}
+
+void free_handle(ampc_mppi *h) {
+  if (!h) return;
+  DeviceGuard g(h->device);
+  if (h->tc) ampc_mppi_tc_destroy(h->tc);
+  cudaFree(h->d_wpack); cudaFree(h->d_consts); cudaFree(h->d_act); cudaFree(h->d_costs); cudaFree(h->d_term);
+  cudaFree(h->d_partials); cudaFree(h->d_x0); cudaFree(h->d_u); cudaFree(h->d_eps); cudaFree(h->d_ticket);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  if (h->h_eps) cudaFreeHost(h->h_eps);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int launch_rollout(ampc_mppi *h, const float *dev_x0, const float *dev_eps, uint64_t seed, uint64_t counter,
+                   float *dev_u, float *dev_record, cudaStream_t stream) {
+  AmpcMppiParams p = h->p;
+  p.x0 = dev_x0;
+  p.eps = dev_eps;
+  p.seed = seed;
+  p.ctr = counter;
+  p.u_out = dev_u;
+  p.record_out = dev_record;
+  if (h->tc) return ampc_mppi_tc_launch(h->tc, p, stream);
+  return ampc_mppi_fp32_launch(p, h->resident, h->smem, stream);
+}
+
+}  // namespace
+
+extern "C" int ampc_mppi_create(ampc_mppi **out, const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp,
+                                const ampc_quad_cost *cost) {
+  AMPC_REQUIRE(out, AMPC_ERR_INVALID, "null out");
+  *out = nullptr;
+  int rc = validate(cfg, mlp, cost);
+  if (rc) return rc;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  AMPC_REQUIRE(ce == cudaSuccess && ndev > 0, AMPC_ERR_CUDA,
+               "no CUDA device: libampc_b200 has no CPU fallback (%s)", cudaGetErrorString(ce));
+  AMPC_REQUIRE(cfg->device >= 0 && cfg->device < ndev, AMPC_ERR_INVALID, "device %d of %d", cfg->device, ndev);
+  DeviceGuard g(cfg->device);
+  cudaDeviceProp prop;
+  AMPC_CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+  AMPC_REQUIRE(prop.major == 10, AMPC_ERR_UNSUPPORTED,
+               "libampc_b200 is built for sm_100a only; device %d is sm_%d%d", cfg->device, prop.major, prop.minor);
+
+  ampc_mppi *h = new ampc_mppi();
+  h->cfg = *cfg;
+  h->device = cfg->device;
+  const int nx = cfg->nx, nu = cfg->nu, H = cfg->H, K = cfg->K;
+  h->HN = H * nu;
+  AmpcMppiParams &p = h->p;
+  memset(&p, 0, sizeof(p));
+  p.K = K; p.H = H; p.nx = nx; p.nu = nu;
+  p.k_offset = cfg->k_offset; p.K_global = cfg->K_global;
+  p.terminal_mode = cfg->terminal_mode;
+  p.q_diag = is_diag(cost->Q, nx);
+  p.f_diag = is_diag(cost->F, nx);
+  p.act = mlp->act;
+  p.n_layers = mlp->n_layers;
+  p.max_width = 0;
+  for (int l = 0; l <= mlp->n_layers; ++l) {
+    p.dims[l] = mlp->dims[l];
+    if (mlp->dims[l] > p.max_width) p.max_width = mlp->dims[l];
+  }
+  p.inv_lmda = (float)(1.0 / cfg->lmda);
+  p.sqrt_sigma = (float)sqrt(cfg->sigma);
+  p.lam_over_sigma = (float)(cfg->lmda / cfg->sigma);
+
+  // constants block
+  const AmpcConstLayout cl(nx, nu);
+  std::vector<float> hc(cl.total, 0.f);
+  for (int j = 0; j < nx + nu; ++j) {
+    hc[cl.xu_mean + j] = (float)mlp->xu_mean[j];
+    hc[cl.xu_inv + j] = (float)(1.0 / mlp->xu_std[j]);
+  }
+  for (int j = 0; j < nx; ++j) {
+    hc[cl.dy_mean + j] = (float)mlp->dy_mean[j];
+    hc[cl.dy_std + j] = (float)mlp->dy_std[j];
+    hc[cl.goal + j] = (float)cost->goal[j];
+  }
+  for (int i = 0; i < nx * nx; ++i) { hc[cl.Q + i] = (float)cost->Q[i]; hc[cl.F + i] = (float)cost->F[i]; }
+  for (int i = 0; i < nu * nu; ++i) hc[cl.R + i] = (float)cost->R[i];
+  for (int j = 0; j < nu; ++j) {   // mppi.py:100-102, :137-138 (ctrl_scale = umax)
+    hc[cl.lo + j] = (float)(cost->umin[j] / cost->umax[j]);
+    hc[cl.hi + j] = (float)(cost->umax[j] / cost->umax[j]);
+    hc[cl.scale + j] = (float)cost->umax[j];
+  }
+
+#define AMPC_CREATE_CHECK(expr)                                                                   \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      ampc_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__,      \
+                     cudaGetErrorString(_e));                                                     \
+      free_handle(h);                                                                             \
+      return AMPC_ERR_CUDA;                                                                       \
+    }                                                                                             \
+  } while (0)
+
+  AMPC_CREATE_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  AMPC_CREATE_CHECK(cudaMalloc(&h->d_consts, cl.total * sizeof(float)));
+  AMPC_CREATE_CHECK(cudaMemcpy(h->d_consts, hc.data(), cl.total * sizeof(float), cudaMemcpyHostToDevice));
+  AMPC_CREATE_CHECK(cudaMalloc(&h->d_act, h->HN * sizeof(float)));
+  AMPC_CREATE_CHECK(cudaMemset(h->d_act, 0, h->HN * sizeof(float)));
+  AMPC_CREATE_CHECK(cudaMalloc(&h->d_costs, (size_t)K * sizeof(float)));
+  AMPC_CREATE_CHECK(cudaMalloc(&h->d_term, sizeof(float)));
+  AMPC_CREATE_CHECK(cudaMemset(h->d_term, 0, sizeof(float)));
+  AMPC_CREATE_CHECK(cudaMalloc(&h->d_x0, nx * sizeof(float)));
+  AMPC_CREATE_CHECK(cudaMalloc(&h->d_u, nu * sizeof(float)));
+  AMPC_CREATE_CHECK(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
+  AMPC_CREATE_CHECK(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
+  AMPC_CREATE_CHECK(cudaMallocHost(&h->h_pin, (nx + nu) * sizeof(float)));
+  p.consts = h->d_consts; p.act_seq = h->d_act; p.costs = h->d_costs; p.term_out = h->d_term;
+  p.ticket = h->d_ticket;
+
+  if (cfg->precision == AMPC_PREC_BF16) {
+    const char *why = "";
+    if (!ampc_mppi_tc_supported(cfg, mlp, &why)) {
+      ampc_set_error("precision=bf16 (tcgen05) does not support this problem: %s", why);
+      free_handle(h);
+      return AMPC_ERR_UNSUPPORTED;
+    }
+    rc = ampc_mppi_tc_create(&h->tc, cfg, mlp);
+    if (rc) { free_handle(h); return rc; }
+    h->n_partials = ampc_mppi_tc_grid(h->tc);
+  } else if (cfg->precision == AMPC_PREC_FP32) {
+    // fp32 pack: per layer Wt[k][8*npt] (in-major, zero padded) then bias[8*npt]
+    int off = 0;
+    for (int l = 0; l < mlp->n_layers; ++l) {
+      const int N = mlp->dims[l + 1], Kin = mlp->dims[l];
+      int npt = pow2ceil((N + 7) / 8);
+      if (npt == 0) npt = 1;
+      p.npt[l] = npt;
+      p.woff[l] = off; off += Kin * 8 * npt;
+      p.boff[l] = off; off += 8 * npt;
+      off = (off + 3) & ~3;
+    }
+    p.wpack_floats = off;
+    std::vector<float> hw(off, 0.f);
+    for (int l = 0; l < mlp->n_layers; ++l) {
+      const int N = mlp->dims[l + 1], Kin = mlp->dims[l], NP = 8 * p.npt[l];
+      for (int k = 0; k < Kin; ++k)
+        for (int j = 0; j < N; ++j) hw[p.woff[l] + k * NP + j] = (float)mlp->W[l][(size_t)j * Kin + k];
+      for (int j = 0; j < N; ++j) hw[p.boff[l] + j] = (float)mlp->b[l][j];
+    }
+    AMPC_CREATE_CHECK(cudaMalloc(&h->d_wpack, off * sizeof(float)));
+    AMPC_CREATE_CHECK(cudaMemcpy(h->d_wpack, hw.data(), off * sizeof(float), cudaMemcpyHostToDevice));
+    p.wpack = h->d_wpack;
+    rc = ampc_mppi_fp32_configure(p, &h->resident, &h->smem);
+    if (rc) { free_handle(h); return rc; }
+    h->n_partials = ampc_mppi_fp32_grid(p);
+  } else {
+    ampc_set_error("unknown precision %d", cfg->precision);
+    free_handle(h);
+    return AMPC_ERR_INVALID;
+  }
+  AMPC_CREATE_CHECK(cudaMalloc(&h->d_partials, (size_t)h->n_partials * (2 + h->HN) * sizeof(float)));
+  p.partials = h->d_partials;
+  *out = h;
+  return AMPC_OK;
+}
+
+extern "C" int ampc_mppi_destroy(ampc_mppi *h) {
+  free_handle(h);
+  return AMPC_OK;
+}
+
+extern "C" int ampc_mppi_set_act_seq(ampc_mppi *h, const double *host_act) {
+  AMPC_REQUIRE(h && host_act, AMPC_ERR_INVALID, "null argument");
+  DeviceGuard g(h->device);
+  std::vector<float> t(h->HN);
+  for (int i = 0; i < h->HN; ++i) t[i] = (float)host_act[i];
+  AMPC_CUDA_CHECK(cudaMemcpy(h->d_act, t.data(), h->HN * sizeof(float), cudaMemcpyHostToDevice));
+  return AMPC_OK;
+}
+
+extern "C" int ampc_mppi_get_act_seq(ampc_mppi *h, double *host_act) {
+  AMPC_REQUIRE(h && host_act, AMPC_ERR_INVALID, "null argument");
+  DeviceGuard g(h->device);
+  std::vector<float> t(h->HN);
+  AMPC_CUDA_CHECK(cudaDeviceSynchronize());
+  AMPC_CUDA_CHECK(cudaMemcpy(t.data(), h->d_act, h->HN * sizeof(float), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < h->HN; ++i) host_act[i] = t[i];
+  return AMPC_OK;
+}
+
+extern "C" int ampc_mppi_solve(ampc_mppi *h, const float *dev_x0, const float *dev_eps, uint64_t seed,
+                               uint64_t counter, float *dev_u, void *stream) {
+  AMPC_REQUIRE(h && dev_x0 && dev_u, AMPC_ERR_INVALID, "null argument");
+  DeviceGuard g(h->device);
+  return launch_rollout(h, dev_x0, dev_eps, seed, counter, dev_u, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int ampc_mppi_solve_host(ampc_mppi *h, const double *host_x0, const double *host_eps, uint64_t seed,
+                                    uint64_t counter, double *host_u) {
+  AMPC_REQUIRE(h && host_x0 && host_u, AMPC_ERR_INVALID, "null argument");
+  DeviceGuard g(h->device);
+  const int nx = h->cfg.nx, nu = h->cfg.nu;
+  for (int j = 0; j < nx; ++j) h->h_pin[j] = (float)host_x0[j];
+  AMPC_CUDA_CHECK(cudaMemcpyAsync(h->d_x0, h->h_pin, nx * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  const float *d_eps = nullptr;
+  if (host_eps) {
+    const size_t n = (size_t)h->cfg.H * h->cfg.K * nu;
+    if (h->eps_elems < n) {
+      if (h->h_eps) cudaFreeHost(h->h_eps);
+      cudaFree(h->d_eps);
+      h->h_eps = nullptr; h->d_eps = nullptr; h->eps_elems = 0;
+      AMPC_CUDA_CHECK(cudaMallocHost(&h->h_eps, n * sizeof(float)));
+      AMPC_CUDA_CHECK(cudaMalloc(&h->d_eps, n * sizeof(float)));
+      h->eps_elems = n;
+    }
+    for (size_t i = 0; i < n; ++i) h->h_eps[i] = (float)host_eps[i];
+    AMPC_CUDA_CHECK(cudaMemcpyAsync(h->d_eps, h->h_eps, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    d_eps = h->d_eps;
+  }
+  int rc = launch_rollout(h, h->d_x0, d_eps, seed, counter, h->d_u, nullptr, h->stream);
+  if (rc) return rc;
+  AMPC_CUDA_CHECK(cudaMemcpyAsync(h->h_pin + nx, h->d_u, nu * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  AMPC_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  for (int j = 0; j < nu; ++j) host_u[j] = h->h_pin[nx + j];
+  return AMPC_OK;
+}
+
+extern "C" int ampc_mppi_get_costs(ampc_mppi *h, double *host_costs, double *term_const) {
+  AMPC_REQUIRE(h && host_costs, AMPC_ERR_INVALID, "null argument");
+  DeviceGuard g(h->device);
+  std::vector<float> t(h->cfg.K);
+  float term = 0.f;
+  AMPC_CUDA_CHECK(cudaDeviceSynchronize());
+  AMPC_CUDA_CHECK(cudaMemcpy(t.data(), h->d_costs, (size_t)h->cfg.K * sizeof(float), cudaMemcpyDeviceToHost));
+  AMPC_CUDA_CHECK(cudaMemcpy(&term, h->d_term, sizeof(float), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < h->cfg.K; ++i) host_costs[i] = t[i];
+  if (term_const) *term_const = term;
+  return AMPC_OK;
+}
+
+extern "C" int ampc_mppi_get_noise(ampc_mppi *h, uint64_t seed, uint64_t counter, float *host_eps) {
+  AMPC_REQUIRE(h && host_eps, AMPC_ERR_INVALID, "null argument");
+  DeviceGuard g(h->device);
+  const size_t n = (size_t)h->cfg.H * h->cfg.K * h->cfg.nu;
+  float *d = nullptr;
+  AMPC_CUDA_CHECK(cudaMalloc(&d, n * sizeof(float)));
+  noise_kernel<<<296, 256, 0, h->stream>>>(d, h->cfg.H, h->cfg.K, h->cfg.nu, h->cfg.k_offset, h->p.sqrt_sigma,
+                                           seed, counter);
+  ampc_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host_eps, d, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  AMPC_CUDA_CHECK(e);
+  return AMPC_OK;
+}
+
+extern "C" int ampc_mppi_record_floats(const ampc_mppi *h) { return h ? 2 + h->HN : 0; }
+
+extern "C" int ampc_mppi_rollout_partial(ampc_mppi *h, const float *dev_x0, const float *dev_eps, uint64_t seed,
+                                         uint64_t counter, float *dev_record, void *stream) {
+  AMPC_REQUIRE(h && dev_x0 && dev_record, AMPC_ERR_INVALID, "null argument");
+  DeviceGuard g(h->device);
+  return launch_rollout(h, dev_x0, dev_eps, seed, counter, h->d_u, dev_record, (cudaStream_t)stream);
+}
+
+extern "C" int ampc_mppi_merge(ampc_mppi *h, const float *dev_records, int32_t n_records, float *dev_u,
+                               void *stream) {
+  AMPC_REQUIRE(h && dev_records && dev_u && n_records >= 1, AMPC_ERR_INVALID, "bad argument");
+  DeviceGuard g(h->device);
+  const AmpcConstLayout cl(h->cfg.nx, h->cfg.nu);
+  const size_t smem = (((h->HN + 3) & ~3) + 64 + AMPC_MERGE_CACHE) * sizeof(float);
+  merge_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(dev_records, n_records, h->cfg.H, h->cfg.nu, h->p.inv_lmda,
+                                                       h->d_consts + cl.scale, h->d_act, dev_u);
+  ampc_count_launch();
+  AMPC_CUDA_CHECK(cudaGetLastError());
+  return AMPC_OK;
+}

@@ -1,0 +1,264 @@
+"""MPPI controller on the B200 engine -- drop-in for ``autompc.control.mppi.MPPI``.
+
+Same construction contract (``Controller(system, task, model, **hyperparams)``,
+``autompc/control/controller.py:30-33``), same hyper-parameter names
+(``horizon``, ``sigma``, ``lmda``, ``num_path``, ``seed``, ``niter``;
+``autompc/control/mppi.py:87-94``), same ``run`` / ``reset`` / ``traj_to_state``
+/ ``state_dim`` behaviour (``mppi.py:107-108``, ``:154-176``).  One ``run`` is
+one CUDA launch (shift + K rollouts + softmax update) through the C ABI.
+
+Engine-only keyword arguments (all optional):
+
+``noise``      ``"philox"`` (default; in-kernel Philox4x32-10 keyed by
+               ``(seed, cur_step, sample, step)``) or ``"numpy"`` (parity mode:
+               the noise is drawn on the host from the global NumPy stream in
+               exactly the reference's order, ``mppi.py:126``, and uploaded).
+``precision``  ``"fp32"`` | ``"bf16"`` | ``"auto"`` (bf16 tcgen05 kernel when the
+               MLP shape allows it, else fp32).
+``terminal``   ``"reference"`` (default: last sample's terminal cost added to
+               all samples, ``mppi.py:79-82``) or ``"per_sample"``.
+``device``     CUDA ordinal.
+``group``      a ``torch.distributed`` process group: samples are sharded over
+               its ranks and one all-gather of the softmax partial record is
+               done per solve.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from .mlp import MLPWeights
+from .plugin import Controller, ControllerFactory
+
+
+def _quad_cost_of(task, nx, nu):
+    cost = task.get_cost()
+    try:
+        Q, R, F = cost.get_cost_matrices()
+        goal = cost.get_goal()
+    except Exception as e:
+        raise ValueError("the B200 MPPI engine supports quadratic costs only (QuadCost): %s" % e)
+    bounds = np.asarray(task.get_ctrl_bounds(), dtype=np.float64)
+    return _abi.QuadCostHolder(Q, R, F, goal, bounds[:, 0], bounds[:, 1], nx, nu)
+
+
+class MPPI(Controller):
+    def __init__(self, system, task, model, **kwargs):
+        super().__init__(system, task, model)
+        self.kwargs = kwargs
+        self.dim_state, self.dim_ctrl = model.state_dim, system.ctrl_dim
+        self.seed = int(kwargs.get("seed", 0))
+        self.H = int(kwargs.get("horizon", 20))
+        self.num_path = int(kwargs.get("num_path", 1000))
+        self.num_iter = kwargs.get("niter", 1)
+        self.sigma = float(kwargs.get("sigma", 1))
+        self.lmda = float(kwargs.get("lmda", 1.0))
+        self.noise = kwargs.get("noise", "philox")
+        if self.noise not in ("philox", "numpy"):
+            raise ValueError("noise must be 'philox' or 'numpy'")
+        precision = kwargs.get("precision", "auto")
+        terminal = kwargs.get("terminal", "reference")
+        if terminal not in ("reference", "per_sample"):
+            raise ValueError("terminal must be 'reference' or 'per_sample'")
+        self.device = int(kwargs.get("device", 0))
+        self.group = kwargs.get("group", None)
+        self.weights = MLPWeights.from_model(model)
+        nx, nu = self.weights.nx, self.weights.nu
+        if nx != system.obs_dim or nu != system.ctrl_dim:
+            raise ValueError("model dims do not match the system")
+        self.umin = np.asarray(task.get_ctrl_bounds(), dtype=np.float64)[:, 0]
+        self.umax = np.asarray(task.get_ctrl_bounds(), dtype=np.float64)[:, 1]
+        self.ctrl_scale = self.umax                                        # mppi.py:102
+        # --- sharding over ranks
+        self.world, self.rank = 1, 0
+        if self.group is not None:
+            import torch.distributed as dist
+            self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        base, rem = divmod(self.num_path, self.world)
+        self.K_local = base + (1 if self.rank < rem else 0)
+        self.k_offset = self.rank * base + min(self.rank, rem)
+        if self.K_local < 1:
+            raise ValueError("num_path=%d cannot be sharded over %d ranks" % (self.num_path, self.world))
+        # --- engine handle
+        self._mlp_holder = _abi.MlpDescHolder(self.weights)
+        self._cost_holder = _quad_cost_of(task, nx, nu)
+        lib = _abi.lib()
+        self._h = None
+        order = {"auto": ["bf16", "fp32"], "fp32": ["fp32"], "bf16": ["bf16"]}.get(precision)
+        if order is None:
+            raise ValueError("precision must be 'auto', 'fp32' or 'bf16'")
+        err = None
+        for prec in order:
+            cfg = _abi.MppiCfg(self.K_local, self.H, nx, nu, self.sigma, self.lmda,
+                               0 if terminal == "reference" else 1, _abi.PREC_CODES[prec], self.k_offset,
+                               self.num_path, self.device)
+            h = C.c_void_p()
+            rc = lib.ampc_mppi_create(C.byref(h), C.byref(cfg), C.byref(self._mlp_holder.desc),
+                                      C.byref(self._cost_holder.desc))
+            if rc == _abi.AMPC_OK:
+                self._h, self.precision = h, prec
+                break
+            err = rc
+            if not (precision == "auto" and rc == _abi.AMPC_ERR_UNSUPPORTED):
+                _abi.check(rc)
+        if self._h is None:
+            _abi.check(err)
+        self._dev_bufs = None
+        self._init_act_sequence()
+
+    def _init_act_sequence(self):
+        # mppi.py:97-99 -- N(0, sqrt(sigma)) draw from the global NumPy stream; trailing dim is
+        # ctrl_dim (the reference hard-codes 1, mppi.py:22, and only runs for ctrl_dim == 1).
+        self.cur_step = 0
+        self.niter = 1                                                     # mppi.py:105
+        act = np.random.normal(scale=np.sqrt(self.sigma), size=(self.H, self.dim_ctrl))
+        self._set_act(act)
+
+    # ------------------------------------------------------------------ engine access ---
+    def _set_act(self, act):
+        a = _abi.f64(act, (self.H, self.dim_ctrl))
+        _abi.check(_abi.lib().ampc_mppi_set_act_seq(self._h, _abi.dptr(a)))
+
+    @property
+    def act_sequence(self):
+        a = np.empty((self.H, self.dim_ctrl))
+        _abi.check(_abi.lib().ampc_mppi_get_act_seq(self._h, _abi.dptr(a)))
+        return a
+
+    @act_sequence.setter
+    def act_sequence(self, value):
+        self._set_act(value)
+
+    def last_costs(self):
+        """(costs (K_local,), terminal scalar) of the latest solve -- parity tap."""
+        c = np.empty(self.K_local)
+        t = C.c_double(0.0)
+        _abi.check(_abi.lib().ampc_mppi_get_costs(self._h, _abi.dptr(c), C.byref(t)))
+        return c, t.value
+
+    def philox_noise(self, counter=None):
+        """(H, K_local, nu) unclipped noise the Philox path uses for solve `counter`."""
+        counter = self.cur_step if counter is None else counter
+        e = np.empty((self.H, self.K_local, self.dim_ctrl), dtype=np.float32)
+        _abi.check(_abi.lib().ampc_mppi_get_noise(self._h, self.seed, counter,
+                                                  e.ctypes.data_as(C.POINTER(C.c_float))))
+        return e
+
+    def sample_numpy_noise(self):
+        """mppi.py:126: K*H*nu draws in C order over (K,H,nu), transposed to (H,K,nu)."""
+        eps = np.random.normal(scale=np.sqrt(self.sigma), size=(self.num_path, self.H, self.dim_ctrl))
+        eps = eps.transpose((1, 0, 2))
+        return np.ascontiguousarray(eps[:, self.k_offset:self.k_offset + self.K_local, :])
+
+    # ------------------------------------------------------------------ solve ---
+    def solve(self, x0, eps=None):
+        """One MPPI iteration from observation x0 (mppi.py:158-161); returns the scaled first action."""
+        x0 = _abi.f64(x0, (self.dim_state,))
+        if eps is None and self.noise == "numpy":
+            eps = self.sample_numpy_noise()
+        if self.world > 1:
+            u = self._solve_sharded(x0, eps)
+        else:
+            u = np.empty(self.dim_ctrl)
+            e_ptr = None
+            if eps is not None:
+                eps = _abi.f64(eps, (self.H, self.K_local, self.dim_ctrl))
+                e_ptr = _abi.dptr(eps)
+            _abi.check(_abi.lib().ampc_mppi_solve_host(self._h, _abi.dptr(x0), e_ptr, self.seed, self.cur_step,
+                                                       _abi.dptr(u)))
+        self.cur_step += 1
+        return u
+
+    def _solve_sharded(self, x0, eps):
+        import torch
+        import torch.distributed as dist
+        lib = _abi.lib()
+        dev = torch.device("cuda", self.device)
+        if self._dev_bufs is None:
+            nrec = lib.ampc_mppi_record_floats(self._h)
+            self._dev_bufs = dict(
+                x0=torch.empty(self.dim_state, dtype=torch.float32, device=dev),
+                u=torch.empty(self.dim_ctrl, dtype=torch.float32, device=dev),
+                rec=torch.empty(nrec, dtype=torch.float32, device=dev),
+                recs=torch.empty(self.world * nrec, dtype=torch.float32, device=dev),
+                x0_pin=torch.empty(self.dim_state, dtype=torch.float32).pin_memory(),
+                u_pin=torch.empty(self.dim_ctrl, dtype=torch.float32).pin_memory())
+        b = self._dev_bufs
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            b["x0_pin"].copy_(torch.from_numpy(x0).to(torch.float32))
+            b["x0"].copy_(b["x0_pin"], non_blocking=True)
+            e_ptr = None
+            if eps is not None:
+                e_dev = torch.from_numpy(np.ascontiguousarray(eps, dtype=np.float32)).to(dev)
+                e_ptr = e_dev.data_ptr()
+            _abi.check(lib.ampc_mppi_rollout_partial(self._h, b["x0"].data_ptr(), e_ptr, self.seed, self.cur_step,
+                                                     b["rec"].data_ptr(), stream))
+            dist.all_gather_into_tensor(b["recs"], b["rec"], group=self.group)
+            _abi.check(lib.ampc_mppi_merge(self._h, b["recs"].data_ptr(), self.world, b["u"].data_ptr(), stream))
+            b["u_pin"].copy_(b["u"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return b["u_pin"].numpy().astype(np.float64)
+
+    def solve_device(self, x0_dev, u_dev, eps_dev=None, stream=0):
+        """Asynchronous solve on device float32 tensors/pointers (no host round trip).
+        ``x0_dev`` / ``u_dev`` / ``eps_dev`` expose ``data_ptr()`` (torch tensors)."""
+        _abi.check(_abi.lib().ampc_mppi_solve(self._h, x0_dev.data_ptr(),
+                                              None if eps_dev is None else eps_dev.data_ptr(), self.seed,
+                                              self.cur_step, u_dev.data_ptr(), stream))
+        self.cur_step += 1
+
+    # ------------------------------------------------------------------ Controller API ---
+    def run(self, constate, new_obs):                                      # mppi.py:154-168
+        nu = self.system.ctrl_dim
+        constate = np.asarray(constate)
+        x0 = self.model.update_state(constate[:-nu], constate[-nu:], np.asarray(new_obs, dtype=np.float64))
+        for _ in range(self.niter):
+            ret_action = self.solve(x0)
+        statenew = np.concatenate([x0, ret_action])
+        return ret_action, statenew
+
+    def reset(self):                                                       # mppi.py:107-108
+        self._init_act_sequence()
+
+    def traj_to_state(self, traj):                                         # mppi.py:170-172
+        return np.concatenate([self.model.traj_to_state(traj), traj[-1].ctrl])
+
+    @property
+    def state_dim(self):                                                   # mppi.py:174-176
+        return self.model.state_dim + self.system.ctrl_dim
+
+    @staticmethod
+    def is_compatible(system, task, model):                                # mppi.py:178-181
+        return True
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _abi.lib().ampc_mppi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MPPIFactory(ControllerFactory):
+    """Same hyper-parameters and ranges as ``autompc.control.mppi.MPPIFactory`` (mppi.py:26-64)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.Controller = MPPI
+        self.name = "MPPI"
+
+    def get_configuration_space(self):
+        import ConfigSpace as CS
+        import ConfigSpace.hyperparameters as CSH
+        cs = CS.ConfigurationSpace()
+        cs.add_hyperparameter(CSH.UniformIntegerHyperparameter(name="horizon", lower=5, upper=30, default_value=20))
+        cs.add_hyperparameter(CSH.UniformFloatHyperparameter(name="sigma", lower=1e-4, upper=2.0, default_value=1.0))
+        cs.add_hyperparameter(CSH.UniformFloatHyperparameter(name="lmda", lower=0.1, upper=2.0, default_value=1.0))
+        cs.add_hyperparameter(CSH.UniformIntegerHyperparameter(name="num_path", lower=100, upper=1000,
+                                                               default_value=200))
+        return cs

@@ -1,0 +1,184 @@
+/*
+ * ampc_b200.h -- C ABI of the B200-native MPC solve engine (libampc_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of williamedwards/autompc: the
+ * sampling / shooting MPC solve.  The reference has no FFI today (it is 100 %
+ * Python); each entry point below names the reference interface it replaces
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes
+ * binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - every function returns AMPC_OK (0) or a negative ampc_status; the message
+ *    for the calling thread's last failure is ampc_last_error();
+ *  - "host" pointers are plain CPU memory owned by the caller, float64 and
+ *    row-major exactly as the reference keeps them (NumPy / torch state_dict);
+ *  - "dev" pointers are CUDA device memory on the handle's device, owned by the
+ *    caller (e.g. torch.Tensor.data_ptr()); calls taking dev pointers are
+ *    asynchronous on the given cudaStream_t (passed as void*), calls taking
+ *    host pointers are synchronous;
+ *  - a handle is not thread-safe; distinct handles are independent;
+ *  - there is NO CPU fallback: without a CUDA device create() fails.
+ */
+#ifndef AMPC_B200_H
+#define AMPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ampc_status {
+  AMPC_OK = 0,
+  AMPC_ERR_INVALID = -1,     /* bad shape / argument            -> ValueError in the shim   */
+  AMPC_ERR_UNSUPPORTED = -2, /* model / size outside the engine -> ValueError in the shim   */
+  AMPC_ERR_CUDA = -3,        /* CUDA runtime failure            -> RuntimeError in the shim */
+  AMPC_ERR_NOMEM = -4
+} ampc_status;
+
+/* activation codes: torch.nn.{ReLU,Tanh,Sigmoid,SELU}, autompc/sysid/mlp.py:44-53 */
+enum { AMPC_ACT_RELU = 0, AMPC_ACT_TANH = 1, AMPC_ACT_SIGMOID = 2, AMPC_ACT_SELU = 3 };
+
+/* arithmetic of the MPPI rollout kernel */
+enum {
+  AMPC_PREC_FP32 = 0, /* CUDA-core fp32 FMA, any layer sizes <= 256                       */
+  AMPC_PREC_BF16 = 1  /* tcgen05 (UMMA) bf16 x bf16 -> fp32 in TMEM; state/cost stay fp32  */
+};
+
+#define AMPC_MAX_LAYERS 5 /* <= 4 hidden + output, autompc/sysid/mlp.py:110-111 */
+#define AMPC_MAX_WIDTH 256 /* hidden_size upper bound, autompc/sysid/mlp.py:112-119 */
+
+/* The learned dynamics: what autompc.sysid.mlp.MLP.get_parameters() holds
+ * (autompc/sysid/mlp.py:308-313).  All pointers are HOST float64.            */
+typedef struct ampc_mlp_desc {
+  int32_t n_layers;        /* hidden layers + output layer                                   */
+  const int32_t *dims;     /* n_layers+1 entries: [nx+nu, h_1, ..., h_L, nx]                 */
+  const double *const *W;  /* per layer, (out,in) row-major like torch.nn.Linear.weight      */
+  const double *const *b;  /* per layer, (out,)                                              */
+  int32_t act;             /* AMPC_ACT_*                                                     */
+  const double *xu_mean, *xu_std; /* (nx+nu,)  z-score of the input, mlp.py:20-24           */
+  const double *dy_mean, *dy_std; /* (nx,)     un-z-score of the output, mlp.py:26-30       */
+} ampc_mlp_desc;
+
+/* Quadratic cost (autompc/costs/quad_cost.py:7-51) and control box
+ * (autompc/tasks/task.py:257-267).  HOST float64, full matrices.              */
+typedef struct ampc_quad_cost {
+  const double *Q;    /* (nx,nx) */
+  const double *R;    /* (nu,nu) */
+  const double *F;    /* (nx,nx) */
+  const double *goal; /* (nx,)   */
+  const double *umin; /* (nu,)   */
+  const double *umax; /* (nu,)   must be finite and > 0: the reference normalises by umax, mppi.py:102 */
+} ampc_quad_cost;
+
+/* ------------------------------------------------------------------ MPPI --- */
+/* Replaces autompc.control.mppi.MPPI (autompc/control/mppi.py:66-181).         */
+typedef struct ampc_mppi_cfg {
+  int32_t K;             /* num_path owned by THIS handle (the local shard)                  */
+  int32_t H;             /* horizon (>= 2: mppi.py:123 indexes act_sequence[-2])             */
+  int32_t nx, nu;
+  double sigma;          /* noise VARIANCE (scale = sqrt(sigma), mppi.py:18)                  */
+  double lmda;
+  int32_t terminal_mode; /* 0 = reference: terminal cost of the LAST sample added to all
+                                samples (mppi.py:79-82,148) -- cancels in the softmax;
+                            1 = per-sample terminal cost (explicit non-reference option)      */
+  int32_t precision;     /* AMPC_PREC_*                                                       */
+  int32_t k_offset;      /* first global sample index of this shard (multi-GPU), else 0       */
+  int32_t K_global;      /* total samples over all shards, else K                             */
+  int32_t device;        /* CUDA device ordinal                                               */
+} ampc_mppi_cfg;
+
+typedef struct ampc_mppi ampc_mppi;
+
+/* MPPI.__init__ (mppi.py:67-105) minus the random act_sequence draw, which
+ * stays on the host (global NumPy stream) and is uploaded with set_act_seq.    */
+int ampc_mppi_create(ampc_mppi **out, const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp,
+                     const ampc_quad_cost *cost);
+int ampc_mppi_destroy(ampc_mppi *h);
+
+/* self.act_sequence (H,nu) float64, normalised controls (mppi.py:97-99).       */
+int ampc_mppi_set_act_seq(ampc_mppi *h, const double *host_act);
+int ampc_mppi_get_act_seq(ampc_mppi *h, double *host_act);
+
+/* One MPPI.run (mppi.py:154-168) = shift (:122-123) + K rollouts (:126-150) +
+ * update (:110-118), with HOST buffers: copies x0 in, u out, synchronises.
+ *   host_eps : NULL -> in-kernel Philox4x32-10 noise keyed by (seed, counter,
+ *              global sample, step);  else (H,K,nu) float64 UNCLIPPED noise
+ *              already scaled by sqrt(sigma) (what mppi.py:126 draws) --
+ *              the "external eps" parity mode.
+ *   host_u   : (nu,) = act_sequence[0] * umax after the update.                */
+int ampc_mppi_solve_host(ampc_mppi *h, const double *host_x0, const double *host_eps,
+                         uint64_t seed, uint64_t counter, double *host_u);
+
+/* Same solve with DEVICE float32 buffers, asynchronous on `stream`.
+ *   dev_eps: NULL or (H,K,nu) float32.                                         */
+int ampc_mppi_solve(ampc_mppi *h, const float *dev_x0, const float *dev_eps, uint64_t seed,
+                    uint64_t counter, float *dev_u, void *stream);
+
+/* Parity taps (synchronous).  costs: (K,) what do_rollouts returns (mppi.py:152)
+ * WITHOUT the terminal_mode-0 scalar, which is returned separately.            */
+int ampc_mppi_get_costs(ampc_mppi *h, double *host_costs, double *term_const);
+/* The exact unclipped noise the Philox path uses for (seed, counter): (H,K,nu). */
+int ampc_mppi_get_noise(ampc_mppi *h, uint64_t seed, uint64_t counter, float *host_eps);
+
+/* Multi-GPU (samples sharded over ranks).  rollout_partial
+ * writes this shard's softmax partial record
+ *     [ min cost m, sum_k exp(-(c_k-m)/lmda), sum_k exp(-(c_k-m)/lmda) * eps_k (H*nu) ]
+ * (ampc_mppi_record_floats() float32) to dev_record; after the ranks exchange
+ * records (one all-gather), merge applies mppi.py:115-118 on every rank.       */
+int ampc_mppi_record_floats(const ampc_mppi *h);
+int ampc_mppi_rollout_partial(ampc_mppi *h, const float *dev_x0, const float *dev_eps,
+                              uint64_t seed, uint64_t counter, float *dev_record, void *stream);
+int ampc_mppi_merge(ampc_mppi *h, const float *dev_records, int32_t n_records, float *dev_u,
+                    void *stream);
+
+/* ------------------------------------------------------- MLP model ops --- */
+/* Replaces autompc.sysid.mlp.MLP.pred / pred_batch (mlp.py:219-236) and
+ * pred_diff / pred_diff_batch (mlp.py:238-305).  float64 on the device (the
+ * reference network is .double(), mlp.py:165).  HOST buffers, synchronous.     */
+typedef struct ampc_mlp ampc_mlp;
+int ampc_mlp_create(ampc_mlp **out, const ampc_mlp_desc *mlp, int32_t nx, int32_t nu, int32_t device);
+int ampc_mlp_destroy(ampc_mlp *m);
+/* X (m,nx), U (m,nu) -> Xn (m,nx) */
+int ampc_mlp_pred_batch(ampc_mlp *m, int32_t batch, const double *X, const double *U, double *Xn);
+/* + Jx (m,nx,nx) = d Xn / d X, Ju (m,nx,nu) = d Xn / d U */
+int ampc_mlp_pred_diff_batch(ampc_mlp *m, int32_t batch, const double *X, const double *U,
+                             double *Xn, double *Jx, double *Ju);
+
+/* ------------------------------------------------------------------ iLQR --- */
+/* Replaces autompc.control.ilqr.IterativeLQR.compute_ilqr_default
+ * (autompc/control/ilqr.py:100-265) for MLP dynamics + QuadCost: the whole
+ * solve (init rollout with Jacobians, up to max_iter x [backward Riccati,
+ * 10-alpha line search, Jacobian refresh]) is one kernel launch, float64.      */
+typedef struct ampc_ilqr_cfg {
+  int32_t H, nx, nu;
+  double dt;
+  int32_t bounded;         /* clip controls to [umin,umax] (ilqr.py:203-204)   */
+  int32_t max_iter;        /* 50  */
+  int32_t ls_max_iter;     /* 10  */
+  double ls_discount;      /* 0.2 */
+  double ls_cost_threshold;/* 0.3 */
+  double u_threshold;      /* 1e-3 */
+  int32_t device;
+} ampc_ilqr_cfg;
+typedef struct ampc_ilqr ampc_ilqr;
+int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const ampc_mlp_desc *mlp,
+                     const ampc_quad_cost *cost);
+int ampc_ilqr_destroy(ampc_ilqr *h);
+/* host buffers: x0 (nx,), uguess (H,nu) or NULL (= zeros, ilqr.py:282);
+ * out: states (H+1,nx), ctrls (H,nu), Ks (H,nu,nx), ks (H,nu),
+ *      info[0]=converged, info[1]=iterations run, info[2]=line-search-failed,
+ *      alpha_idx (max_iter,) adopted line-search index per iteration (-1 past the end). */
+int ampc_ilqr_solve_host(ampc_ilqr *h, const double *x0, const double *uguess, double *states,
+                         double *ctrls, double *Ks, double *ks, int32_t *info, int32_t *alpha_idx);
+
+/* ------------------------------------------------------------------ misc --- */
+const char *ampc_last_error(void);
+const char *ampc_version(void);
+/* number of kernels this library has launched in this process (bench evidence) */
+uint64_t ampc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMPC_B200_H */
