@@ -169,13 +169,11 @@ class MPPI(Controller):
         self.cur_step += 1
         return u
 
-    def _solve_sharded(self, x0, eps):
+    def _shard_bufs(self):
         import torch
-        import torch.distributed as dist
-        lib = _abi.lib()
-        dev = torch.device("cuda", self.device)
         if self._dev_bufs is None:
-            nrec = lib.ampc_mppi_record_floats(self._h)
+            dev = torch.device("cuda", self.device)
+            nrec = _abi.lib().ampc_mppi_record_floats(self._h)
             self._dev_bufs = dict(
                 x0=torch.empty(self.dim_state, dtype=torch.float32, device=dev),
                 u=torch.empty(self.dim_ctrl, dtype=torch.float32, device=dev),
@@ -183,19 +181,35 @@ class MPPI(Controller):
                 recs=torch.empty(self.world * nrec, dtype=torch.float32, device=dev),
                 x0_pin=torch.empty(self.dim_state, dtype=torch.float32).pin_memory(),
                 u_pin=torch.empty(self.dim_ctrl, dtype=torch.float32).pin_memory())
-        b = self._dev_bufs
+        return self._dev_bufs
+
+    def solve_device_sharded(self, x0_dev, u_dev, eps_dev=None):
+        """Sharded solve on device tensors, asynchronous on torch's current stream: local rollouts ->
+        one all-gather of the (min, sum w, sum w*eps) record -> merge on every rank."""
+        import torch
+        import torch.distributed as dist
+        lib = _abi.lib()
+        b = self._shard_bufs()
+        stream = torch.cuda.current_stream().cuda_stream
+        _abi.check(lib.ampc_mppi_rollout_partial(self._h, x0_dev.data_ptr(),
+                                                 None if eps_dev is None else eps_dev.data_ptr(), self.seed,
+                                                 self.cur_step, b["rec"].data_ptr(), stream))
+        dist.all_gather_into_tensor(b["recs"], b["rec"], group=self.group)
+        _abi.check(lib.ampc_mppi_merge(self._h, b["recs"].data_ptr(), self.world, u_dev.data_ptr(), stream))
+        self.cur_step += 1
+
+    def _solve_sharded(self, x0, eps):
+        import torch
+        dev = torch.device("cuda", self.device)
+        b = self._shard_bufs()
         with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream().cuda_stream
             b["x0_pin"].copy_(torch.from_numpy(x0).to(torch.float32))
             b["x0"].copy_(b["x0_pin"], non_blocking=True)
-            e_ptr = None
+            e_dev = None
             if eps is not None:
                 e_dev = torch.from_numpy(np.ascontiguousarray(eps, dtype=np.float32)).to(dev)
-                e_ptr = e_dev.data_ptr()
-            _abi.check(lib.ampc_mppi_rollout_partial(self._h, b["x0"].data_ptr(), e_ptr, self.seed, self.cur_step,
-                                                     b["rec"].data_ptr(), stream))
-            dist.all_gather_into_tensor(b["recs"], b["rec"], group=self.group)
-            _abi.check(lib.ampc_mppi_merge(self._h, b["recs"].data_ptr(), self.world, b["u"].data_ptr(), stream))
+            self.solve_device_sharded(b["x0"], b["u"], e_dev)
+            self.cur_step -= 1            # solve() advances the counter
             b["u_pin"].copy_(b["u"], non_blocking=True)
             torch.cuda.current_stream().synchronize()
         return b["u_pin"].numpy().astype(np.float64)
@@ -203,6 +217,8 @@ class MPPI(Controller):
     def solve_device(self, x0_dev, u_dev, eps_dev=None, stream=0):
         """Asynchronous solve on device float32 tensors/pointers (no host round trip).
         ``x0_dev`` / ``u_dev`` / ``eps_dev`` expose ``data_ptr()`` (torch tensors)."""
+        if self.world > 1:
+            return self.solve_device_sharded(x0_dev, u_dev, eps_dev)
         _abi.check(_abi.lib().ampc_mppi_solve(self._h, x0_dev.data_ptr(),
                                               None if eps_dev is None else eps_dev.data_ptr(), self.seed,
                                               self.cur_step, u_dev.data_ptr(), stream))

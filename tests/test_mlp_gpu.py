@@ -1,0 +1,71 @@
+"""GPU parity: float64 MLP inference / Jacobian kernels (through the C ABI) against
+fixtures recorded from the UNMODIFIED reference ``autompc.sysid.mlp.MLP``
+(``pred`` / ``pred_batch`` mlp.py:219-236, ``pred_diff`` / ``pred_diff_batch`` :238-305).
+Tolerance: float64 on both sides, different summation order -> atol 1e-12 (states ~1), Jacobians 1e-11."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.mppi_oracle import MLPParams, mlp_pred_batch, mlp_pred_diff_batch
+from tests.helpers import GOLDEN, synthetic_mlp
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(p):
+    from autompc_b200 import B200MLP
+    from autompc_b200.plugin import System
+    from tests.gpu_helpers import weights_of
+    system = System(["x%d" % i for i in range(p.nx)], ["u%d" % i for i in range(p.nu)])
+    return B200MLP(system, weights_of(p))
+
+
+def test_mlp_kernels_match_reference_fixture():
+    z = np.load(os.path.join(GOLDEN, "mlp_cases.npz"))
+    for c in range(int(z["n_cases"])):
+        pre = "c%d_" % c
+        p = MLPParams.from_npz(z, pre)
+        m = _model(p)
+        X, U = z[pre + "X"], z[pre + "U"]
+        np.testing.assert_allclose(m.pred_batch(X, U), z[pre + "pred_batch"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(m.pred(X[0], U[0]), z[pre + "pred0"], rtol=0, atol=1e-12)
+        xn, jx, ju = m.pred_diff_batch(X, U)
+        np.testing.assert_allclose(xn, z[pre + "diff_xn"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(jx, z[pre + "diff_jx"], rtol=0, atol=1e-11)
+        np.testing.assert_allclose(ju, z[pre + "diff_ju"], rtol=0, atol=1e-11)
+        xn1, jx1, ju1 = m.pred_diff(X[1], U[1])
+        np.testing.assert_allclose(xn1, z[pre + "diff1_xn"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(jx1, z[pre + "diff1_jx"], rtol=0, atol=1e-11)
+        np.testing.assert_allclose(ju1, z[pre + "diff1_ju"], rtol=0, atol=1e-11)
+
+
+@pytest.mark.parametrize("act", ["relu", "tanh", "sigmoid", "selu"])
+def test_mlp_kernels_match_oracle_large(act):
+    """C3-sized network, ragged batch sizes (incl. 1 and a non-multiple of the CTA width)."""
+    p = synthetic_mlp(17, 6, [256, 256, 256], act=act, seed=4)
+    m = _model(p)
+    rng = np.random.default_rng(0)
+    for batch in (1, 50, 333):
+        X, U = rng.normal(size=(batch, 17)), rng.normal(size=(batch, 6))
+        np.testing.assert_allclose(m.pred_batch(X, U), mlp_pred_batch(p, X, U), rtol=0, atol=1e-12)
+        xn, jx, ju = m.pred_diff_batch(X, U)
+        rxn, rjx, rju = mlp_pred_diff_batch(p, X, U)
+        np.testing.assert_allclose(xn, rxn, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(jx, rjx, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(ju, rju, rtol=0, atol=1e-11)
+
+
+def test_mlp_parameter_round_trip_and_errors():
+    p = synthetic_mlp(4, 1, [64, 64], seed=8)
+    m = _model(p)
+    params = m.get_parameters()                       # same keys as mlp.py:308-313
+    assert set(params) >= {"net_state", "xu_means", "xu_std", "dy_means", "dy_std"}
+    m2 = _model(synthetic_mlp(4, 1, [64, 64], seed=9))
+    m2.set_parameters(params)
+    X, U = np.ones((3, 4)), np.ones((3, 1))
+    np.testing.assert_array_equal(m.pred_batch(X, U), m2.pred_batch(X, U))
+    with pytest.raises(ValueError):
+        m.pred_batch(np.ones((3, 5)), U)
+    with pytest.raises(NotImplementedError):
+        m.train([])

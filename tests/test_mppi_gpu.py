@@ -1,0 +1,252 @@
+"""GPU parity: the CUDA MPPI solve (through the C ABI) against
+ (1) fixtures recorded from the UNMODIFIED reference (ctrl_dim == 1), replaying the
+     global NumPy noise stream from the recorded seed ("external eps" mode), and
+ (2) the float64 oracle restatement on the same noise (ctrl_dim > 1, other
+     activations, dense Q, Philox noise fetched back from the device).
+
+Tolerances (stated).  The reference is float64; the engine
+computes in float32 ("fp32": CUDA-core FMA) or bf16 x bf16 -> fp32 tensor-core
+products with fp32 state/cost ("bf16").  The softmax amplifies ABSOLUTE cost error
+by 1/lmda, so the tolerance on the updated action sequence is per (precision, lmda,
+cost scale); the numbers below are for the listed cases:
+   fp32 : costs rtol 2e-5, action sequence atol 2e-3 (normalised controls, |.| <= 1)
+   bf16 : costs rtol 2e-3, action sequence atol 5e-2
+   exact: argmin(costs) (trajectory index), the shift indexing, the RNG draw order.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import philox
+from oracle.mppi_oracle import MPPIOracle, QuadCostParams, mlp_pred_batch
+from tests.helpers import GOLDEN, load_cartpole, synthetic_mlp
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": dict(cost_rtol=2e-5, act_atol=2e-3), "bf16": dict(cost_rtol=2e-3, act_atol=5e-2)}
+
+
+def _engine(p, cost, umin, umax, **kw):
+    from autompc_b200 import MPPI
+    from tests.gpu_helpers import problem_of
+    system, task, model = problem_of(p, cost, umin, umax)
+    return MPPI(system, task, model, **kw)
+
+
+def _check_solve(ctl, o, x0, eps, tol, check_argmin=True):
+    """One solve on both sides with the same unclipped noise; compares costs, argmin, act, u."""
+    ctl.act_sequence = o.act_sequence           # same warm start on both sides (float32 copy on the device)
+    u = ctl.solve(x0, eps=eps)
+    u_o = o.solve(x0, eps=eps.copy())
+    costs, term = ctl.last_costs()
+    ref = o.last_costs - o.term_const          # the engine returns the reference's terminal scalar separately
+    np.testing.assert_allclose(costs, ref, rtol=tol["cost_rtol"], atol=tol["cost_rtol"] * np.abs(ref).max())
+    np.testing.assert_allclose(term, o.term_const, rtol=max(tol["cost_rtol"], 1e-5) * 10,
+                               atol=tol["cost_rtol"] * np.abs(ref).max())
+    if check_argmin:
+        assert int(np.argmin(costs)) == int(np.argmin(ref))
+    np.testing.assert_allclose(ctl.act_sequence, o.act_sequence, rtol=0, atol=tol["act_atol"])
+    np.testing.assert_allclose(u, u_o, rtol=0, atol=tol["act_atol"] * np.abs(o.ctrl_scale).max())
+    return u, u_o
+
+
+@pytest.mark.parametrize("name", ["mppi_cartpole_K256_H20", "mppi_cartpole_K100_H5", "mppi_cartpole_K512_H30",
+                                  "mppi_cartpole_K4096_H30"])
+def test_mppi_matches_unmodified_reference_fixture(name):
+    """ctrl_dim == 1: the checker is the unmodified reference's recorded output."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    mlp, cost, umin, umax, _, _ = load_cartpole()
+    K, H = int(z["K"]), int(z["H"])
+    tol = TOL["fp32"]
+    np.random.seed(int(z["seed"]))
+    ctl = _engine(mlp, cost, umin, umax, horizon=H, num_path=K, sigma=float(z["sigma"]), lmda=float(z["lmda"]),
+                  noise="numpy", precision="fp32")
+    np.testing.assert_allclose(ctl.act_sequence, z["act0"], rtol=0, atol=1e-7)   # same draws, same order (mppi.py:99)
+    constate = np.zeros(5)
+    for s in range(int(z["n_steps"])):
+        x = z["x0_%d" % s]
+        u, constate = ctl.run(constate, x)            # draws K*H normals from the global stream like mppi.py:126
+        costs, term = ctl.last_costs()
+        ref = z["costs_%d" % s]
+        # the terminal scalar (last sample's final state, F up to 3000: mppi.py:79-82) is common to all
+        # samples and cancels in the softmax; float32 state error after H steps is amplified by F there,
+        # so the absolute level gets 1e-4 and the softmax-relevant differences the fp32 tolerance
+        np.testing.assert_allclose(costs + term, ref, rtol=1e-4)
+        np.testing.assert_allclose(costs - costs.min(), ref - ref.min(), rtol=0,
+                                   atol=tol["cost_rtol"] * np.abs(ref).max())
+        assert int(np.argmin(costs)) == int(z["argmin_%d" % s])                  # bit-exact trajectory index
+        # the engine carries its own float32 action sequence across steps: tolerance grows mildly with s
+        np.testing.assert_allclose(ctl.act_sequence, z["act_%d" % s], rtol=0, atol=tol["act_atol"] * (1 + s))
+        np.testing.assert_allclose(u, z["u_%d" % s], rtol=0, atol=tol["act_atol"] * (1 + s) * 20.0)
+        np.testing.assert_allclose(constate, np.concatenate([x, u]))
+    ctl.close()
+
+
+CASES = [
+    # nx, nu, hidden, act, K, H, sigma, lmda, dense
+    (17, 6, [256, 256, 256], "relu", 2048, 50, 1.0, 1.0, False),      # C3 dims at reduced K
+    (17, 6, [64, 64], "tanh", 300, 12, 0.5, 0.7, True),
+    (4, 1, [32], "sigmoid", 77, 7, 0.3, 0.5, False),
+    (3, 2, [48, 24, 16], "selu", 129, 9, 0.8, 2.0, True),
+    (4, 1, [64, 64], "relu", 1, 2, 1.0, 1.0, False),                  # K=1, minimum horizon
+    (6, 3, [100, 60], "relu", 1000, 20, 1.0, 1.0, False),             # widths that are not powers of two
+]
+
+
+@pytest.mark.parametrize("nx,nu,hidden,act,K,H,sigma,lmda,dense", CASES)
+def test_mppi_fp32_matches_oracle(nx, nu, hidden, act, K, H, sigma, lmda, dense):
+    """ctrl_dim > 1 (restated oracle), all activations, dense Q/R/F, ragged K."""
+    rng = np.random.default_rng(5)
+    p = synthetic_mlp(nx, nu, hidden, act=act, seed=3)
+    if dense:
+        A, B, C = rng.normal(size=(nx, nx)), rng.normal(size=(nu, nu)), rng.normal(size=(nx, nx))
+        cost = QuadCostParams(A @ A.T / nx, 0.01 * (B @ B.T), C @ C.T, goal=0.1 * rng.normal(size=nx))
+    else:
+        cost = QuadCostParams(np.eye(nx), 0.01 * np.eye(nu), 10 * np.eye(nx), goal=0.05 * rng.normal(size=nx))
+    umax = rng.uniform(0.5, 2.0, size=nu)
+    umin = -umax * rng.uniform(0.5, 1.0, size=nu)
+    np.random.seed(1)
+    ctl = _engine(p, cost, umin, umax, horizon=H, num_path=K, sigma=sigma, lmda=lmda, noise="numpy",
+                  precision="fp32")
+    np.random.seed(1)
+    o = MPPIOracle(p, cost, umin, umax, horizon=H, num_path=K, sigma=sigma, lmda=lmda)
+    x0 = rng.normal(size=nx)
+    for _ in range(3):                                   # warm-started consecutive solves (shift indexing)
+        eps = o.sample_eps()
+        u, _ = _check_solve(ctl, o, x0, eps, TOL["fp32"], check_argmin=K > 1)
+        x0 = mlp_pred_batch(p, x0[None], u[None])[0]
+    ctl.close()
+
+
+def test_mppi_per_sample_terminal_option():
+    """terminal='per_sample' (explicit non-reference option): each sample pays its own terminal cost."""
+    p = synthetic_mlp(5, 2, [32, 32], seed=9)
+    cost = QuadCostParams(np.eye(5), 0.1 * np.eye(2), 50 * np.eye(5))
+    umin, umax = [-1.0, -2.0], [1.0, 2.0]
+    np.random.seed(4)
+    ctl = _engine(p, cost, umin, umax, horizon=8, num_path=200, noise="numpy", precision="fp32",
+                  terminal="per_sample")
+    np.random.seed(4)
+    o = MPPIOracle(p, cost, umin, umax, horizon=8, num_path=200)
+    x0 = np.linspace(-1, 1, 5)
+    eps = o.sample_eps()
+    act = o.act_sequence.copy()
+    ctl.solve(x0, eps=eps)
+    costs_ref, eps_c = o.do_rollouts(x0, eps.copy())
+    per = costs_ref - o.term_const + np.einsum("ki,ij,kj->k", o.last_path - cost.goal, cost.F, o.last_path - cost.goal)
+    costs, _ = ctl.last_costs()
+    np.testing.assert_allclose(costs, per, rtol=2e-5)
+    S = np.exp(-(per - per.min()))
+    shifted = np.concatenate([act[1:], act[-1:]])
+    np.testing.assert_allclose(ctl.act_sequence, shifted + np.einsum("hkj,k->hj", eps_c, S / S.sum()), atol=2e-3)
+    ctl.close()
+
+
+def test_philox_stream_matches_restatement():
+    """The in-kernel generator, restated in NumPy (oracle/philox.py): integer stream identical,
+    float transforms to ~1e-5; and moments of a large draw."""
+    p = synthetic_mlp(4, 6, [16], seed=1)
+    cost = QuadCostParams(np.eye(4), np.eye(6), np.eye(4))
+    ctl = _engine(p, cost, -np.ones(6), np.ones(6), horizon=11, num_path=4099, sigma=0.49, seed=1234567890123,
+                  precision="fp32")
+    e = ctl.philox_noise(counter=7)
+    ref = philox.mppi_noise(1234567890123, 7, 11, 4099, 6, 0.49)
+    np.testing.assert_allclose(e, ref, rtol=0, atol=2e-5)
+    assert abs(e.mean()) < 5e-3 and abs(e.std() - 0.7) < 5e-3
+    e2 = ctl.philox_noise(counter=8)
+    assert abs(np.corrcoef(e.ravel(), e2.ravel())[0, 1]) < 0.01      # different solves, independent noise
+    ctl.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32"])
+def test_philox_mode_equals_external_eps_mode(precision):
+    """Performance mode (in-kernel Philox) == parity mode fed the same noise, and == the oracle."""
+    p = synthetic_mlp(17, 6, [64, 64], seed=2)
+    cost = QuadCostParams(np.eye(17), 0.01 * np.eye(6), 10 * np.eye(17))
+    kw = dict(horizon=15, num_path=777, sigma=1.0, lmda=1.0, seed=99, precision=precision)
+    np.random.seed(0)
+    a = _engine(p, cost, -np.ones(6), np.ones(6), **kw)
+    np.random.seed(0)
+    b = _engine(p, cost, -np.ones(6), np.ones(6), **kw)
+    np.random.seed(0)
+    o = MPPIOracle(p, cost, -np.ones(6), np.ones(6), horizon=15, num_path=777)
+    x0 = np.random.default_rng(3).normal(size=17)
+    for step in range(2):
+        eps = a.philox_noise().astype(np.float64)        # noise of solve `cur_step`
+        ua = a.solve(x0)                                 # Philox in-kernel
+        ub = b.solve(x0, eps=eps)                        # same numbers uploaded
+        np.testing.assert_allclose(ua, ub, rtol=0, atol=1e-6)
+        np.testing.assert_allclose(a.last_costs()[0], b.last_costs()[0], rtol=1e-6)
+        uo = o.solve(x0, eps=eps)
+        np.testing.assert_allclose(ua, uo, rtol=0, atol=TOL[precision]["act_atol"])
+    a.close()
+    b.close()
+
+
+def test_sharded_partials_merge_equals_single_handle():
+    """Multi-GPU data path on one device: 3 shards (k_offset) -> rollout_partial -> merge
+    == one handle over all samples (Philox keyed by GLOBAL sample index)."""
+    import ctypes as C
+    import torch
+    from autompc_b200 import _abi
+    p = synthetic_mlp(17, 6, [64, 64], seed=2)
+    cost = QuadCostParams(np.eye(17), 0.01 * np.eye(6), 10 * np.eye(17))
+    K, H = 1000, 10
+    np.random.seed(0)
+    full = _engine(p, cost, -np.ones(6), np.ones(6), horizon=H, num_path=K, seed=5, precision="fp32")
+    act0 = full.act_sequence
+    x0 = np.random.default_rng(1).normal(size=17)
+    u_full = full.solve(x0)
+    lib = _abi.lib()
+    shards, recs = [], []
+    dev = torch.device("cuda", 0)
+    x0_d = torch.tensor(x0, dtype=torch.float32, device=dev)
+    splits = [(0, 334), (334, 333), (667, 333)]
+    for off, n in splits:                        # shard geometry through the C ABI directly
+        cfg = _abi.MppiCfg(n, H, 17, 6, 1.0, 1.0, 0, 0, off, K, 0)
+        h = C.c_void_p()
+        _abi.check(lib.ampc_mppi_create(C.byref(h), C.byref(cfg), C.byref(full._mlp_holder.desc),
+                                        C.byref(full._cost_holder.desc)))
+        a = np.ascontiguousarray(act0)
+        _abi.check(lib.ampc_mppi_set_act_seq(h, _abi.dptr(a)))
+        rec = torch.zeros(lib.ampc_mppi_record_floats(h), dtype=torch.float32, device=dev)
+        _abi.check(lib.ampc_mppi_rollout_partial(h, x0_d.data_ptr(), None, 5, 0, rec.data_ptr(), None))
+        shards.append(h)
+        recs.append(rec)
+    torch.cuda.synchronize()
+    allrec = torch.cat(recs).contiguous()
+    u_d = torch.zeros(6, dtype=torch.float32, device=dev)
+    for h in shards:
+        _abi.check(lib.ampc_mppi_merge(h, allrec.data_ptr(), len(shards), u_d.data_ptr(), None))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(u_d.cpu().numpy(), u_full, rtol=0, atol=2e-6)
+    for h in shards:
+        a = np.empty((H, 6))
+        _abi.check(lib.ampc_mppi_get_act_seq(h, _abi.dptr(a)))
+        np.testing.assert_allclose(a, full.act_sequence, rtol=0, atol=2e-6)
+        lib.ampc_mppi_destroy(h)
+    full.close()
+
+
+def test_closed_loop_through_plugin_surface():
+    """simulate()-style loop (utils/simulation.py:45-63) with the engine as Controller and B200MLP as
+    the stepped model: fixed-size state, fresh arrays, reset() redraws (mppi.py:107-108)."""
+    from autompc_b200 import MPPI, B200MLP
+    from autompc_b200.problems import cartpole_problem
+    from autompc_b200.mlp import MLPWeights
+    z = np.load(os.path.join(GOLDEN, "cartpole_mlp.npz"))
+    system, task, w, x0 = cartpole_problem(MLPWeights.from_npz(z))
+    model = B200MLP(system, w)
+    np.random.seed(0)
+    ctl = MPPI(system, task, model, horizon=20, num_path=512, precision="fp32")
+    assert ctl.state_dim == 5
+    x, constate = x0.copy(), np.concatenate([x0, np.zeros(1)])
+    for _ in range(5):
+        u, constate = ctl.run(constate, x)
+        assert u.shape == (1,) and constate.shape == (5,) and np.all(np.abs(u) <= 20.0 + 1e-5)
+        x = model.pred(x, u)
+    a = ctl.act_sequence
+    ctl.reset()
+    assert ctl.cur_step == 0 and not np.allclose(a, ctl.act_sequence)
+    ctl.close()
