@@ -138,7 +138,7 @@ struct AmpcConstLayout {
 struct AmpcMppiParams {
   int K, H, nx, nu;
   int k_offset, K_global;
-  int terminal_mode, q_diag, f_diag, act;
+  int terminal_mode, q_diag, f_diag, r_diag, act;
   int n_layers;
   int dims[AMPC_MAX_LAYERS + 1];
   int npt[AMPC_MAX_LAYERS];   // fp32 kernel: outputs per thread of each layer

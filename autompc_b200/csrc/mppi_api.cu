@@ -200,6 +200,7 @@ extern "C" int ampc_mppi_create(ampc_mppi **out, const ampc_mppi_cfg *cfg, const
   p.terminal_mode = cfg->terminal_mode;
   p.q_diag = is_diag(cost->Q, nx);
   p.f_diag = is_diag(cost->F, nx);
+  p.r_diag = is_diag(cost->R, nu);
   p.act = mlp->act;
   p.n_layers = mlp->n_layers;
   p.max_width = 0;

@@ -1,13 +1,645 @@
-// tcgen05 (UMMA) bf16 MPPI rollout path -- placeholder until the kernel lands.
+// MPPI rollout + softmax update on the 5th-generation tensor cores (tcgen05 / UMMA, sm_100a).
+//
+// One launch = one MPPI.run (autompc/control/mppi.py:154-168), same contract as mppi_fp32.cu.
+//
+// Mapping.  A CTA owns 128 samples; sample t <-> thread t <-> TMEM lane t, so the state, the
+// running cost and the noise of a sample never leave its thread.  Per horizon step the MLP is a
+// chain of n_layers dependent GEMMs  D[128 x N_l] = A[128 x K_l] . W_l^T :
+//   * W_l (torch.nn.Linear layout (out,in) == K-major B operand) is converted to bf16 once on the
+//     host, laid out as the UMMA canonical K-major SWIZZLE_128B shared-memory image, and stays
+//     RESIDENT in shared memory for the whole solve (no per-step weight traffic);
+//   * A_l (the activations) lives in TENSOR MEMORY as packed bf16 and is the TMEM A operand of
+//     tcgen05.mma (".ts" form) -- activations never touch shared memory;
+//   * D_l is the fp32 accumulator in TMEM; the sample's thread reads its row with tcgen05.ld,
+//     applies bias + activation, packs to bf16 and writes the next layer's A row with tcgen05.st.
+// With CG=2 the kernel runs as CTA pairs (cta_group::2, UMMA M=256): each CTA keeps HALF of the
+// output neurons of every layer in its shared memory, which is what lets the 3x256 network
+// (283 KB of bf16 weights) stay resident; the leader CTA's single MMA thread issues for both.
+// Warps 0-3: samples/epilogue.  Warp 4: MMA issue + TMEM allocation.
+// Synchronisation is two mbarriers: bar_a (activations of a layer are in TMEM: 4 warps x CG CTAs
+// arrive) and bar_d (tcgen05.commit: the layer's accumulator is complete, multicast to the pair).
+//
+// The clipped noise (mppi.py:139) of every (step, control, sample) is written to an L2-resident
+// scratch and re-read once the softmax weights are known (mppi.py:115-117); per-CTA partial records
+// (min, sum w, sum w*eps) are merged by the last CTA to finish, exactly like the fp32 kernel.
+#include <cuda_bf16.h>
+
+#include <vector>
+
 #include "ampc_common.cuh"
 
-struct AmpcTcPlan { int unused; };
+namespace {
 
-int ampc_mppi_tc_supported(const ampc_mppi_cfg *, const ampc_mlp_desc *, const char **why) {
-  *why = "tcgen05 path not built in this revision";
+constexpr int TM = 128;              // samples per CTA
+constexpr int NTHR = 160;            // 4 sample warps + 1 MMA warp
+constexpr int TMEM_COLS = 512;
+constexpr int TMEM_D = 0;            // accumulator columns [0,256)
+constexpr int TMEM_A = 256;          // packed bf16 activations, columns [256,384)
+constexpr int MAXL = AMPC_MAX_LAYERS;
+
+struct TcArgs {
+  int n_layers;
+  int kpad[MAXL], npad[MAXL];        // padded K (multiple of 16) and N (multiple of 32) per layer
+  uint32_t w_off[MAXL];              // byte offset of layer l's B image inside one CTA's weight image
+  uint32_t w_bytes;                  // bytes of one CTA's weight image
+  int b_off[MAXL];                   // float offset of the layer's (padded) bias
+  int bias_floats;
+  uint32_t idesc[MAXL];              // UMMA instruction descriptors
+  const uint8_t *wimg;               // CG images back to back
+  const float *bias;
+  float *epsc;                       // (H*nu, Kc) clipped noise scratch
+  int Kc;                            // grid * 128
+};
+
+// ------------------------------------------------------------------ PTX wrappers ---
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// arrive on the barrier at the same shared offset in CTA `cta` of the cluster (works for the own CTA too)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) {
+      printf("ampc mppi_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(TMEM_COLS) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(TMEM_COLS) : "memory");
+}
+// D[tmem] (+)= A[tmem, packed bf16] . B[smem desc]^T
+template <int CG>
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if constexpr (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  else
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// {lo, hi} -> packed bf16x2 (element with the even K index in the low half)
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor: 128-byte rows, 8-row (1024 B) swizzle atoms
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// d^T M d for this thread's sample; v laid out [i][TM]
+__device__ __forceinline__ float quad_full(const float *M, const float *v, const float *off, int n, bool diag, int t) {
+  float c = 0.f;
+  if (diag) {
+    for (int i = 0; i < n; ++i) {
+      const float di = v[i * TM + t] - (off ? off[i] : 0.f);
+      c = fmaf(M[i * n + i] * di, di, c);
+    }
+  } else {
+    for (int i = 0; i < n; ++i) {
+      const float di = v[i * TM + t] - (off ? off[i] : 0.f);
+      float row = 0.f;
+      for (int j = 0; j < n; ++j) row = fmaf(M[i * n + j], v[j * TM + t] - (off ? off[j] : 0.f), row);
+      c = fmaf(di, row, c);
+    }
+  }
+  return c;
+}
+
+template <int CG>
+__global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppiParams p, const TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nx = p.nx, nu = p.nu, H = p.H, HN = H * nu, L = a.n_layers;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const AmpcConstLayout cl(nx, nu);
+
+  // ---- shared memory carve (weight image first, 1024-byte aligned for the 128B swizzle atoms)
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t *base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t *s_w = base;
+  float *s_bias = reinterpret_cast<float *>(base + a.w_bytes);
+  float *s_const = s_bias + ((a.bias_floats + 3) & ~3);
+  float *s_act = s_const + cl.total;                   // shifted act_sequence (H*nu)
+  float *s_x = s_act + ((HN + 3) & ~3);                // state [nx][128]
+  float *s_u = s_x + nx * TM;                          // scaled control [nu][128]
+  float *s_wgt = s_u + nu * TM;                        // softmax numerators [128]
+  float *s_red = s_wgt + TM;                           // 32
+  float *s_misc = s_red + 32;                          // 64 + AMPC_MERGE_CACHE
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_misc + 64 + AMPC_MERGE_CACHE);   // [0]=bar_a [1]=bar_d
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2);
+  __shared__ int s_last;
+
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(a.wimg + (size_t)cta_rank * a.w_bytes);
+    uint4 *dst = reinterpret_cast<uint4 *>(s_w);
+    for (int i = tid; i < (int)(a.w_bytes >> 4); i += NTHR) dst[i] = __ldg(src + i);
+  }
+  for (int i = tid; i < a.bias_floats; i += NTHR) s_bias[i] = a.bias[i];
+  for (int i = tid; i < cl.total; i += NTHR) s_const[i] = p.consts[i];
+  for (int e = tid; e < HN; e += NTHR) {               // mppi.py:122-123
+    const int i = e / nu, j = e - i * nu;
+    const int src = (i + 1 < H) ? i + 1 : H - 1;
+    s_act[e] = p.act_seq[src * nu + j];
+  }
+  if (tid < TM)
+    for (int j = 0; j < nx; ++j) s_x[j * TM + tid] = p.x0[j];   // mppi.py:129-130
+  const uint32_t bar_a = smem_u32(&s_bar[0]), bar_d = smem_u32(&s_bar[1]);
+  if (tid == 0) {
+    mbar_init(bar_a, 4 * CG);
+    mbar_init(bar_d, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc<CG>(smem_u32(s_tmem));
+  fence_proxy_async_smem();                            // weight image (generic-proxy stores) -> tensor-core reads
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const float *c_mean = s_const + cl.xu_mean, *c_inv = s_const + cl.xu_inv;
+  const float *c_dym = s_const + cl.dy_mean, *c_dys = s_const + cl.dy_std;
+  const float *c_goal = s_const + cl.goal, *c_Q = s_const + cl.Q, *c_R = s_const + cl.R, *c_F = s_const + cl.F;
+  const float *c_lo = s_const + cl.lo, *c_hi = s_const + cl.hi, *c_scale = s_const + cl.scale;
+
+  const int k_local = blockIdx.x * TM + tid;           // meaningful for tid < 128
+  const bool valid = (tid < TM) && (k_local < p.K);
+  float cost_acc = 0.f;
+
+  if (warp == 4) {
+    // =========================== MMA issuer (leader CTA of the pair) ===========================
+    if (cta_rank == 0) {
+      uint32_t ph = 0;
+      const uint32_t d_addr = tmem_base + TMEM_D, a_addr = tmem_base + TMEM_A;
+      const uint32_t w_addr = smem_u32(s_w);
+      for (int i = 0; i < H; ++i) {
+        for (int l = 0; l < L; ++l) {
+          mbar_wait(bar_a, ph);
+          ph ^= 1u;
+          tc_fence_after();
+          if (lane == 0) {
+            const int rows = a.npad[l] / CG;            // B rows held by each CTA
+            const uint64_t d0 = make_b_desc(w_addr + a.w_off[l]);
+            const int nks = a.kpad[l] >> 4;
+            for (int ks = 0; ks < nks; ++ks) {
+              const uint32_t boff = (uint32_t)(ks >> 2) * (uint32_t)(rows * 128) + (uint32_t)(ks & 3) * 32u;
+              umma_ts<CG>(d_addr, a_addr + (uint32_t)ks * 8u, d0 + (uint64_t)(boff >> 4), a.idesc[l], ks > 0);
+            }
+            umma_commit<CG>(bar_d);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // =========================== sample threads (warps 0-3) ===========================
+    const int t = tid;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t kg = (uint32_t)(p.k_offset + k_local);
+    const int nblk = (nu + 3) >> 2;
+    const int nin = nx + nu;
+    uint32_t ph = 0;
+    auto signal_a = [&]() {
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(bar_a, 0u); else mbar_arrive_local(bar_a);
+      }
+    };
+    for (int i = 0; i < H; ++i) {
+      // ---- controls: noise, clip, write-back (mppi.py:134-139), action cost (:143)
+      for (int blk = 0; blk < nblk; ++blk) {
+        float n4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.eps == nullptr) {
+          ampc_normal4(p.seed, p.ctr, kg, (uint32_t)i, (uint32_t)blk, n4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) n4[q] *= p.sqrt_sigma;
+        } else if (valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = blk * 4 + q;
+            if (j < nu) n4[q] = p.eps[((size_t)i * p.K + k_local) * nu + j];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = blk * 4 + q;
+          if (j < nu) {
+            const float a0 = s_act[i * nu + j];
+            const float av = fminf(c_hi[j], fmaxf(c_lo[j], n4[q] + a0));
+            const float e = av - a0;
+            a.epsc[(size_t)(i * nu + j) * a.Kc + k_local] = e;
+            s_u[j * TM + t] = av * c_scale[j];
+            cost_acc = fmaf(p.lam_over_sigma * av, e, cost_acc);
+          }
+        }
+      }
+      // ---- stage cost at the pre-step state (mppi.py:142; cost.py:79-81, :131-132)
+      cost_acc += quad_full(c_Q, s_x, c_goal, nx, p.q_diag, t);
+      cost_acc += quad_full(c_R, s_u, nullptr, nu, p.r_diag, t);
+      // ---- z-score (mlp.py:20-24) -> bf16 -> A operand in TMEM
+      for (int g = 0; g < (a.kpad[0] >> 4); ++g) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float z[2];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int j = g * 16 + q * 2 + hh;
+            float v = 0.f;
+            if (j < nx) v = (s_x[j * TM + t] - c_mean[j]) * c_inv[j];
+            else if (j < nin) v = (s_u[(j - nx) * TM + t] - c_mean[j]) * c_inv[j];
+            z[hh] = v;
+          }
+          pk[q] = pack_bf16(z[0], z[1]);
+        }
+        tmem_st8(lane_base + TMEM_A + g * 8, pk);
+      }
+      signal_a();
+      // ---- hidden layers: D -> bias + activation -> bf16 -> A
+      for (int l = 0; l < L - 1; ++l) {
+        mbar_wait(bar_d, ph);
+        ph ^= 1u;
+        tc_fence_after();
+        const float *bl = s_bias + a.b_off[l];
+        const int np = a.npad[l];
+        for (int c0 = 0; c0 < np; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(lane_base + TMEM_D + c0, r);
+          tc_wait_ld();
+          uint32_t pk[16];
+          if (p.act == AMPC_ACT_RELU) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              pk[q] = pack_bf16_relu(__uint_as_float(r[2 * q]) + bl[c0 + 2 * q],
+                                     __uint_as_float(r[2 * q + 1]) + bl[c0 + 2 * q + 1]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              pk[q] = pack_bf16(ampc_act<float>(p.act, __uint_as_float(r[2 * q]) + bl[c0 + 2 * q]),
+                                ampc_act<float>(p.act, __uint_as_float(r[2 * q + 1]) + bl[c0 + 2 * q + 1]));
+          }
+          tmem_st16(lane_base + TMEM_A + (c0 >> 1), pk);
+        }
+        signal_a();
+      }
+      // ---- output layer: un-z-score + integrate (mlp.py:235-236)
+      mbar_wait(bar_d, ph);
+      ph ^= 1u;
+      tc_fence_after();
+      {
+        const float *bl = s_bias + a.b_off[L - 1];
+        for (int c0 = 0; c0 < a.npad[L - 1]; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(lane_base + TMEM_D + c0, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const int j = c0 + q;
+            if (j < nx) s_x[j * TM + t] += fmaf(__uint_as_float(r[q]) + bl[j], c_dys[j], c_dym[j]);
+          }
+        }
+      }
+    }
+  }
+
+  // =========================== softmax partials of this CTA (mppi.py:110-118) ===========================
+  float c = INFINITY;
+  if (tid < TM) {
+    const float term = quad_full(c_F, s_x, c_goal, nx, p.f_diag, tid);   // mppi.py:79-82, :146-148
+    c = cost_acc;
+    if (p.terminal_mode == 1) c += term;
+    else if (valid && (p.k_offset + k_local) == p.K_global - 1) *p.term_out = term;
+    if (valid) p.costs[k_local] = c; else c = INFINITY;
+    const float m = ampc_warp_min(c);
+    if (lane == 0) s_red[warp] = m;
+  }
+  __syncthreads();
+  const float m_cta = fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3]));
+  if (tid < TM) {
+    const float wgt = valid ? expf(-(c - m_cta) * p.inv_lmda) : 0.f;      // mppi.py:115
+    s_wgt[tid] = wgt;
+    const float s = ampc_warp_sum(wgt);
+    if (lane == 0) s_red[8 + warp] = s;
+  }
+  __syncthreads();
+  float *rec = p.partials + (size_t)blockIdx.x * (2 + HN);
+  if (tid == 0) {
+    rec[0] = m_cta;
+    rec[1] = (s_red[8] + s_red[9]) + (s_red[10] + s_red[11]);
+  }
+  for (int e = warp; e < HN; e += NTHR / 32) {                            // mppi.py:117 (per-CTA share)
+    const float *src = a.epsc + (size_t)e * a.Kc + (size_t)blockIdx.x * TM;
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < TM / 32; ++q) v = fmaf(s_wgt[lane + 32 * q], __ldcg(src + lane + 32 * q), v);
+    v = ampc_warp_sum(v);
+    if (lane == 0) rec[2 + e] = v;
+  }
+  // ---- last CTA to finish merges all partials and applies the update
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int tk = atomicAdd(p.ticket, 1u);
+    s_last = (tk == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    ampc_merge_records(p.partials, (int)gridDim.x, 2 + HN, HN, nu, p.inv_lmda, s_act, c_scale, p.act_seq, p.u_out,
+                       p.record_out, s_misc);
+    if (tid == 0) *p.ticket = 0u;
+  }
+  // ---- teardown
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 4) tmem_dealloc<CG>(tmem_base);
+}
+
+uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)((u >> 16) | ((u & 0xFFFFu) ? 0x40u : 0u));
+  u += 0x7FFFu + ((u >> 16) & 1u);   // round to nearest even
+  return (uint16_t)(u >> 16);
+}
+
+size_t tc_smem_bytes(const TcArgs &a, int nx, int nu, int H) {
+  const AmpcConstLayout cl(nx, nu);
+  const size_t floats = (size_t)((a.bias_floats + 3) & ~3) + cl.total + ((H * nu + 3) & ~3) + (size_t)nx * TM +
+                        (size_t)nu * TM + TM + 32 + 64 + AMPC_MERGE_CACHE;
+  return 1024 + a.w_bytes + floats * sizeof(float) + 2 * sizeof(uint64_t) + 16;
+}
+
+int roundup(int v, int m) { return (v + m - 1) / m * m; }
+
+void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg) {
+  memset(&a, 0, sizeof(a));
+  a.n_layers = mlp->n_layers;
+  uint32_t off = 0;
+  int boff = 0;
+  for (int l = 0; l < mlp->n_layers; ++l) {
+    a.kpad[l] = (l == 0) ? roundup(mlp->dims[0], 16) : a.npad[l - 1];
+    a.npad[l] = roundup(mlp->dims[l + 1], 32);
+    const int rows = a.npad[l] / cg, kblk = (a.kpad[l] + 63) / 64;
+    a.w_off[l] = off;
+    off += (uint32_t)kblk * rows * 128;
+    a.b_off[l] = boff;
+    boff += a.npad[l];
+    // kind::f16: c=f32 (bit 4), a=bf16 (bit 7), b=bf16 (bit 10), both K-major, N>>3 at 17, M>>4 at 24
+    a.idesc[l] = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.npad[l] >> 3) << 17) |
+                 ((uint32_t)((TM * cg) >> 4) << 24);
+  }
+  a.w_bytes = off;
+  a.bias_floats = boff;
+}
+
+}  // namespace
+
+struct AmpcTcPlan {
+  TcArgs args;
+  int cg = 1;
+  int grid = 0;
+  size_t smem = 0;
+  uint8_t *d_wimg = nullptr;
+  float *d_bias = nullptr;
+  float *d_epsc = nullptr;
+};
+
+static bool tc_shape_ok(const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp, const char **why) {
+  if (cfg->nx + cfg->nu > 64) { *why = "nx+nu > 64"; return false; }
+  if (cfg->nx > 64) { *why = "nx > 64"; return false; }
+  for (int l = 1; l < mlp->n_layers; ++l)
+    if (mlp->dims[l] > 256) { *why = "hidden width > 256"; return false; }
+  return true;
+}
+
+// picks CG=1 when the whole bf16 weight image fits next to the working set, else CG=2 (half per CTA)
+static int tc_pick_cg(const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp, size_t cap, TcArgs *out, size_t *smem_out) {
+  for (int cg = 1; cg <= 2; ++cg) {
+    TcArgs a;
+    fill_args(a, mlp, cg);
+    const size_t need = tc_smem_bytes(a, cfg->nx, cfg->nu, cfg->H);
+    if (need <= cap) {
+      *out = a;
+      *smem_out = need;
+      return cg;
+    }
+  }
   return 0;
 }
-int ampc_mppi_tc_create(AmpcTcPlan **, const ampc_mppi_cfg *, const ampc_mlp_desc *) { return AMPC_ERR_UNSUPPORTED; }
-void ampc_mppi_tc_destroy(AmpcTcPlan *) {}
-int ampc_mppi_tc_grid(const AmpcTcPlan *) { return 0; }
-int ampc_mppi_tc_launch(AmpcTcPlan *, const AmpcMppiParams &, cudaStream_t) { return AMPC_ERR_UNSUPPORTED; }
+
+int ampc_mppi_tc_supported(const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp, const char **why) {
+  if (!tc_shape_ok(cfg, mlp, why)) return 0;
+  int dev = 0, max_optin = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+    *why = "cannot query the device";
+    return 0;
+  }
+  TcArgs a;
+  size_t smem = 0;
+  if (!tc_pick_cg(cfg, mlp, (size_t)max_optin, &a, &smem)) {
+    *why = "bf16 weight image does not fit in the shared memory of a CTA pair";
+    return 0;
+  }
+  return 1;
+}
+
+void ampc_mppi_tc_destroy(AmpcTcPlan *plan) {
+  if (!plan) return;
+  cudaFree(plan->d_wimg);
+  cudaFree(plan->d_bias);
+  cudaFree(plan->d_epsc);
+  delete plan;
+}
+
+int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp) {
+  *out = nullptr;
+  int dev = 0, max_optin = 0;
+  AMPC_CUDA_CHECK(cudaGetDevice(&dev));
+  AMPC_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  AmpcTcPlan *pl = new AmpcTcPlan();
+  int cg = tc_pick_cg(cfg, mlp, (size_t)max_optin, &pl->args, &pl->smem);
+  const char *force = getenv("AMPC_TC_FORCE_CG");
+  if (force && (force[0] == '1' || force[0] == '2')) {
+    const int f = force[0] - '0';
+    fill_args(pl->args, mlp, f);
+    pl->smem = tc_smem_bytes(pl->args, cfg->nx, cfg->nu, cfg->H);
+    cg = (pl->smem <= (size_t)max_optin) ? f : 0;
+  }
+  if (!cg) {
+    delete pl;
+    ampc_set_error("tcgen05 MPPI path: weights do not fit in shared memory");
+    return AMPC_ERR_UNSUPPORTED;
+  }
+  pl->cg = cg;
+  TcArgs &a = pl->args;
+  const int tiles = (cfg->K + TM - 1) / TM;
+  pl->grid = roundup(tiles, cg);
+  a.Kc = pl->grid * TM;
+  // ---- weight images: per CTA rank r, per layer, per 64-wide K block: rows x 128 B, 16-byte chunks XOR-swizzled
+  std::vector<uint16_t> img((size_t)cg * a.w_bytes / 2, 0);
+  std::vector<float> bias(a.bias_floats, 0.f);
+  for (int l = 0; l < mlp->n_layers; ++l) {
+    const int Kl = mlp->dims[l], Nl = mlp->dims[l + 1];
+    const int rows = a.npad[l] / cg, kblk = (a.kpad[l] + 63) / 64;
+    for (int r = 0; r < cg; ++r)
+      for (int kb = 0; kb < kblk; ++kb)
+        for (int n = 0; n < rows; ++n)
+          for (int ch = 0; ch < 8; ++ch) {
+            const size_t byte = (size_t)r * a.w_bytes + a.w_off[l] + (size_t)kb * rows * 128 + (size_t)n * 128 +
+                                (size_t)((ch ^ (n & 7)) * 16);
+            for (int e = 0; e < 8; ++e) {
+              const int k = kb * 64 + ch * 8 + e, ng = r * rows + n;
+              const float v = (ng < Nl && k < Kl) ? (float)mlp->W[l][(size_t)ng * Kl + k] : 0.f;
+              img[byte / 2 + e] = f32_to_bf16(v);
+            }
+          }
+    for (int j = 0; j < Nl; ++j) bias[a.b_off[l] + j] = (float)mlp->b[l][j];
+  }
+  cudaError_t e = cudaMalloc(&pl->d_wimg, img.size() * 2);
+  if (e == cudaSuccess) e = cudaMemcpy(pl->d_wimg, img.data(), img.size() * 2, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_bias, bias.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(pl->d_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_epsc, (size_t)cfg->H * cfg->nu * a.Kc * sizeof(float));
+  if (e == cudaSuccess)
+    e = (cg == 1) ? cudaFuncSetAttribute(mppi_rollout_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem)
+                  : cudaFuncSetAttribute(mppi_rollout_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
+  if (e != cudaSuccess) {
+    ampc_set_error("tcgen05 MPPI path create: %s", cudaGetErrorString(e));
+    ampc_mppi_tc_destroy(pl);
+    return AMPC_ERR_CUDA;
+  }
+  a.wimg = pl->d_wimg;
+  a.bias = pl->d_bias;
+  a.epsc = pl->d_epsc;
+  *out = pl;
+  return AMPC_OK;
+}
+
+int ampc_mppi_tc_grid(const AmpcTcPlan *plan) { return plan->grid; }
+int ampc_mppi_tc_cta_group(const AmpcTcPlan *plan) { return plan->cg; }
+
+int ampc_mppi_tc_launch(AmpcTcPlan *plan, const AmpcMppiParams &p, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan->grid);
+  cfg.blockDim = dim3(NTHR);
+  cfg.dynamicSmemBytes = plan->smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = plan->cg;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = (plan->cg == 1) ? cudaLaunchKernelEx(&cfg, mppi_rollout_tc_kernel<1>, p, plan->args)
+                                  : cudaLaunchKernelEx(&cfg, mppi_rollout_tc_kernel<2>, p, plan->args);
+  ampc_count_launch();
+  AMPC_CUDA_CHECK(e);
+  return AMPC_OK;
+}
