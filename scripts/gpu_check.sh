@@ -2,7 +2,7 @@
 # Round-trip GPU check: parity tests, smoke, one bench line.  Run under gpurun from the repo root.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
-timeout 1200 python -m pytest tests -m gpu -q -x --timeout 600 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
+timeout 1200 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1
 timeout 600 python bench.py --steps ${STEPS:-50} --warmup 5 > gpurun_out/bench.log 2>&1
 tail -5 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log; tail -2 gpurun_out/bench.log

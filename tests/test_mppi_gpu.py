@@ -66,6 +66,12 @@ def test_mppi_matches_unmodified_reference_fixture(name):
     constate = np.zeros(5)
     for s in range(int(z["n_steps"])):
         x = z["x0_%d" % s]
+        if s > 0:
+            # free-running float32 warm start stays near the reference's; then re-synchronise so that every
+            # step is compared from an identical starting point (the learned cartpole dynamics near the
+            # upright are unstable: H-step rollouts amplify a 1e-6 warm-start difference)
+            np.testing.assert_allclose(ctl.act_sequence, z["act_%d" % (s - 1)], rtol=0, atol=10 * tol["act_atol"])
+            ctl.act_sequence = z["act_%d" % (s - 1)]
         u, constate = ctl.run(constate, x)            # draws K*H normals from the global stream like mppi.py:126
         costs, term = ctl.last_costs()
         ref = z["costs_%d" % s]
@@ -76,9 +82,8 @@ def test_mppi_matches_unmodified_reference_fixture(name):
         np.testing.assert_allclose(costs - costs.min(), ref - ref.min(), rtol=0,
                                    atol=tol["cost_rtol"] * np.abs(ref).max())
         assert int(np.argmin(costs)) == int(z["argmin_%d" % s])                  # bit-exact trajectory index
-        # the engine carries its own float32 action sequence across steps: tolerance grows mildly with s
-        np.testing.assert_allclose(ctl.act_sequence, z["act_%d" % s], rtol=0, atol=tol["act_atol"] * (1 + s))
-        np.testing.assert_allclose(u, z["u_%d" % s], rtol=0, atol=tol["act_atol"] * (1 + s) * 20.0)
+        np.testing.assert_allclose(ctl.act_sequence, z["act_%d" % s], rtol=0, atol=tol["act_atol"])
+        np.testing.assert_allclose(u, z["u_%d" % s], rtol=0, atol=tol["act_atol"] * 20.0)
         np.testing.assert_allclose(constate, np.concatenate([x, u]))
     ctl.close()
 
@@ -250,3 +255,104 @@ def test_closed_loop_through_plugin_surface():
     ctl.reset()
     assert ctl.cur_step == 0 and not np.allclose(a, ctl.act_sequence)
     ctl.close()
+
+
+# ----------------------------------------------------------------------------- tcgen05 (bf16) path ---
+TC_CASES = [
+    # nx, nu, hidden, act, K, H, sigma, lmda, force_cg
+    (4, 1, [64, 64], "relu", 4096, 30, 1.0, 1.0, None),               # C2 dims (weights fit one CTA: cta_group::1)
+    (4, 1, [64, 64], "relu", 300, 20, 1.0, 1.0, "2"),                 # same network as a CTA pair, ragged K
+    (17, 6, [256, 256, 256], "relu", 2048, 50, 1.0, 1.0, None),       # C3 dims: cta_group::2 (half the weights per CTA)
+    (17, 6, [128, 128], "tanh", 555, 12, 0.5, 0.7, "1"),
+    (17, 6, [100, 60], "sigmoid", 129, 9, 0.8, 2.0, "2"),             # widths padded to 32
+    (3, 2, [48, 24, 16, 40], "selu", 77, 7, 0.3, 0.5, None),          # 4 hidden layers
+    (4, 1, [32], "relu", 1, 2, 1.0, 1.0, None),                       # K=1, minimum horizon
+]
+
+
+@pytest.mark.parametrize("nx,nu,hidden,act,K,H,sigma,lmda,force_cg", TC_CASES)
+def test_mppi_bf16_tensor_core_matches_oracle(nx, nu, hidden, act, K, H, sigma, lmda, force_cg, monkeypatch):
+    """bf16 x bf16 -> fp32 tcgen05 products, fp32 state / cost / softmax: stated bf16 tolerance."""
+    if force_cg:
+        monkeypatch.setenv("AMPC_TC_FORCE_CG", force_cg)
+    else:
+        monkeypatch.delenv("AMPC_TC_FORCE_CG", raising=False)
+    rng = np.random.default_rng(5)
+    p = synthetic_mlp(nx, nu, hidden, act=act, seed=3)
+    cost = QuadCostParams(np.eye(nx), 0.01 * np.eye(nu), 10 * np.eye(nx), goal=0.05 * rng.normal(size=nx))
+    umax = rng.uniform(0.5, 2.0, size=nu)
+    umin = -umax * rng.uniform(0.5, 1.0, size=nu)
+    np.random.seed(1)
+    ctl = _engine(p, cost, umin, umax, horizon=H, num_path=K, sigma=sigma, lmda=lmda, noise="numpy",
+                  precision="bf16")
+    assert ctl.precision == "bf16"
+    np.random.seed(1)
+    o = MPPIOracle(p, cost, umin, umax, horizon=H, num_path=K, sigma=sigma, lmda=lmda)
+    x0 = rng.normal(size=nx)
+    for _ in range(3):
+        eps = o.sample_eps()
+        # argmin is exact unless two samples are closer than the bf16 cost tolerance
+        ref_sorted = None
+        u, _ = _check_solve(ctl, o, x0, eps, TOL["bf16"], check_argmin=False)
+        costs, _t = ctl.last_costs()
+        ref = o.last_costs - o.term_const
+        ref_sorted = np.sort(ref)
+        if K > 1 and ref_sorted[1] - ref_sorted[0] > 4 * TOL["bf16"]["cost_rtol"] * abs(ref_sorted[0]):
+            assert int(np.argmin(costs)) == int(np.argmin(ref))
+        x0 = mlp_pred_batch(p, x0[None], u[None])[0]
+    ctl.close()
+
+
+def test_mppi_bf16_philox_equals_external_eps_and_fp32():
+    """Same Philox noise in both kernels: bf16 result within bf16 tolerance of the fp32 kernel and the oracle."""
+    p = synthetic_mlp(17, 6, [256, 256, 256], seed=2)
+    cost = QuadCostParams(np.eye(17), 0.01 * np.eye(6), 10 * np.eye(17))
+    kw = dict(horizon=20, num_path=1000, sigma=1.0, lmda=1.0, seed=77)
+    np.random.seed(0)
+    a = _engine(p, cost, -np.ones(6), np.ones(6), precision="bf16", **kw)
+    np.random.seed(0)
+    b = _engine(p, cost, -np.ones(6), np.ones(6), precision="bf16", **kw)
+    np.random.seed(0)
+    c = _engine(p, cost, -np.ones(6), np.ones(6), precision="fp32", **kw)
+    x0 = np.random.default_rng(3).normal(size=17)
+    eps = a.philox_noise().astype(np.float64)
+    np.testing.assert_array_equal(eps, c.philox_noise().astype(np.float64))     # one generator for both kernels
+    ua, ub, uc = a.solve(x0), b.solve(x0, eps=eps), c.solve(x0)
+    np.testing.assert_allclose(ua, ub, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(a.last_costs()[0], b.last_costs()[0], rtol=1e-6)
+    np.testing.assert_allclose(a.last_costs()[0], c.last_costs()[0], rtol=TOL["bf16"]["cost_rtol"])
+    np.testing.assert_allclose(ua, uc, rtol=0, atol=TOL["bf16"]["act_atol"])
+    for e in (a, b, c):
+        e.close()
+
+
+def test_mppi_full_size_c3_properties():
+    """BASELINE config 3 at full size (K=16384, H=50) on one GPU, checked through size-independent
+    properties: (i) the update is a convex combination of the clipped noise => every entry of
+    act_sequence - shift(act_sequence) lies inside the clip box; (ii) costs of the first 256 samples
+    equal a K=256 solve on the same global sample indices (samples are independent);
+    (iii) identical seeds => identical result; (iv) auto precision picks the tensor-core path."""
+    from autompc_b200.problems import halfcheetah_dim_problem
+    from autompc_b200 import MPPI, B200MLP
+    system, task, w, x0 = halfcheetah_dim_problem()
+    model = B200MLP(system, w)
+    np.random.seed(0)
+    big = MPPI(system, task, model, horizon=50, num_path=16384, seed=3)
+    assert big.precision == "bf16"
+    act0 = big.act_sequence
+    u1 = big.solve(x0)
+    costs_big, _ = big.last_costs()
+    shifted = np.concatenate([act0[1:], act0[-1:]])
+    upd = big.act_sequence - shifted
+    assert np.all(np.isfinite(upd)) and np.all(shifted + upd <= 1 + 1e-5) and np.all(shifted + upd >= -1 - 1e-5)
+    np.random.seed(0)
+    small = MPPI(system, task, model, horizon=50, num_path=256, seed=3)
+    small.solve(x0)
+    np.testing.assert_allclose(small.last_costs()[0], costs_big[:256], rtol=1e-6)
+    np.random.seed(0)
+    again = MPPI(system, task, model, horizon=50, num_path=16384, seed=3)
+    u2 = again.solve(x0)
+    np.testing.assert_array_equal(again.last_costs()[0], costs_big)
+    np.testing.assert_allclose(u1, u2, rtol=0, atol=1e-6)      # merge order of CTA partials may differ
+    for e in (big, small, again):
+        e.close()
