@@ -15,9 +15,19 @@
 // With CG=2 the kernel runs as CTA pairs (cta_group::2, UMMA M=256): each CTA keeps HALF of the
 // output neurons of every layer in its shared memory, which is what lets the 3x256 network
 // (283 KB of bf16 weights) stay resident; the leader CTA's single MMA thread issues for both.
-// Warps 0-3: samples/epilogue.  Warp 4: MMA issue + TMEM allocation.
-// Synchronisation is two mbarriers: bar_a (activations of a layer are in TMEM: 4 warps x CG CTAs
-// arrive) and bar_d (tcgen05.commit: the layer's accumulator is complete, multicast to the pair).
+// Warps 0-3 ("owners", thread t <-> sample t): noise, clipping, control/action cost, z-score,
+// integration.  Warps 4-7 ("helpers", thread 128+t <-> sample t): state cost.  Both groups share the
+// layer epilogues: warp w serves TMEM lane quarter w%4 and column half w/4 of every chunk.
+// Warp 8: MMA issue + TMEM allocation.
+// Pipelining inside the dependent GEMM chain.  Every GEMM is issued at full width (N up to 256: 16
+// tcgen05.mma of K=16 per 256-wide layer), accumulating alternately into two 256-column TMEM
+// buffers.  The epilogue of GEMM n reads D_n 64 columns at a time and writes the packed bf16
+// activations IN PLACE over the accumulator columns it has just consumed; each 64-column group is
+// one K-group of GEMM n+1, released to the issuer through its own mbarrier (bar_a[g]), so GEMM n+1
+// starts after the FIRST group is packed and only a quarter of each epilogue is exposed.
+// bar_d (tcgen05.commit, multicast to the CTA pair) = "accumulator of the GEMM complete".
+// Work that does not depend on the state (next step's noise, clipping, control cost) runs in the
+// shadow of the layer-1 MMAs.
 //
 // The clipped noise (mppi.py:139) of every (step, control, sample) is written to an L2-resident
 // scratch and re-read once the softmax weights are known (mppi.py:115-117); per-CTA partial records
@@ -31,20 +41,23 @@
 namespace {
 
 constexpr int TM = 128;              // samples per CTA
-constexpr int NTHR = 160;            // 4 sample warps + 1 MMA warp
+constexpr int NEPI = 256;            // 8 epilogue warps: 4 owner + 4 helper
+constexpr int NTHR = NEPI + 32;      // + 1 MMA warp
+constexpr int MMA_WARP = NEPI / 32;
 constexpr int TMEM_COLS = 512;
-constexpr int TMEM_D = 0;            // accumulator columns [0,256)
-constexpr int TMEM_A = 256;          // packed bf16 activations, columns [256,384)
+constexpr int TMEM_BUF = 256;        // two accumulator / activation buffers: columns [0,256) and [256,512)
 constexpr int MAXL = AMPC_MAX_LAYERS;
+constexpr int MAXG = 4;              // 64-element K-groups per layer (256 / 64)
 
 struct TcArgs {
   int n_layers;
-  int kpad[MAXL], npad[MAXL];        // padded K (multiple of 16) and N (multiple of 32) per layer
+  int kpad[MAXL], npad[MAXL];        // padded K (16s; hidden: 64s) and N (hidden: 64s; output: 32s) per layer
   uint32_t w_off[MAXL];              // byte offset of layer l's B image inside one CTA's weight image
   uint32_t w_bytes;                  // bytes of one CTA's weight image
   int b_off[MAXL];                   // float offset of the layer's (padded) bias
   int bias_floats;
-  uint32_t idesc[MAXL];              // UMMA instruction descriptors
+  uint32_t idesc[MAXL];              // UMMA instruction descriptors (N = chunk width)
+  int cw[MAXL], nch[MAXL];           // chunk width (32/64/128 columns) and chunks per layer
   const uint8_t *wimg;               // CG images back to back
   const float *bias;
   float *epsc;                       // (H*nu, Kc) clipped noise scratch
@@ -71,7 +84,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
       : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
@@ -121,30 +134,32 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   else
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(TMEM_COLS) : "memory");
 }
-// D[tmem] (+)= A[tmem, packed bf16] . B[smem desc]^T
+// D[tmem] (+)= A[tmem, packed bf16] . B[smem desc]^T ; executed by a converged warp, one elected lane issues
 template <int CG>
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate) {
   if constexpr (CG == 1)
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
   else
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   if constexpr (CG == 1)
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
   else
     asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar),
         "h"((uint16_t)3)
         : "memory");
 }
@@ -208,6 +223,38 @@ __device__ __forceinline__ float quad_full(const float *M, const float *v, const
   return c;
 }
 
+// bias + activation + bf16 pack of NV consecutive accumulator columns (NV = 16 or 32)
+template <int NV>
+__device__ __forceinline__ void epi_pack(const uint32_t (&r)[NV], const float *bias, int act, uint32_t (&pk)[NV / 2]) {
+  const float4 *b4 = reinterpret_cast<const float4 *>(bias);
+  if (act == AMPC_ACT_RELU) {
+#pragma unroll
+    for (int q = 0; q < NV / 4; ++q) {
+      const float4 b = b4[q];
+      const float2 v0 = __fadd2_rn(make_float2(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), make_float2(b.x, b.y));
+      const float2 v1 = __fadd2_rn(make_float2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])), make_float2(b.z, b.w));
+      pk[2 * q] = pack_bf16_relu(v0.x, v0.y);
+      pk[2 * q + 1] = pack_bf16_relu(v1.x, v1.y);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < NV / 4; ++q) {
+      const float4 b = b4[q];
+      pk[2 * q] = pack_bf16(ampc_act<float>(act, __uint_as_float(r[4 * q]) + b.x),
+                            ampc_act<float>(act, __uint_as_float(r[4 * q + 1]) + b.y));
+      pk[2 * q + 1] = pack_bf16(ampc_act<float>(act, __uint_as_float(r[4 * q + 2]) + b.z),
+                                ampc_act<float>(act, __uint_as_float(r[4 * q + 3]) + b.w));
+    }
+  }
+}
+
+// K-step ks (16 K-elements = 8 packed TMEM columns) of an activation matrix lives at this column offset:
+// 64-element groups stay in the 64 accumulator columns they were computed from, the two 32-element
+// halves (one per epilogue warp of a lane quarter) each at the start of their own 32 columns.
+__device__ __forceinline__ uint32_t a_kcol(int ks) {
+  return (uint32_t)((ks >> 2) * 64 + ((ks >> 1) & 1) * 32 + (ks & 1) * 8);
+}
+
 template <int CG>
 __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppiParams p, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -225,11 +272,11 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   float *s_act = s_const + cl.total;                   // shifted act_sequence (H*nu)
   float *s_x = s_act + ((HN + 3) & ~3);                // state [nx][128]
   float *s_u = s_x + nx * TM;                          // scaled control [nu][128]
-  float *s_wgt = s_u + nu * TM;                        // softmax numerators [128]
+  float *s_wgt = s_u + nu * TM;                        // helper cost share, then softmax numerators [128]
   float *s_red = s_wgt + TM;                           // 32
   float *s_misc = s_red + 32;                          // 64 + AMPC_MERGE_CACHE
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_misc + 64 + AMPC_MERGE_CACHE);   // [0]=bar_a [1]=bar_d
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_misc + 64 + AMPC_MERGE_CACHE);   // [0]=bar_d, [1..4]=bar_a[g]
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 1 + MAXG);
   __shared__ int s_last;
 
   {
@@ -246,13 +293,13 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   }
   if (tid < TM)
     for (int j = 0; j < nx; ++j) s_x[j * TM + tid] = p.x0[j];   // mppi.py:129-130
-  const uint32_t bar_a = smem_u32(&s_bar[0]), bar_d = smem_u32(&s_bar[1]);
+  const uint32_t bar_d = smem_u32(&s_bar[0]), bar_a0 = smem_u32(&s_bar[1]);
   if (tid == 0) {
-    mbar_init(bar_a, 4 * CG);
     mbar_init(bar_d, 1);
+    for (int g = 0; g < MAXG; ++g) mbar_init(bar_a0 + 8u * g, (NEPI / 32) * CG);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc<CG>(smem_u32(s_tmem));
+  if (warp == MMA_WARP) tmem_alloc<CG>(smem_u32(s_tmem));
   fence_proxy_async_smem();                            // weight image (generic-proxy stores) -> tensor-core reads
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -264,53 +311,73 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   const float *c_goal = s_const + cl.goal, *c_Q = s_const + cl.Q, *c_R = s_const + cl.R, *c_F = s_const + cl.F;
   const float *c_lo = s_const + cl.lo, *c_hi = s_const + cl.hi, *c_scale = s_const + cl.scale;
 
-  const int k_local = blockIdx.x * TM + tid;           // meaningful for tid < 128
-  const bool valid = (tid < TM) && (k_local < p.K);
+  const int t = tid & (TM - 1);                        // sample slot of this thread (owner or helper)
+  const int k_local = blockIdx.x * TM + t;
+  const bool valid = k_local < p.K;
   float cost_acc = 0.f;
 
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     // =========================== MMA issuer (leader CTA of the pair) ===========================
+    // The whole warp runs this loop with warp-uniform operands; one elected lane issues.
     if (cta_rank == 0) {
-      uint32_t ph = 0;
-      const uint32_t d_addr = tmem_base + TMEM_D, a_addr = tmem_base + TMEM_A;
+      uint32_t pa = 0;                                  // parity bit g of bar_a[g]
+      uint32_t n = 0;                                   // GEMM counter: D_n in buffer n&1, A_n in the other one
       const uint32_t w_addr = smem_u32(s_w);
       for (int i = 0; i < H; ++i) {
-        for (int l = 0; l < L; ++l) {
-          mbar_wait(bar_a, ph);
-          ph ^= 1u;
-          tc_fence_after();
-          if (lane == 0) {
-            const int rows = a.npad[l] / CG;            // B rows held by each CTA
-            const uint64_t d0 = make_b_desc(w_addr + a.w_off[l]);
-            const int nks = a.kpad[l] >> 4;
-            for (int ks = 0; ks < nks; ++ks) {
-              const uint32_t boff = (uint32_t)(ks >> 2) * (uint32_t)(rows * 128) + (uint32_t)(ks & 3) * 32u;
-              umma_ts<CG>(d_addr, a_addr + (uint32_t)ks * 8u, d0 + (uint64_t)(boff >> 4), a.idesc[l], ks > 0);
+        for (int l = 0; l < L; ++l, ++n) {
+          const int rows = a.npad[l] / CG;              // B rows held by each CTA (per 64-wide K block)
+          const int nks = a.kpad[l] >> 4;
+          const uint32_t idesc = a.idesc[l];
+          const uint32_t d_addr = tmem_base + (n & 1u) * TMEM_BUF;
+          const uint32_t a_addr = tmem_base + ((n + 1u) & 1u) * TMEM_BUF;
+          const uint32_t kb_stride = (uint32_t)(rows * 128) >> 4;
+          uint64_t desc = make_b_desc(w_addr + a.w_off[l]);
+          for (int g = 0; g * 4 < nks; ++g) {
+            mbar_wait(bar_a0 + 8u * g, (pa >> g) & 1u);
+            pa ^= (1u << g);
+            tc_fence_after();
+            const uint32_t ag = a_addr + (uint32_t)g * 64u;
+            if (g * 4 + 4 <= nks) {
+              umma_ts<CG>(d_addr, ag, desc, idesc, (uint32_t)(g > 0));
+              umma_ts<CG>(d_addr, ag + 8u, desc + 2u, idesc, 1u);
+              umma_ts<CG>(d_addr, ag + 32u, desc + 4u, idesc, 1u);
+              umma_ts<CG>(d_addr, ag + 40u, desc + 6u, idesc, 1u);
+            } else {
+              for (int j = 0; g * 4 + j < nks; ++j)
+                umma_ts<CG>(d_addr, a_addr + a_kcol(g * 4 + j), desc + (uint64_t)(2 * j), idesc, (uint32_t)((g * 4 + j) > 0));
             }
-            umma_commit<CG>(bar_d);
+            desc += kb_stride;
           }
+          umma_commit<CG>(bar_d);
           __syncwarp();
         }
       }
     }
   } else {
-    // =========================== sample threads (warps 0-3) ===========================
-    const int t = tid;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // =========================== epilogue warps: owners (0-3) and helpers (4-7) ===========================
+    const bool owner = warp < 4;
+    const int hf = warp >> 2;                           // which 32 of every 64 columns this warp serves
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t kg = (uint32_t)(p.k_offset + k_local);
     const int nblk = (nu + 3) >> 2;
     const int nin = nx + nu;
-    uint32_t ph = 0;
-    auto signal_a = [&]() {
+    uint32_t pd = 0;                                    // parity of bar_d
+    uint32_t n = 0;                                     // GEMM counter (see the issuer)
+    auto wait_d = [&]() {
+      mbar_wait(bar_d, pd);
+      pd ^= 1u;
+      tc_fence_after();
+    };
+    auto signal_a = [&](int g) {                        // "my part of activation group g is in TMEM, my D reads are done"
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_cluster(bar_a, 0u); else mbar_arrive_local(bar_a);
+        if constexpr (CG == 2) mbar_arrive_cluster(bar_a0 + 8u * g, 0u); else mbar_arrive_local(bar_a0 + 8u * g);
       }
     };
-    for (int i = 0; i < H; ++i) {
-      // ---- controls: noise, clip, write-back (mppi.py:134-139), action cost (:143)
+    // controls of step i: noise, clip, write-back (mppi.py:134-139), action cost (:143), control cost (:142)
+    auto prepare_controls = [&](int i) {
       for (int blk = 0; blk < nblk; ++blk) {
         float n4[4] = {0.f, 0.f, 0.f, 0.f};
         if (p.eps == nullptr) {
@@ -337,10 +404,10 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
           }
         }
       }
-      // ---- stage cost at the pre-step state (mppi.py:142; cost.py:79-81, :131-132)
-      cost_acc += quad_full(c_Q, s_x, c_goal, nx, p.q_diag, t);
       cost_acc += quad_full(c_R, s_u, nullptr, nu, p.r_diag, t);
-      // ---- z-score (mlp.py:20-24) -> bf16 -> A operand in TMEM
+    };
+    // layer-0 input: z-score (mlp.py:20-24) -> bf16 -> A operand columns of buffer `buf`
+    auto write_input = [&](uint32_t buf) {
       for (int g = 0; g < (a.kpad[0] >> 4); ++g) {
         uint32_t pk[8];
 #pragma unroll
@@ -356,45 +423,56 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
           }
           pk[q] = pack_bf16(z[0], z[1]);
         }
-        tmem_st8(lane_base + TMEM_A + g * 8, pk);
+        tmem_st8(lane_base + buf * TMEM_BUF + a_kcol(g), pk);
       }
-      signal_a();
-      // ---- hidden layers: D -> bias + activation -> bf16 -> A
-      for (int l = 0; l < L - 1; ++l) {
-        mbar_wait(bar_d, ph);
-        ph ^= 1u;
-        tc_fence_after();
+    };
+    if (owner) {
+      prepare_controls(0);
+      write_input(1u);                                  // GEMM 0 reads A from buffer 1
+    }
+    signal_a(0);
+
+    for (int i = 0; i < H; ++i) {
+      // ---- hidden layers: D (buffer n&1) -> bias + activation -> bf16, written IN PLACE over the consumed
+      //      accumulator columns; each 64-column group is released to the next GEMM as soon as it is packed
+      for (int l = 0; l < L - 1; ++l, ++n) {
         const float *bl = s_bias + a.b_off[l];
-        const int np = a.npad[l];
-        for (int c0 = 0; c0 < np; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(lane_base + TMEM_D + c0, r);
-          tc_wait_ld();
+        const int ng = a.npad[l] >> 6;
+        const uint32_t dbuf = lane_base + (n & 1u) * TMEM_BUF;
+        wait_d();
+        if (l == 0 && !owner && L < 3) cost_acc += quad_full(c_Q, s_x, c_goal, nx, p.q_diag, t);   // mppi.py:142
+        uint32_t ra[32], rb[32];                        // two register stages: the next group's LDTM overlaps the packing
+        auto finish = [&](const uint32_t (&r)[32], int g) {
           uint32_t pk[16];
-          if (p.act == AMPC_ACT_RELU) {
-#pragma unroll
-            for (int q = 0; q < 16; ++q)
-              pk[q] = pack_bf16_relu(__uint_as_float(r[2 * q]) + bl[c0 + 2 * q],
-                                     __uint_as_float(r[2 * q + 1]) + bl[c0 + 2 * q + 1]);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 16; ++q)
-              pk[q] = pack_bf16(ampc_act<float>(p.act, __uint_as_float(r[2 * q]) + bl[c0 + 2 * q]),
-                                ampc_act<float>(p.act, __uint_as_float(r[2 * q + 1]) + bl[c0 + 2 * q + 1]));
+          const int col = g * 64 + hf * 32;
+          epi_pack<32>(r, bl + col, p.act, pk);
+          tmem_st16(dbuf + col, pk);
+          signal_a(g);
+        };
+        tmem_ld32(dbuf + hf * 32, ra);
+        for (int g = 0; g < ng; g += 2) {
+          tc_wait_ld();
+          if (g + 1 < ng) tmem_ld32(dbuf + (g + 1) * 64 + hf * 32, rb);
+          finish(ra, g);
+          if (g + 1 < ng) {
+            tc_wait_ld();
+            if (g + 2 < ng) tmem_ld32(dbuf + (g + 2) * 64 + hf * 32, ra);
+            finish(rb, g + 1);
           }
-          tmem_st16(lane_base + TMEM_A + (c0 >> 1), pk);
         }
-        signal_a();
+        if (l == 0) {                                   // off the critical path: the layer-1 MMAs are running
+          if (owner) { if (i + 1 < H) prepare_controls(i + 1); }
+          else if (L >= 3) cost_acc += quad_full(c_Q, s_x, c_goal, nx, p.q_diag, t);               // mppi.py:142
+        }
       }
-      // ---- output layer: un-z-score + integrate (mlp.py:235-236)
-      mbar_wait(bar_d, ph);
-      ph ^= 1u;
-      tc_fence_after();
-      {
+      // ---- output layer: un-z-score + integrate (mlp.py:235-236), then the next step's input in place
+      wait_d();
+      if (owner) {
         const float *bl = s_bias + a.b_off[L - 1];
+        const uint32_t dbuf = lane_base + (n & 1u) * TMEM_BUF;
         for (int c0 = 0; c0 < a.npad[L - 1]; c0 += 32) {
           uint32_t r[32];
-          tmem_ld32(lane_base + TMEM_D + c0, r);
+          tmem_ld32(dbuf + c0, r);
           tc_wait_ld();
 #pragma unroll
           for (int q = 0; q < 32; ++q) {
@@ -402,15 +480,20 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
             if (j < nx) s_x[j * TM + t] += fmaf(__uint_as_float(r[q]) + bl[j], c_dys[j], c_dym[j]);
           }
         }
+        if (i + 1 < H) write_input(n & 1u);             // GEMM n+1 reads A from buffer n&1
       }
+      if (i + 1 < H) signal_a(0);
+      ++n;
     }
+    if (!owner) s_wgt[t] = cost_acc;                    // helper's share (state costs)
   }
 
   // =========================== softmax partials of this CTA (mppi.py:110-118) ===========================
+  __syncthreads();
   float c = INFINITY;
   if (tid < TM) {
     const float term = quad_full(c_F, s_x, c_goal, nx, p.f_diag, tid);   // mppi.py:79-82, :146-148
-    c = cost_acc;
+    c = cost_acc + s_wgt[tid];
     if (p.terminal_mode == 1) c += term;
     else if (valid && (p.k_offset + k_local) == p.K_global - 1) *p.term_out = term;
     if (valid) p.costs[k_local] = c; else c = INFINITY;
@@ -456,7 +539,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   // ---- teardown
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
-  if (warp == 4) tmem_dealloc<CG>(tmem_base);
+  if (warp == MMA_WARP) tmem_dealloc<CG>(tmem_base);
 }
 
 uint16_t f32_to_bf16(float f) {
@@ -471,10 +554,16 @@ size_t tc_smem_bytes(const TcArgs &a, int nx, int nu, int H) {
   const AmpcConstLayout cl(nx, nu);
   const size_t floats = (size_t)((a.bias_floats + 3) & ~3) + cl.total + ((H * nu + 3) & ~3) + (size_t)nx * TM +
                         (size_t)nu * TM + TM + 32 + 64 + AMPC_MERGE_CACHE;
-  return 1024 + a.w_bytes + floats * sizeof(float) + 2 * sizeof(uint64_t) + 16;
+  return 1024 + a.w_bytes + floats * sizeof(float) + (1 + MAXG) * sizeof(uint64_t) + 16;
 }
 
 int roundup(int v, int m) { return (v + m - 1) / m * m; }
+
+int chunk_width(int npad, bool last) {
+  // hidden layers are issued as N-chunks so that epilogues overlap the remaining MMAs; the output layer is one chunk
+  (void)last;
+  return npad;                        // every GEMM is issued at full width
+}
 
 void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg) {
   memset(&a, 0, sizeof(a));
@@ -483,14 +572,16 @@ void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg) {
   int boff = 0;
   for (int l = 0; l < mlp->n_layers; ++l) {
     a.kpad[l] = (l == 0) ? roundup(mlp->dims[0], 16) : a.npad[l - 1];
-    a.npad[l] = roundup(mlp->dims[l + 1], 32);
+    a.npad[l] = (l == mlp->n_layers - 1) ? roundup(mlp->dims[l + 1], 32) : roundup(mlp->dims[l + 1], 64);
     const int rows = a.npad[l] / cg, kblk = (a.kpad[l] + 63) / 64;
     a.w_off[l] = off;
     off += (uint32_t)kblk * rows * 128;
     a.b_off[l] = boff;
     boff += a.npad[l];
     // kind::f16: c=f32 (bit 4), a=bf16 (bit 7), b=bf16 (bit 10), both K-major, N>>3 at 17, M>>4 at 24
-    a.idesc[l] = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.npad[l] >> 3) << 17) |
+    a.cw[l] = chunk_width(a.npad[l], l == mlp->n_layers - 1);
+    a.nch[l] = a.npad[l] / a.cw[l];
+    a.idesc[l] = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.cw[l] >> 3) << 17) |
                  ((uint32_t)((TM * cg) >> 4) << 24);
   }
   a.w_bytes = off;
@@ -593,8 +684,10 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
           for (int ch = 0; ch < 8; ++ch) {
             const size_t byte = (size_t)r * a.w_bytes + a.w_off[l] + (size_t)kb * rows * 128 + (size_t)n * 128 +
                                 (size_t)((ch ^ (n & 7)) * 16);
+            const int crow = a.cw[l] / cg;      // rows of one chunk held by each CTA
+            const int ng = (n / crow) * a.cw[l] + r * crow + (n % crow);   // D column (= neuron) of local row n
             for (int e = 0; e < 8; ++e) {
-              const int k = kb * 64 + ch * 8 + e, ng = r * rows + n;
+              const int k = kb * 64 + ch * 8 + e;
               const float v = (ng < Nl && k < Kl) ? (float)mlp->W[l][(size_t)ng * Kl + k] : 0.f;
               img[byte / 2 + e] = f32_to_bf16(v);
             }
