@@ -47,7 +47,7 @@ constexpr int MMA_WARP = NEPI / 32;
 constexpr int TMEM_COLS = 512;
 constexpr int TMEM_BUF = 256;        // two accumulator / activation buffers: columns [0,256) and [256,512)
 constexpr int MAXL = AMPC_MAX_LAYERS;
-constexpr int MAXG = 4;              // 64-element K-groups per layer (256 / 64)
+constexpr int MAXG = 2;              // N-halves of a GEMM = K-pairs of the next one
 
 struct TcArgs {
   int n_layers;
@@ -57,7 +57,9 @@ struct TcArgs {
   int b_off[MAXL];                   // float offset of the layer's (padded) bias
   int bias_floats;
   uint32_t idesc[MAXL];              // UMMA instruction descriptors (N = chunk width)
-  int cw[MAXL], nch[MAXL];           // chunk width (32/64/128 columns) and chunks per layer
+  int cw[MAXL], nch[MAXL];           // = hwid, nh (kept for the weight-image row permutation)
+  int nh[MAXL], hwid[MAXL];          // N-halves of the layer's GEMM and their width (npad / nh)
+  int nkp[MAXL], awid[MAXL];         // K-pairs of the layer's GEMM and their width in K elements
   const uint8_t *wimg;               // CG images back to back
   const float *bias;
   float *epsc;                       // (H*nu, Kc) clipped noise scratch
@@ -248,11 +250,18 @@ __device__ __forceinline__ void epi_pack(const uint32_t (&r)[NV], const float *b
   }
 }
 
-// K-step ks (16 K-elements = 8 packed TMEM columns) of an activation matrix lives at this column offset:
-// 64-element groups stay in the 64 accumulator columns they were computed from, the two 32-element
-// halves (one per epilogue warp of a lane quarter) each at the start of their own 32 columns.
-__device__ __forceinline__ uint32_t a_kcol(int ks) {
-  return (uint32_t)((ks >> 2) * 64 + ((ks >> 1) & 1) * 32 + (ks & 1) * 8);
+// Issues the KSP K-steps of one K-pair of one N-half, fully unrolled with compile-time column offsets:
+// the pair's K elements sit in two sub-halves (one per epilogue warp of a lane quarter), each packed at the
+// start of its own KSP*8 accumulator columns.
+template <int CG, int KSP>
+__device__ __forceinline__ void issue_pair(uint32_t dh, uint32_t a_pair, uint64_t desc_pair, uint32_t kb_stride,
+                                           uint32_t idesc, bool first_pair) {
+#pragma unroll
+  for (int j = 0; j < KSP; ++j) {
+    const uint32_t acol = (uint32_t)((j / (KSP / 2)) * (KSP * 8) + (j % (KSP / 2)) * 8);
+    const uint64_t d = desc_pair + (uint64_t)((uint32_t)(j >> 2) * kb_stride + (uint32_t)(j & 3) * 2u);
+    umma_ts<CG>(dh, a_pair + acol, d, idesc, (j == 0 && first_pair) ? 0u : 1u);
+  }
 }
 
 template <int CG>
@@ -275,8 +284,8 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   float *s_wgt = s_u + nu * TM;                        // helper cost share, then softmax numerators [128]
   float *s_red = s_wgt + TM;                           // 32
   float *s_misc = s_red + 32;                          // 64 + AMPC_MERGE_CACHE
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_misc + 64 + AMPC_MERGE_CACHE);   // [0]=bar_d, [1..4]=bar_a[g]
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 1 + MAXG);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_misc + 64 + AMPC_MERGE_CACHE);   // [0..1]=bar_d[h], [2..3]=bar_a[kp]
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2 * MAXG);
   __shared__ int s_last;
 
   {
@@ -293,9 +302,9 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   }
   if (tid < TM)
     for (int j = 0; j < nx; ++j) s_x[j * TM + tid] = p.x0[j];   // mppi.py:129-130
-  const uint32_t bar_d = smem_u32(&s_bar[0]), bar_a0 = smem_u32(&s_bar[1]);
+  const uint32_t bar_d0 = smem_u32(&s_bar[0]), bar_a0 = smem_u32(&s_bar[MAXG]);
   if (tid == 0) {
-    mbar_init(bar_d, 1);
+    for (int g = 0; g < MAXG; ++g) mbar_init(bar_d0 + 8u * g, 1);
     for (int g = 0; g < MAXG; ++g) mbar_init(bar_a0 + 8u * g, (NEPI / 32) * CG);
     fence_mbar_init();
   }
@@ -319,36 +328,44 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   if (warp == MMA_WARP) {
     // =========================== MMA issuer (leader CTA of the pair) ===========================
     // The whole warp runs this loop with warp-uniform operands; one elected lane issues.
+    // GEMM n = (step, layer).  Its N is issued as nh halves (one commit each: bar_d[h]); its K as nkp
+    // pairs, pair kp being exactly what the epilogue of half kp of GEMM n-1 produced (bar_a[kp]).
+    // Issue order (h0,kp0) (h1,kp0) | (h0,kp1)+commit (h1,kp1)+commit keeps the tensor pipe busy with the
+    // kp0 work of GEMM n while the epilogue of half 1 of GEMM n-1 is still running.
     if (cta_rank == 0) {
-      uint32_t pa = 0;                                  // parity bit g of bar_a[g]
+      uint32_t pa = 0;                                  // parity bit kp of bar_a[kp]
       uint32_t n = 0;                                   // GEMM counter: D_n in buffer n&1, A_n in the other one
       const uint32_t w_addr = smem_u32(s_w);
       for (int i = 0; i < H; ++i) {
         for (int l = 0; l < L; ++l, ++n) {
           const int rows = a.npad[l] / CG;              // B rows held by each CTA (per 64-wide K block)
-          const int nks = a.kpad[l] >> 4;
+          const int nks = a.kpad[l] >> 4, nh = a.nh[l], nkp = a.nkp[l];
+          const int ksp = a.awid[l] >> 4;               // K-steps per pair
+          const uint32_t hrow_off = (uint32_t)((a.hwid[l] / CG) * 128) >> 4;   // B rows of one N-half (descriptor units)
           const uint32_t idesc = a.idesc[l];
           const uint32_t d_addr = tmem_base + (n & 1u) * TMEM_BUF;
           const uint32_t a_addr = tmem_base + ((n + 1u) & 1u) * TMEM_BUF;
           const uint32_t kb_stride = (uint32_t)(rows * 128) >> 4;
-          uint64_t desc = make_b_desc(w_addr + a.w_off[l]);
-          for (int g = 0; g * 4 < nks; ++g) {
-            mbar_wait(bar_a0 + 8u * g, (pa >> g) & 1u);
-            pa ^= (1u << g);
+          const uint64_t lbase = make_b_desc(w_addr + a.w_off[l]);
+          for (int kp = 0; kp < nkp; ++kp) {
+            mbar_wait(bar_a0 + 8u * kp, (pa >> kp) & 1u);
+            pa ^= (1u << kp);
             tc_fence_after();
-            const uint32_t ag = a_addr + (uint32_t)g * 64u;
-            if (g * 4 + 4 <= nks) {
-              umma_ts<CG>(d_addr, ag, desc, idesc, (uint32_t)(g > 0));
-              umma_ts<CG>(d_addr, ag + 8u, desc + 2u, idesc, 1u);
-              umma_ts<CG>(d_addr, ag + 32u, desc + 4u, idesc, 1u);
-              umma_ts<CG>(d_addr, ag + 40u, desc + 6u, idesc, 1u);
-            } else {
-              for (int j = 0; g * 4 + j < nks; ++j)
-                umma_ts<CG>(d_addr, a_addr + a_kcol(g * 4 + j), desc + (uint64_t)(2 * j), idesc, (uint32_t)((g * 4 + j) > 0));
+            const uint32_t a_pair = a_addr + (uint32_t)(kp * a.awid[l]);
+            const uint32_t pair_off = (uint32_t)((kp * ksp) >> 2) * kb_stride;
+            for (int h = 0; h < nh; ++h) {
+              const uint32_t dh = d_addr + (uint32_t)(h * a.hwid[l]);
+              const uint64_t hb = lbase + (uint64_t)(hrow_off * (uint32_t)h + pair_off);
+              if (l > 0 && ksp == 8) issue_pair<CG, 8>(dh, a_pair, hb, kb_stride, idesc, kp == 0);
+              else if (l > 0) issue_pair<CG, 4>(dh, a_pair, hb, kb_stride, idesc, kp == 0);
+              else {
+                for (int ks = 0; ks < nks; ++ks)       // input layer: 1..4 K-steps at columns {0, 8, 32, 40}
+                  umma_ts<CG>(dh, a_pair + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8), hb + (uint64_t)(ks * 2), idesc,
+                              (uint32_t)(ks > 0));
+              }
+              if (kp == nkp - 1) umma_commit<CG>(bar_d0 + 8u * h);
             }
-            desc += kb_stride;
           }
-          umma_commit<CG>(bar_d);
           __syncwarp();
         }
       }
@@ -361,11 +378,11 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
     const uint32_t kg = (uint32_t)(p.k_offset + k_local);
     const int nblk = (nu + 3) >> 2;
     const int nin = nx + nu;
-    uint32_t pd = 0;                                    // parity of bar_d
+    uint32_t pd = 0;                                    // parity bit h of bar_d[h]
     uint32_t n = 0;                                     // GEMM counter (see the issuer)
-    auto wait_d = [&]() {
-      mbar_wait(bar_d, pd);
-      pd ^= 1u;
+    auto wait_d = [&](int h) {
+      mbar_wait(bar_d0 + 8u * h, (pd >> h) & 1u);
+      pd ^= (1u << h);
       tc_fence_after();
     };
     auto signal_a = [&](int g) {                        // "my part of activation group g is in TMEM, my D reads are done"
@@ -423,7 +440,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
           }
           pk[q] = pack_bf16(z[0], z[1]);
         }
-        tmem_st8(lane_base + buf * TMEM_BUF + a_kcol(g), pk);
+        tmem_st8(lane_base + buf * TMEM_BUF + (uint32_t)((g >> 1) * 32 + (g & 1) * 8), pk);
       }
     };
     if (owner) {
@@ -437,28 +454,28 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
       //      accumulator columns; each 64-column group is released to the next GEMM as soon as it is packed
       for (int l = 0; l < L - 1; ++l, ++n) {
         const float *bl = s_bias + a.b_off[l];
-        const int ng = a.npad[l] >> 6;
+        const int nh = a.nh[l], hwid = a.hwid[l], sw = hwid >> 1;
         const uint32_t dbuf = lane_base + (n & 1u) * TMEM_BUF;
-        wait_d();
-        if (l == 0 && !owner && L < 3) cost_acc += quad_full(c_Q, s_x, c_goal, nx, p.q_diag, t);   // mppi.py:142
-        uint32_t ra[32], rb[32];                        // two register stages: the next group's LDTM overlaps the packing
-        auto finish = [&](const uint32_t (&r)[32], int g) {
-          uint32_t pk[16];
-          const int col = g * 64 + hf * 32;
-          epi_pack<32>(r, bl + col, p.act, pk);
-          tmem_st16(dbuf + col, pk);
-          signal_a(g);
-        };
-        tmem_ld32(dbuf + hf * 32, ra);
-        for (int g = 0; g < ng; g += 2) {
+        for (int h = 0; h < nh; ++h) {
+          wait_d(h);
+          if (l == 0 && h == 0 && !owner && L < 3) cost_acc += quad_full(c_Q, s_x, c_goal, nx, p.q_diag, t);   // mppi.py:142
+          const int c0 = h * hwid + hf * sw;            // this warp's sw (32 or 64) columns of the half
+          uint32_t ra[32], pk[16];
+          tmem_ld32(dbuf + c0, ra);
           tc_wait_ld();
-          if (g + 1 < ng) tmem_ld32(dbuf + (g + 1) * 64 + hf * 32, rb);
-          finish(ra, g);
-          if (g + 1 < ng) {
+          if (sw == 64) {
+            uint32_t rb[32];
+            tmem_ld32(dbuf + c0 + 32, rb);
+            epi_pack<32>(ra, bl + c0, p.act, pk);
+            tmem_st16(dbuf + c0, pk);
             tc_wait_ld();
-            if (g + 2 < ng) tmem_ld32(dbuf + (g + 2) * 64 + hf * 32, ra);
-            finish(rb, g + 1);
+            epi_pack<32>(rb, bl + c0 + 32, p.act, pk);
+            tmem_st16(dbuf + c0 + 16, pk);
+          } else {
+            epi_pack<32>(ra, bl + c0, p.act, pk);
+            tmem_st16(dbuf + c0, pk);
           }
+          signal_a(h);
         }
         if (l == 0) {                                   // off the critical path: the layer-1 MMAs are running
           if (owner) { if (i + 1 < H) prepare_controls(i + 1); }
@@ -466,7 +483,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
         }
       }
       // ---- output layer: un-z-score + integrate (mlp.py:235-236), then the next step's input in place
-      wait_d();
+      wait_d(0);
       if (owner) {
         const float *bl = s_bias + a.b_off[L - 1];
         const uint32_t dbuf = lane_base + (n & 1u) * TMEM_BUF;
@@ -554,15 +571,15 @@ size_t tc_smem_bytes(const TcArgs &a, int nx, int nu, int H) {
   const AmpcConstLayout cl(nx, nu);
   const size_t floats = (size_t)((a.bias_floats + 3) & ~3) + cl.total + ((H * nu + 3) & ~3) + (size_t)nx * TM +
                         (size_t)nu * TM + TM + 32 + 64 + AMPC_MERGE_CACHE;
-  return 1024 + a.w_bytes + floats * sizeof(float) + (1 + MAXG) * sizeof(uint64_t) + 16;
+  return 1024 + a.w_bytes + floats * sizeof(float) + 2 * MAXG * sizeof(uint64_t) + 16;
 }
 
 int roundup(int v, int m) { return (v + m - 1) / m * m; }
 
 int chunk_width(int npad, bool last) {
   // hidden layers are issued as N-chunks so that epilogues overlap the remaining MMAs; the output layer is one chunk
-  (void)last;
-  return npad;                        // every GEMM is issued at full width
+  if (last || npad < 128) return npad;
+  return npad / 2;                    // hidden GEMMs of width >= 128 are issued as two N-halves
 }
 
 void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg) {
@@ -572,7 +589,10 @@ void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg) {
   int boff = 0;
   for (int l = 0; l < mlp->n_layers; ++l) {
     a.kpad[l] = (l == 0) ? roundup(mlp->dims[0], 16) : a.npad[l - 1];
-    a.npad[l] = (l == mlp->n_layers - 1) ? roundup(mlp->dims[l + 1], 32) : roundup(mlp->dims[l + 1], 64);
+    {
+      const int nl = mlp->dims[l + 1];
+      a.npad[l] = (l == mlp->n_layers - 1) ? roundup(nl, 32) : (nl <= 64 ? 64 : (nl <= 128 ? 128 : 256));
+    }
     const int rows = a.npad[l] / cg, kblk = (a.kpad[l] + 63) / 64;
     a.w_off[l] = off;
     off += (uint32_t)kblk * rows * 128;
@@ -581,6 +601,10 @@ void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg) {
     // kind::f16: c=f32 (bit 4), a=bf16 (bit 7), b=bf16 (bit 10), both K-major, N>>3 at 17, M>>4 at 24
     a.cw[l] = chunk_width(a.npad[l], l == mlp->n_layers - 1);
     a.nch[l] = a.npad[l] / a.cw[l];
+    a.nh[l] = a.nch[l];
+    a.hwid[l] = a.cw[l];
+    a.nkp[l] = (l == 0) ? 1 : a.nh[l - 1];
+    a.awid[l] = (l == 0) ? 64 : a.hwid[l - 1];
     a.idesc[l] = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.cw[l] >> 3) << 17) |
                  ((uint32_t)((TM * cg) >> 4) << 24);
   }
