@@ -68,11 +68,18 @@ __device__ __forceinline__ void ampc_normal4(uint64_t seed, uint64_t ctr, uint32
   for (int q = 0; q < 2; ++q) {
     const float u1 = (float)((r[2 * q] >> 8) + 1u) * inv24;  // (0,1]
     const float u2 = (float)(r[2 * q + 1] >> 8) * inv24;     // [0,1)
+#ifdef __CUDA_ARCH__
+    // SFU path: lg2 / sin / cos approximations (abs error ~1e-6 on the unit normal, checked against the
+    // float64 restatement in oracle/philox.py); the angle is reduced to [-pi, pi) first.
+    const float rad = sqrtf(-1.3862943611198906f * __log2f(u1));
+    const float ang = 6.283185307179586f * (u2 - 0.5f);
+    n[2 * q] = -rad * __cosf(ang);
+    n[2 * q + 1] = -rad * __sinf(ang);
+#else
     const float rad = sqrtf(-2.0f * logf(u1));
-    float s, c;
-    sincospif(2.0f * u2, &s, &c);
-    n[2 * q] = rad * c;
-    n[2 * q + 1] = rad * s;
+    n[2 * q] = rad * cosf(6.283185307179586f * u2);
+    n[2 * q + 1] = rad * sinf(6.283185307179586f * u2);
+#endif
   }
 }
 

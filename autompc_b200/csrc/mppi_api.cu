@@ -34,6 +34,7 @@ int ampc_mppi_tc_create(AmpcTcPlan **plan, const ampc_mppi_cfg *cfg, const ampc_
 void ampc_mppi_tc_destroy(AmpcTcPlan *plan);
 int ampc_mppi_tc_grid(const AmpcTcPlan *plan);
 int ampc_mppi_tc_launch(AmpcTcPlan *plan, const AmpcMppiParams &p, cudaStream_t stream);
+int ampc_mppi_tc_trace(AmpcTcPlan *plan, unsigned long long *host, int max_words);
 
 // ------------------------------------------------------------------- handle ---
 struct ampc_mppi {
@@ -417,4 +418,12 @@ extern "C" int ampc_mppi_merge(ampc_mppi *h, const float *dev_records, int32_t n
   ampc_count_launch();
   AMPC_CUDA_CHECK(cudaGetLastError());
   return AMPC_OK;
+}
+
+// Debug tap (not part of the reference surface): timeline of CTA 0 of the tcgen05 kernel when the handle was
+// created with AMPC_TC_TRACE=1 in the environment.  Returns the number of 64-bit words written.
+extern "C" int ampc_mppi_debug_trace(ampc_mppi *h, unsigned long long *host, int32_t max_words) {
+  if (!h || !h->tc || !host) return 0;
+  DeviceGuard g(h->device);
+  return ampc_mppi_tc_trace(h->tc, host, max_words);
 }

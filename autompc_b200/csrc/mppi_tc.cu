@@ -47,6 +47,7 @@ constexpr int MMA_WARP = NEPI / 32;
 constexpr int TMEM_COLS = 512;
 constexpr int TMEM_BUF = 256;        // two accumulator / activation buffers: columns [0,256) and [256,512)
 constexpr int MAXL = AMPC_MAX_LAYERS;
+constexpr int TRACE_EV = 64;
 constexpr int MAXG = 2;              // N-halves of a GEMM = K-pairs of the next one
 
 struct TcArgs {
@@ -64,6 +65,8 @@ struct TcArgs {
   const float *bias;
   float *epsc;                       // (H*nu, Kc) clipped noise scratch
   int Kc;                            // grid * 128
+  int nxp;                           // padded state width (kernel template): input K columns [0,nxp) = state
+  unsigned long long *trace;         // debug timeline (AMPC_TC_TRACE=1), else null: [warp][event] = clock<<8 | tag
 };
 
 // ------------------------------------------------------------------ PTX wrappers ---
@@ -264,7 +267,7 @@ __device__ __forceinline__ void issue_pair(uint32_t dh, uint32_t a_pair, uint64_
   }
 }
 
-template <int CG>
+template <int CG, int NXP>
 __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppiParams p, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -281,7 +284,9 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   float *s_act = s_const + cl.total;                   // shifted act_sequence (H*nu)
   float *s_x = s_act + ((HN + 3) & ~3);                // state [nx][128]
   float *s_u = s_x + nx * TM;                          // scaled control [nu][128]
-  float *s_wgt = s_u + nu * TM;                        // helper cost share, then softmax numerators [128]
+  float2 *s_zc = reinterpret_cast<float2 *>(s_u + ((nu * TM + 3) & ~3));   // input z-score as (scale, bias) per K column [64]
+  float2 *s_ic = s_zc + 64;                            // integration as (dy_std, b_out*dy_std + dy_mean) per state [32]
+  float *s_wgt = reinterpret_cast<float *>(s_ic + 32); // helper cost share, then softmax numerators [128]
   float *s_red = s_wgt + TM;                           // 32
   float *s_misc = s_red + 32;                          // 64 + AMPC_MERGE_CACHE
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_misc + 64 + AMPC_MERGE_CACHE);   // [0..1]=bar_d[h], [2..3]=bar_a[kp]
@@ -302,6 +307,25 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   }
   if (tid < TM)
     for (int j = 0; j < nx; ++j) s_x[j * TM + tid] = p.x0[j];   // mppi.py:129-130
+  // K column k of the input layer: k < NXP -> state k (zero beyond nx); NXP <= k < NXP+nu -> control k-NXP
+  // (the weight image uses the same permutation).  z = v * scale + bias  (mlp.py:20-24).
+  for (int k = tid; k < 64; k += NTHR) {
+    const int j = (k < NXP) ? (k < nx ? k : -1) : (k - NXP < nu ? nx + (k - NXP) : -1);
+    float2 zc = make_float2(0.f, 0.f);
+    if (j >= 0) {
+      const float inv = p.consts[cl.xu_inv + j];
+      zc = make_float2(inv, -p.consts[cl.xu_mean + j] * inv);
+    }
+    s_zc[k] = zc;
+  }
+  for (int j = tid; j < 32; j += NTHR) {                // x' = x + (y + b) * dy_std + dy_mean   (mlp.py:26-30, :236)
+    float2 ic = make_float2(0.f, 0.f);
+    if (j < nx) {
+      const float ds = p.consts[cl.dy_std + j];
+      ic = make_float2(ds, fmaf(a.bias[a.b_off[L - 1] + j], ds, p.consts[cl.dy_mean + j]));
+    }
+    s_ic[j] = ic;
+  }
   const uint32_t bar_d0 = smem_u32(&s_bar[0]), bar_a0 = smem_u32(&s_bar[MAXG]);
   if (tid == 0) {
     for (int g = 0; g < MAXG; ++g) mbar_init(bar_d0 + 8u * g, 1);
@@ -314,9 +338,13 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  // debug timeline of CTA 0: up to TRACE_EV events per warp (steps 10 and 11), tag = kind*16 + index
+  int trace_n = 0;
+  auto trace = [&](int step, int tag) {
+    if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && step >= 10 && step < 12 && trace_n < TRACE_EV)
+      a.trace[warp * TRACE_EV + trace_n++] = ((unsigned long long)clock64() << 8) | (unsigned long long)(tag & 255);
+  };
 
-  const float *c_mean = s_const + cl.xu_mean, *c_inv = s_const + cl.xu_inv;
-  const float *c_dym = s_const + cl.dy_mean, *c_dys = s_const + cl.dy_std;
   const float *c_goal = s_const + cl.goal, *c_Q = s_const + cl.Q, *c_R = s_const + cl.R, *c_F = s_const + cl.F;
   const float *c_lo = s_const + cl.lo, *c_hi = s_const + cl.hi, *c_scale = s_const + cl.scale;
 
@@ -351,6 +379,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
             mbar_wait(bar_a0 + 8u * kp, (pa >> kp) & 1u);
             pa ^= (1u << kp);
             tc_fence_after();
+            trace(i, 0x10 + l * 2 + kp);                // bar_a[kp] of layer l observed
             const uint32_t a_pair = a_addr + (uint32_t)(kp * a.awid[l]);
             const uint32_t pair_off = (uint32_t)((kp * ksp) >> 2) * kb_stride;
             for (int h = 0; h < nh; ++h) {
@@ -358,12 +387,14 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
               const uint64_t hb = lbase + (uint64_t)(hrow_off * (uint32_t)h + pair_off);
               if (l > 0 && ksp == 8) issue_pair<CG, 8>(dh, a_pair, hb, kb_stride, idesc, kp == 0);
               else if (l > 0) issue_pair<CG, 4>(dh, a_pair, hb, kb_stride, idesc, kp == 0);
-              else {
-                for (int ks = 0; ks < nks; ++ks)       // input layer: 1..4 K-steps at columns {0, 8, 32, 40}
-                  umma_ts<CG>(dh, a_pair + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8), hb + (uint64_t)(ks * 2), idesc,
-                              (uint32_t)(ks > 0));
+              else {                                  // input layer: 1..4 K-steps at columns {0, 8, 32, 40}
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  if (ks < nks)
+                    umma_ts<CG>(dh, a_pair + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8), hb + (uint64_t)(ks * 2), idesc,
+                                ks > 0 ? 1u : 0u);
               }
-              if (kp == nkp - 1) umma_commit<CG>(bar_d0 + 8u * h);
+              if (kp == nkp - 1) { umma_commit<CG>(bar_d0 + 8u * h); trace(i, 0x20 + l * 2 + h); }   // half h committed
             }
           }
           __syncwarp();
@@ -423,24 +454,32 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
       }
       cost_acc += quad_full(c_R, s_u, nullptr, nu, p.r_diag, t);
     };
+    // the sample's state lives in its owner's registers (a shared-memory copy feeds the cost evaluations)
+    float x[NXP];
+#pragma unroll
+    for (int j = 0; j < NXP; ++j) x[j] = (owner && j < nx) ? s_x[j * TM + t] : 0.f;
     // layer-0 input: z-score (mlp.py:20-24) -> bf16 -> A operand columns of buffer `buf`
     auto write_input = [&](uint32_t buf) {
-      for (int g = 0; g < (a.kpad[0] >> 4); ++g) {
-        uint32_t pk[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float z[2];
+      for (int g = 0; g < 4; ++g) {
+        if (g * 16 < a.kpad[0]) {
+          uint32_t pk[8];
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int j = g * 16 + q * 2 + hh;
-            float v = 0.f;
-            if (j < nx) v = (s_x[j * TM + t] - c_mean[j]) * c_inv[j];
-            else if (j < nin) v = (s_u[(j - nx) * TM + t] - c_mean[j]) * c_inv[j];
-            z[hh] = v;
+          for (int q = 0; q < 8; ++q) {
+            float z[2];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int k = g * 16 + q * 2 + hh;
+              const float2 zc = s_zc[k];
+              float v;
+              if (k < NXP) v = x[k < NXP ? k : 0];
+              else v = (k - NXP < nu) ? s_u[(k - NXP) * TM + t] : 0.f;
+              z[hh] = fmaf(v, zc.x, zc.y);
+            }
+            pk[q] = pack_bf16(z[0], z[1]);
           }
-          pk[q] = pack_bf16(z[0], z[1]);
+          tmem_st8(lane_base + buf * TMEM_BUF + (uint32_t)((g >> 1) * 32 + (g & 1) * 8), pk);
         }
-        tmem_st8(lane_base + buf * TMEM_BUF + (uint32_t)((g >> 1) * 32 + (g & 1) * 8), pk);
       }
     };
     if (owner) {
@@ -458,6 +497,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
         const uint32_t dbuf = lane_base + (n & 1u) * TMEM_BUF;
         for (int h = 0; h < nh; ++h) {
           wait_d(h);
+          trace(i, 0x30 + l * 2 + h);                   // bar_d[h] of layer l observed
           if (l == 0 && h == 0 && !owner && L < 3) cost_acc += quad_full(c_Q, s_x, c_goal, nx, p.q_diag, t);   // mppi.py:142
           const int c0 = h * hwid + hf * sw;            // this warp's sw (32 or 64) columns of the half
           uint32_t ra[32], pk[16];
@@ -476,6 +516,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
             tmem_st16(dbuf + c0, pk);
           }
           signal_a(h);
+          trace(i, 0x40 + l * 2 + h);                   // half h packed and released
         }
         if (l == 0) {                                   // off the critical path: the layer-1 MMAs are running
           if (owner) { if (i + 1 < H) prepare_controls(i + 1); }
@@ -484,22 +525,26 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
       }
       // ---- output layer: un-z-score + integrate (mlp.py:235-236), then the next step's input in place
       wait_d(0);
+      trace(i, 0x30 + (L - 1) * 2);
       if (owner) {
-        const float *bl = s_bias + a.b_off[L - 1];
         const uint32_t dbuf = lane_base + (n & 1u) * TMEM_BUF;
-        for (int c0 = 0; c0 < a.npad[L - 1]; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(dbuf + c0, r);
-          tc_wait_ld();
+        uint32_t r[32];
+        tmem_ld32(dbuf, r);
+        tc_wait_ld();
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const int j = c0 + q;
-            if (j < nx) s_x[j * TM + t] += fmaf(__uint_as_float(r[q]) + bl[j], c_dys[j], c_dym[j]);
-          }
+        for (int j = 0; j < NXP; ++j) {
+          const float2 ic = s_ic[j];
+          x[j] = fmaf(__uint_as_float(r[j]), ic.x, x[j] + ic.y);
         }
         if (i + 1 < H) write_input(n & 1u);             // GEMM n+1 reads A from buffer n&1
       }
       if (i + 1 < H) signal_a(0);
+      trace(i, 0x50);                                   // next input released
+      if (owner) {                                      // shared copy for the helpers' stage cost / the terminal cost
+#pragma unroll
+        for (int j = 0; j < NXP; ++j)
+          if (j < nx) s_x[j * TM + t] = x[j];
+      }
       ++n;
     }
     if (!owner) s_wgt[t] = cost_acc;                    // helper's share (state costs)
@@ -570,7 +615,7 @@ uint16_t f32_to_bf16(float f) {
 size_t tc_smem_bytes(const TcArgs &a, int nx, int nu, int H) {
   const AmpcConstLayout cl(nx, nu);
   const size_t floats = (size_t)((a.bias_floats + 3) & ~3) + cl.total + ((H * nu + 3) & ~3) + (size_t)nx * TM +
-                        (size_t)nu * TM + TM + 32 + 64 + AMPC_MERGE_CACHE;
+                        (size_t)((nu * TM + 3) & ~3) + 2 * 64 + 2 * 32 + TM + 32 + 64 + AMPC_MERGE_CACHE;
   return 1024 + a.w_bytes + floats * sizeof(float) + 2 * MAXG * sizeof(uint64_t) + 16;
 }
 
@@ -585,10 +630,14 @@ int chunk_width(int npad, bool last) {
 void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg) {
   memset(&a, 0, sizeof(a));
   a.n_layers = mlp->n_layers;
+  {
+    const int nx = mlp->dims[mlp->n_layers];
+    a.nxp = nx <= 4 ? 4 : (nx <= 8 ? 8 : (nx <= 16 ? 16 : (nx <= 24 ? 24 : 32)));
+  }
   uint32_t off = 0;
   int boff = 0;
   for (int l = 0; l < mlp->n_layers; ++l) {
-    a.kpad[l] = (l == 0) ? roundup(mlp->dims[0], 16) : a.npad[l - 1];
+    a.kpad[l] = (l == 0) ? roundup(a.nxp + (mlp->dims[0] - mlp->dims[mlp->n_layers]), 16) : a.npad[l - 1];
     {
       const int nl = mlp->dims[l + 1];
       a.npad[l] = (l == mlp->n_layers - 1) ? roundup(nl, 32) : (nl <= 64 ? 64 : (nl <= 128 ? 128 : 256));
@@ -614,6 +663,19 @@ void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg) {
 
 }  // namespace
 
+typedef void (*TcKernel)(const AmpcMppiParams, const TcArgs);
+static TcKernel tc_kernel_ptr(int cg, int nxp) {
+#define AMPC_TC_K(N) (cg == 1 ? (TcKernel)mppi_rollout_tc_kernel<1, N> : (TcKernel)mppi_rollout_tc_kernel<2, N>)
+  switch (nxp) {
+    case 4: return AMPC_TC_K(4);
+    case 8: return AMPC_TC_K(8);
+    case 16: return AMPC_TC_K(16);
+    case 24: return AMPC_TC_K(24);
+    default: return AMPC_TC_K(32);
+  }
+#undef AMPC_TC_K
+}
+
 struct AmpcTcPlan {
   TcArgs args;
   int cg = 1;
@@ -622,11 +684,12 @@ struct AmpcTcPlan {
   uint8_t *d_wimg = nullptr;
   float *d_bias = nullptr;
   float *d_epsc = nullptr;
+  unsigned long long *d_trace = nullptr;
 };
 
 static bool tc_shape_ok(const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp, const char **why) {
-  if (cfg->nx + cfg->nu > 64) { *why = "nx+nu > 64"; return false; }
-  if (cfg->nx > 64) { *why = "nx > 64"; return false; }
+  if (cfg->nx > 32) { *why = "nx > 32"; return false; }
+  if (cfg->nu > 32) { *why = "nu > 32"; return false; }
   for (int l = 1; l < mlp->n_layers; ++l)
     if (mlp->dims[l] > 256) { *why = "hidden width > 256"; return false; }
   return true;
@@ -669,6 +732,7 @@ void ampc_mppi_tc_destroy(AmpcTcPlan *plan) {
   cudaFree(plan->d_wimg);
   cudaFree(plan->d_bias);
   cudaFree(plan->d_epsc);
+  cudaFree(plan->d_trace);
   delete plan;
 }
 
@@ -712,7 +776,12 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
             const int ng = (n / crow) * a.cw[l] + r * crow + (n % crow);   // D column (= neuron) of local row n
             for (int e = 0; e < 8; ++e) {
               const int k = kb * 64 + ch * 8 + e;
-              const float v = (ng < Nl && k < Kl) ? (float)mlp->W[l][(size_t)ng * Kl + k] : 0.f;
+              int kin = k;                      // input layer: K columns [0,nxp) = state, [nxp,nxp+nu) = controls
+              if (l == 0) {
+                const int nx = mlp->dims[mlp->n_layers], nu = Kl - nx;
+                kin = (k < a.nxp) ? (k < nx ? k : -1) : (k - a.nxp < nu ? nx + (k - a.nxp) : -1);
+              }
+              const float v = (ng < Nl && kin >= 0 && kin < Kl) ? (float)mlp->W[l][(size_t)ng * Kl + kin] : 0.f;
               img[byte / 2 + e] = f32_to_bf16(v);
             }
           }
@@ -724,8 +793,7 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
   if (e == cudaSuccess) e = cudaMemcpy(pl->d_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_epsc, (size_t)cfg->H * cfg->nu * a.Kc * sizeof(float));
   if (e == cudaSuccess)
-    e = (cg == 1) ? cudaFuncSetAttribute(mppi_rollout_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem)
-                  : cudaFuncSetAttribute(mppi_rollout_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
+    e = cudaFuncSetAttribute(tc_kernel_ptr(cg, a.nxp), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
   if (e != cudaSuccess) {
     ampc_set_error("tcgen05 MPPI path create: %s", cudaGetErrorString(e));
     ampc_mppi_tc_destroy(pl);
@@ -734,6 +802,13 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
   a.wimg = pl->d_wimg;
   a.bias = pl->d_bias;
   a.epsc = pl->d_epsc;
+  a.trace = nullptr;
+  if (getenv("AMPC_TC_TRACE")) {
+    if (cudaMalloc(&pl->d_trace, (NTHR / 32) * TRACE_EV * sizeof(unsigned long long)) == cudaSuccess) {
+      cudaMemset(pl->d_trace, 0, (NTHR / 32) * TRACE_EV * sizeof(unsigned long long));
+      a.trace = pl->d_trace;
+    }
+  }
   *out = pl;
   return AMPC_OK;
 }
@@ -754,9 +829,17 @@ int ampc_mppi_tc_launch(AmpcTcPlan *plan, const AmpcMppiParams &p, cudaStream_t 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = (plan->cg == 1) ? cudaLaunchKernelEx(&cfg, mppi_rollout_tc_kernel<1>, p, plan->args)
-                                  : cudaLaunchKernelEx(&cfg, mppi_rollout_tc_kernel<2>, p, plan->args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_kernel_ptr(plan->cg, plan->args.nxp), p, plan->args);
   ampc_count_launch();
   AMPC_CUDA_CHECK(e);
   return AMPC_OK;
+}
+
+// debug: copies the timeline of CTA 0 (AMPC_TC_TRACE=1) to host; returns the number of 64-bit words
+int ampc_mppi_tc_trace(AmpcTcPlan *plan, unsigned long long *host, int max_words) {
+  const int n = (NTHR / 32) * TRACE_EV;
+  if (!plan || !plan->d_trace || max_words < n) return 0;
+  cudaDeviceSynchronize();
+  cudaMemcpy(host, plan->d_trace, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return n;
 }

@@ -132,6 +132,10 @@ int ampc_mppi_rollout_partial(ampc_mppi *h, const float *dev_x0, const float *de
 int ampc_mppi_merge(ampc_mppi *h, const float *dev_records, int32_t n_records, float *dev_u,
                     void *stream);
 
+/* Debug tap, no reference counterpart: when the handle was created with AMPC_TC_TRACE=1 in the environment,
+ * copies the tcgen05 kernel's timeline of CTA 0 ([warp][64] words = clock64 << 8 | tag) to host.       */
+int ampc_mppi_debug_trace(ampc_mppi *h, unsigned long long *host, int32_t max_words);
+
 /* ------------------------------------------------------- MLP model ops --- */
 /* Replaces autompc.sysid.mlp.MLP.pred / pred_batch (mlp.py:219-236) and
  * pred_diff / pred_diff_batch (mlp.py:238-305).  float64 on the device (the
