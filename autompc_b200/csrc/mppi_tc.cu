@@ -15,10 +15,13 @@
 // With CG=2 the kernel runs as CTA pairs (cta_group::2, UMMA M=256): each CTA keeps HALF of the
 // output neurons of every layer in its shared memory, which is what lets the 3x256 network
 // (283 KB of bf16 weights) stay resident; the leader CTA's single MMA thread issues for both.
-// Warps 0-3 ("owners", thread t <-> sample t): noise, clipping, control/action cost, z-score,
-// integration.  Warps 4-7 ("helpers", thread 128+t <-> sample t): state cost.  Both groups share the
-// layer epilogues: warp w serves TMEM lane quarter w%4 and column half w/4 of every chunk.
-// Warp 8: MMA issue + TMEM allocation.
+// Warps 0-3 ("owners", thread t <-> sample t, state in registers): integration, z-score, next input.
+// Warps 4-7 ("helpers", thread 128+t <-> sample t): stage cost of the state.  Both groups share the
+// layer epilogues: warp w serves TMEM lane quarter w%4 and one 32/64-column half of every N-half.
+// Warps 8-11 ("control", thread 256+t <-> sample t): Philox noise, clipping, clipped-noise write-back,
+// action and control cost -- run one horizon step AHEAD of the GEMM chain through a double-buffered
+// shared array handed over with named barriers, so none of it is on the critical path.
+// Warp 12: MMA issue + TMEM allocation.
 // Pipelining inside the dependent GEMM chain.  Every GEMM is issued at full width (N up to 256: 16
 // tcgen05.mma of K=16 per 256-wide layer), accumulating alternately into two 256-column TMEM
 // buffers.  The epilogue of GEMM n reads D_n 64 columns at a time and writes the packed bf16
@@ -42,8 +45,10 @@ namespace {
 
 constexpr int TM = 128;              // samples per CTA
 constexpr int NEPI = 256;            // 8 epilogue warps: 4 owner + 4 helper
-constexpr int NTHR = NEPI + 32;      // + 1 MMA warp
-constexpr int MMA_WARP = NEPI / 32;
+constexpr int NCTL = 128;            // 4 control warps (noise / clipping / control cost, one step ahead)
+constexpr int NTHR = NEPI + NCTL + 32;   // + 1 MMA warp
+constexpr int MMA_WARP = (NEPI + NCTL) / 32;
+constexpr int BAR_FULL = 1, BAR_EMPTY = 3;   // named barriers 1,2 / 3,4: hand-over of the two control buffers
 constexpr int TMEM_COLS = 512;
 constexpr int TMEM_BUF = 256;        // two accumulator / activation buffers: columns [0,256) and [256,512)
 constexpr int MAXL = AMPC_MAX_LAYERS;
@@ -283,11 +288,12 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   float *s_const = s_bias + ((a.bias_floats + 3) & ~3);
   float *s_act = s_const + cl.total;                   // shifted act_sequence (H*nu)
   float *s_x = s_act + ((HN + 3) & ~3);                // state [nx][128]
-  float *s_u = s_x + nx * TM;                          // scaled control [nu][128]
-  float2 *s_zc = reinterpret_cast<float2 *>(s_u + ((nu * TM + 3) & ~3));   // input z-score as (scale, bias) per K column [64]
+  float *s_u = s_x + nx * TM;                          // scaled control, two buffers of [nu][128]
+  float2 *s_zc = reinterpret_cast<float2 *>(s_u + 2 * nu * TM);   // input z-score as (scale, bias) per K column [64]
   float2 *s_ic = s_zc + 64;                            // integration as (dy_std, b_out*dy_std + dy_mean) per state [32]
   float *s_wgt = reinterpret_cast<float *>(s_ic + 32); // helper cost share, then softmax numerators [128]
-  float *s_red = s_wgt + TM;                           // 32
+  float *s_cc = s_wgt + TM;                            // control warps' cost share [128]
+  float *s_red = s_cc + TM;                            // 32
   float *s_misc = s_red + 32;                          // 64 + AMPC_MERGE_CACHE
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_misc + 64 + AMPC_MERGE_CACHE);   // [0..1]=bar_d[h], [2..3]=bar_a[kp]
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2 * MAXG);
@@ -348,7 +354,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   const float *c_goal = s_const + cl.goal, *c_Q = s_const + cl.Q, *c_R = s_const + cl.R, *c_F = s_const + cl.F;
   const float *c_lo = s_const + cl.lo, *c_hi = s_const + cl.hi, *c_scale = s_const + cl.scale;
 
-  const int t = tid & (TM - 1);                        // sample slot of this thread (owner or helper)
+  const int t = tid & (TM - 1);                        // sample slot of this thread (owner, helper or control)
   const int k_local = blockIdx.x * TM + t;
   const bool valid = k_local < p.K;
   float cost_acc = 0.f;
@@ -365,7 +371,9 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
       uint32_t n = 0;                                   // GEMM counter: D_n in buffer n&1, A_n in the other one
       const uint32_t w_addr = smem_u32(s_w);
       for (int i = 0; i < H; ++i) {
-        for (int l = 0; l < L; ++l, ++n) {
+#pragma unroll
+        for (int l = 0; l < MAXL; ++l) {
+          if (l >= L) break;
           const int rows = a.npad[l] / CG;              // B rows held by each CTA (per 64-wide K block)
           const int nks = a.kpad[l] >> 4, nh = a.nh[l], nkp = a.nkp[l];
           const int ksp = a.awid[l] >> 4;               // K-steps per pair
@@ -398,34 +406,16 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
             }
           }
           __syncwarp();
+          ++n;
         }
       }
     }
-  } else {
-    // =========================== epilogue warps: owners (0-3) and helpers (4-7) ===========================
-    const bool owner = warp < 4;
-    const int hf = warp >> 2;                           // which 32 of every 64 columns this warp serves
-    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  } else if (warp >= NEPI / 32) {
+    // =========================== control warps (8-11): one horizon step ahead ===========================
     const uint32_t kg = (uint32_t)(p.k_offset + k_local);
     const int nblk = (nu + 3) >> 2;
-    const int nin = nx + nu;
-    uint32_t pd = 0;                                    // parity bit h of bar_d[h]
-    uint32_t n = 0;                                     // GEMM counter (see the issuer)
-    auto wait_d = [&](int h) {
-      mbar_wait(bar_d0 + 8u * h, (pd >> h) & 1u);
-      pd ^= (1u << h);
-      tc_fence_after();
-    };
-    auto signal_a = [&](int g) {                        // "my part of activation group g is in TMEM, my D reads are done"
-      tc_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_cluster(bar_a0 + 8u * g, 0u); else mbar_arrive_local(bar_a0 + 8u * g);
-      }
-    };
     // controls of step i: noise, clip, write-back (mppi.py:134-139), action cost (:143), control cost (:142)
-    auto prepare_controls = [&](int i) {
+    auto prepare_controls = [&](int i, float *su) {
       for (int blk = 0; blk < nblk; ++blk) {
         float n4[4] = {0.f, 0.f, 0.f, 0.f};
         if (p.eps == nullptr) {
@@ -447,19 +437,50 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
             const float av = fminf(c_hi[j], fmaxf(c_lo[j], n4[q] + a0));
             const float e = av - a0;
             a.epsc[(size_t)(i * nu + j) * a.Kc + k_local] = e;
-            s_u[j * TM + t] = av * c_scale[j];
+            su[j * TM + t] = av * c_scale[j];
             cost_acc = fmaf(p.lam_over_sigma * av, e, cost_acc);
           }
         }
       }
-      cost_acc += quad_full(c_R, s_u, nullptr, nu, p.r_diag, t);
+      cost_acc += quad_full(c_R, su, nullptr, nu, p.r_diag, t);
+    };
+    for (int i = 0; i < H; ++i) {
+      const int b = i & 1;
+      if (i >= 2) asm volatile("bar.sync %0, %1;" ::"r"(BAR_EMPTY + b), "n"(NEPI / 2 + NCTL) : "memory");   // owners read step i-2
+      prepare_controls(i, s_u + b * nu * TM);
+      __threadfence_block();
+      asm volatile("bar.arrive %0, %1;" ::"r"(BAR_FULL + b), "n"(NEPI / 2 + NCTL) : "memory");
+    }
+    s_cc[t] = cost_acc;                                 // action + control costs of the sample
+  } else {
+    // =========================== epilogue warps: owners (0-3) and helpers (4-7) ===========================
+    const bool owner = warp < 4;
+    const int hf = warp >> 2;                           // which 32 of every 64 columns this warp serves
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t pd = 0;                                    // parity bit h of bar_d[h]
+    uint32_t n = 0;                                     // GEMM counter (see the issuer)
+    auto wait_d = [&](int h) {
+      mbar_wait(bar_d0 + 8u * h, (pd >> h) & 1u);
+      pd ^= (1u << h);
+      tc_fence_after();
+    };
+    auto signal_a = [&](int g) {                        // "my part of activation group g is in TMEM, my D reads are done"
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(bar_a0 + 8u * g, 0u); else mbar_arrive_local(bar_a0 + 8u * g);
+      }
     };
     // the sample's state lives in its owner's registers (a shared-memory copy feeds the cost evaluations)
     float x[NXP];
 #pragma unroll
     for (int j = 0; j < NXP; ++j) x[j] = (owner && j < nx) ? s_x[j * TM + t] : 0.f;
     // layer-0 input: z-score (mlp.py:20-24) -> bf16 -> A operand columns of buffer `buf`
-    auto write_input = [&](uint32_t buf) {
+    auto write_input = [&](uint32_t buf, int step) {
+      const int b = step & 1;
+      const float *su = s_u + b * nu * TM;
+      asm volatile("bar.sync %0, %1;" ::"r"(BAR_FULL + b), "n"(NEPI / 2 + NCTL) : "memory");   // controls of `step` are ready
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         if (g * 16 < a.kpad[0]) {
@@ -473,7 +494,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
               const float2 zc = s_zc[k];
               float v;
               if (k < NXP) v = x[k < NXP ? k : 0];
-              else v = (k - NXP < nu) ? s_u[(k - NXP) * TM + t] : 0.f;
+              else v = (k - NXP < nu) ? su[(k - NXP) * TM + t] : 0.f;
               z[hh] = fmaf(v, zc.x, zc.y);
             }
             pk[q] = pack_bf16(z[0], z[1]);
@@ -481,11 +502,9 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
           tmem_st8(lane_base + buf * TMEM_BUF + (uint32_t)((g >> 1) * 32 + (g & 1) * 8), pk);
         }
       }
+      if (step + 2 < H) asm volatile("bar.arrive %0, %1;" ::"r"(BAR_EMPTY + b), "n"(NEPI / 2 + NCTL) : "memory");
     };
-    if (owner) {
-      prepare_controls(0);
-      write_input(1u);                                  // GEMM 0 reads A from buffer 1
-    }
+    if (owner) write_input(1u, 0);                      // GEMM 0 reads A from buffer 1
     signal_a(0);
 
     for (int i = 0; i < H; ++i) {
@@ -519,8 +538,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
           trace(i, 0x40 + l * 2 + h);                   // half h packed and released
         }
         if (l == 0) {                                   // off the critical path: the layer-1 MMAs are running
-          if (owner) { if (i + 1 < H) prepare_controls(i + 1); }
-          else if (L >= 3) cost_acc += quad_full(c_Q, s_x, c_goal, nx, p.q_diag, t);               // mppi.py:142
+          if (!owner && L >= 3) cost_acc += quad_full(c_Q, s_x, c_goal, nx, p.q_diag, t);               // mppi.py:142
         }
       }
       // ---- output layer: un-z-score + integrate (mlp.py:235-236), then the next step's input in place
@@ -536,7 +554,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
           const float2 ic = s_ic[j];
           x[j] = fmaf(__uint_as_float(r[j]), ic.x, x[j] + ic.y);
         }
-        if (i + 1 < H) write_input(n & 1u);             // GEMM n+1 reads A from buffer n&1
+        if (i + 1 < H) write_input(n & 1u, i + 1);      // GEMM n+1 reads A from buffer n&1
       }
       if (i + 1 < H) signal_a(0);
       trace(i, 0x50);                                   // next input released
@@ -555,7 +573,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   float c = INFINITY;
   if (tid < TM) {
     const float term = quad_full(c_F, s_x, c_goal, nx, p.f_diag, tid);   // mppi.py:79-82, :146-148
-    c = cost_acc + s_wgt[tid];
+    c = cost_acc + s_wgt[tid] + s_cc[tid];
     if (p.terminal_mode == 1) c += term;
     else if (valid && (p.k_offset + k_local) == p.K_global - 1) *p.term_out = term;
     if (valid) p.costs[k_local] = c; else c = INFINITY;
@@ -615,7 +633,7 @@ uint16_t f32_to_bf16(float f) {
 size_t tc_smem_bytes(const TcArgs &a, int nx, int nu, int H) {
   const AmpcConstLayout cl(nx, nu);
   const size_t floats = (size_t)((a.bias_floats + 3) & ~3) + cl.total + ((H * nu + 3) & ~3) + (size_t)nx * TM +
-                        (size_t)((nu * TM + 3) & ~3) + 2 * 64 + 2 * 32 + TM + 32 + 64 + AMPC_MERGE_CACHE;
+                        (size_t)2 * nu * TM + 2 * 64 + 2 * 32 + 2 * TM + 32 + 64 + AMPC_MERGE_CACHE;
   return 1024 + a.w_bytes + floats * sizeof(float) + 2 * MAXG * sizeof(uint64_t) + 16;
 }
 
