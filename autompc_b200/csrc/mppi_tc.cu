@@ -37,6 +37,7 @@
 // (min, sum w, sum w*eps) are merged by the last CTA to finish, exactly like the fp32 kernel.
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "ampc_common.cuh"
@@ -53,6 +54,8 @@ constexpr int TMEM_COLS = 512;
 constexpr int TMEM_BUF = 256;        // two accumulator / activation buffers: columns [0,256) and [256,512)
 constexpr int MAXL = AMPC_MAX_LAYERS;
 constexpr int TRACE_EV = 64;
+// upper word of the K-major SWIZZLE_128B descriptor: SBO = 1024 B (bits 32-45), version 1 (bit 46), layout 2 (bits 61-63)
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 constexpr int MAXG = 2;              // N-halves of a GEMM = K-pairs of the next one
 
 struct TcArgs {
@@ -71,6 +74,7 @@ struct TcArgs {
   float *epsc;                       // (H*nu, Kc) clipped noise scratch
   int Kc;                            // grid * 128
   int nxp;                           // padded state width (kernel template): input K columns [0,nxp) = state
+  int ones[MAXL];                    // layer l's epilogue also writes the constant-one K-step of layer l+1 (bias fold)
   unsigned long long *trace;         // debug timeline (AMPC_TC_TRACE=1), else null: [warp][event] = clock<<8 | tag
 };
 
@@ -233,28 +237,17 @@ __device__ __forceinline__ float quad_full(const float *M, const float *v, const
   return c;
 }
 
-// bias + activation + bf16 pack of NV consecutive accumulator columns (NV = 16 or 32)
+// activation + bf16 pack of NV consecutive accumulator columns (the bias is already in the accumulator:
+// it enters every hidden GEMM through a constant-one K-step, split in two bf16 terms)
 template <int NV>
-__device__ __forceinline__ void epi_pack(const uint32_t (&r)[NV], const float *bias, int act, uint32_t (&pk)[NV / 2]) {
-  const float4 *b4 = reinterpret_cast<const float4 *>(bias);
+__device__ __forceinline__ void epi_pack(const uint32_t (&r)[NV], int act, uint32_t (&pk)[NV / 2]) {
   if (act == AMPC_ACT_RELU) {
 #pragma unroll
-    for (int q = 0; q < NV / 4; ++q) {
-      const float4 b = b4[q];
-      const float2 v0 = __fadd2_rn(make_float2(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), make_float2(b.x, b.y));
-      const float2 v1 = __fadd2_rn(make_float2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])), make_float2(b.z, b.w));
-      pk[2 * q] = pack_bf16_relu(v0.x, v0.y);
-      pk[2 * q + 1] = pack_bf16_relu(v1.x, v1.y);
-    }
+    for (int q = 0; q < NV / 2; ++q) pk[q] = pack_bf16_relu(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]));
   } else {
 #pragma unroll
-    for (int q = 0; q < NV / 4; ++q) {
-      const float4 b = b4[q];
-      pk[2 * q] = pack_bf16(ampc_act<float>(act, __uint_as_float(r[4 * q]) + b.x),
-                            ampc_act<float>(act, __uint_as_float(r[4 * q + 1]) + b.y));
-      pk[2 * q + 1] = pack_bf16(ampc_act<float>(act, __uint_as_float(r[4 * q + 2]) + b.z),
-                                ampc_act<float>(act, __uint_as_float(r[4 * q + 3]) + b.w));
-    }
+    for (int q = 0; q < NV / 2; ++q)
+      pk[q] = pack_bf16(ampc_act<float>(act, __uint_as_float(r[2 * q])), ampc_act<float>(act, __uint_as_float(r[2 * q + 1])));
   }
 }
 
@@ -284,8 +277,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t *base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t *s_w = base;
-  float *s_bias = reinterpret_cast<float *>(base + a.w_bytes);
-  float *s_const = s_bias + ((a.bias_floats + 3) & ~3);
+  float *s_const = reinterpret_cast<float *>(base + a.w_bytes);
   float *s_act = s_const + cl.total;                   // shifted act_sequence (H*nu)
   float *s_x = s_act + ((HN + 3) & ~3);                // state [nx][128]
   float *s_u = s_x + nx * TM;                          // scaled control, two buffers of [nu][128]
@@ -304,7 +296,6 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
     uint4 *dst = reinterpret_cast<uint4 *>(s_w);
     for (int i = tid; i < (int)(a.w_bytes >> 4); i += NTHR) dst[i] = __ldg(src + i);
   }
-  for (int i = tid; i < a.bias_floats; i += NTHR) s_bias[i] = a.bias[i];
   for (int i = tid; i < cl.total; i += NTHR) s_const[i] = p.consts[i];
   for (int e = tid; e < HN; e += NTHR) {               // mppi.py:122-123
     const int i = e / nu, j = e - i * nu;
@@ -322,6 +313,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
       const float inv = p.consts[cl.xu_inv + j];
       zc = make_float2(inv, -p.consts[cl.xu_mean + j] * inv);
     }
+    if (k == NXP + nu || k == NXP + nu + 1) zc = make_float2(0.f, 1.f);   // constant one: carries the layer-0 bias
     s_zc[k] = zc;
   }
   for (int j = tid; j < 32; j += NTHR) {                // x' = x + (y + b) * dy_std + dy_mean   (mlp.py:26-30, :236)
@@ -393,14 +385,18 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
             for (int h = 0; h < nh; ++h) {
               const uint32_t dh = d_addr + (uint32_t)(h * a.hwid[l]);
               const uint64_t hb = lbase + (uint64_t)(hrow_off * (uint32_t)h + pair_off);
-              if (l > 0 && ksp == 8) issue_pair<CG, 8>(dh, a_pair, hb, kb_stride, idesc, kp == 0);
-              else if (l > 0) issue_pair<CG, 4>(dh, a_pair, hb, kb_stride, idesc, kp == 0);
-              else {                                  // input layer: 1..4 K-steps at columns {0, 8, 32, 40}
+              if (l == 0) {                           // input layer: 1..4 K-steps at columns {0, 8, 32, 40}
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                   if (ks < nks)
                     umma_ts<CG>(dh, a_pair + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8), hb + (uint64_t)(ks * 2), idesc,
                                 ks > 0 ? 1u : 0u);
+              } else {
+                if (ksp == 8) issue_pair<CG, 8>(dh, a_pair, hb, kb_stride, idesc, kp == 0);
+                else issue_pair<CG, 4>(dh, a_pair, hb, kb_stride, idesc, kp == 0);
+                if (l < L - 1 && kp == 0)             // constant-one K-step: the layer's bias (extra K block of the image)
+                  umma_ts<CG>(dh, a_addr + (uint32_t)(a.awid[l] >> 2),
+                              lbase + (uint64_t)(hrow_off * (uint32_t)h + (uint32_t)(nks >> 2) * kb_stride), idesc, 1u);
               }
               if (kp == nkp - 1) { umma_commit<CG>(bar_d0 + 8u * h); trace(i, 0x20 + l * 2 + h); }   // half h committed
             }
@@ -511,7 +507,6 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
       // ---- hidden layers: D (buffer n&1) -> bias + activation -> bf16, written IN PLACE over the consumed
       //      accumulator columns; each 64-column group is released to the next GEMM as soon as it is packed
       for (int l = 0; l < L - 1; ++l, ++n) {
-        const float *bl = s_bias + a.b_off[l];
         const int nh = a.nh[l], hwid = a.hwid[l], sw = hwid >> 1;
         const uint32_t dbuf = lane_base + (n & 1u) * TMEM_BUF;
         for (int h = 0; h < nh; ++h) {
@@ -525,14 +520,18 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
           if (sw == 64) {
             uint32_t rb[32];
             tmem_ld32(dbuf + c0 + 32, rb);
-            epi_pack<32>(ra, bl + c0, p.act, pk);
+            epi_pack<32>(ra, p.act, pk);
             tmem_st16(dbuf + c0, pk);
             tc_wait_ld();
-            epi_pack<32>(rb, bl + c0 + 32, p.act, pk);
+            epi_pack<32>(rb, p.act, pk);
             tmem_st16(dbuf + c0 + 16, pk);
           } else {
-            epi_pack<32>(ra, bl + c0, p.act, pk);
+            epi_pack<32>(ra, p.act, pk);
             tmem_st16(dbuf + c0, pk);
+          }
+          if (h == 0 && hf == 0 && a.ones[l]) {         // constant-one K-step of the next GEMM (its bias), in free columns
+            const uint32_t one[8] = {0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            tmem_st8(dbuf + (uint32_t)(hwid >> 2), one);
           }
           signal_a(h);
           trace(i, 0x40 + l * 2 + h);                   // half h packed and released
@@ -632,7 +631,7 @@ uint16_t f32_to_bf16(float f) {
 
 size_t tc_smem_bytes(const TcArgs &a, int nx, int nu, int H) {
   const AmpcConstLayout cl(nx, nu);
-  const size_t floats = (size_t)((a.bias_floats + 3) & ~3) + cl.total + ((H * nu + 3) & ~3) + (size_t)nx * TM +
+  const size_t floats = (size_t)cl.total + ((H * nu + 3) & ~3) + (size_t)nx * TM +
                         (size_t)2 * nu * TM + 2 * 64 + 2 * 32 + 2 * TM + 32 + 64 + AMPC_MERGE_CACHE;
   return 1024 + a.w_bytes + floats * sizeof(float) + 2 * MAXG * sizeof(uint64_t) + 16;
 }
@@ -655,12 +654,16 @@ void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg) {
   uint32_t off = 0;
   int boff = 0;
   for (int l = 0; l < mlp->n_layers; ++l) {
-    a.kpad[l] = (l == 0) ? roundup(a.nxp + (mlp->dims[0] - mlp->dims[mlp->n_layers]), 16) : a.npad[l - 1];
+    // K of the layer's data; hidden layers also consume a constant-one K-step (bias): inside the input layer's
+    // padding (two extra columns), as an extra K block for layers 1..L-2
+    a.kpad[l] = (l == 0) ? roundup(a.nxp + (mlp->dims[0] - mlp->dims[mlp->n_layers]) + 2, 16) : a.npad[l - 1];
     {
       const int nl = mlp->dims[l + 1];
       a.npad[l] = (l == mlp->n_layers - 1) ? roundup(nl, 32) : (nl <= 64 ? 64 : (nl <= 128 ? 128 : 256));
     }
-    const int rows = a.npad[l] / cg, kblk = (a.kpad[l] + 63) / 64;
+    const bool bias_k = (l >= 1 && l <= mlp->n_layers - 2);
+    a.ones[l] = (l + 1 >= 1 && l + 1 <= mlp->n_layers - 2) ? 1 : 0;
+    const int rows = a.npad[l] / cg, kblk = (a.kpad[l] + 63) / 64 + (bias_k ? 1 : 0);
     a.w_off[l] = off;
     off += (uint32_t)kblk * rows * 128;
     a.b_off[l] = boff;
@@ -783,7 +786,9 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
   std::vector<float> bias(a.bias_floats, 0.f);
   for (int l = 0; l < mlp->n_layers; ++l) {
     const int Kl = mlp->dims[l], Nl = mlp->dims[l + 1];
-    const int rows = a.npad[l] / cg, kblk = (a.kpad[l] + 63) / 64;
+    const bool bias_k = (l >= 1 && l <= mlp->n_layers - 2);
+    const int kdata = (a.kpad[l] + 63) / 64;      // K blocks of data; the bias block (if any) follows
+    const int rows = a.npad[l] / cg, kblk = kdata + (bias_k ? 1 : 0);
     for (int r = 0; r < cg; ++r)
       for (int kb = 0; kb < kblk; ++kb)
         for (int n = 0; n < rows; ++n)
@@ -799,7 +804,18 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
                 const int nx = mlp->dims[mlp->n_layers], nu = Kl - nx;
                 kin = (k < a.nxp) ? (k < nx ? k : -1) : (k - a.nxp < nu ? nx + (k - a.nxp) : -1);
               }
-              const float v = (ng < Nl && kin >= 0 && kin < Kl) ? (float)mlp->W[l][(size_t)ng * Kl + kin] : 0.f;
+              float v = (ng < Nl && kin >= 0 && kin < Kl && kb < kdata) ? (float)mlp->W[l][(size_t)ng * Kl + kin] : 0.f;
+              // bias of hidden layers: two bf16 terms (hi + lo) against the constant-one inputs
+              int bsel = -1;
+              if (l == 0 && l <= mlp->n_layers - 2) bsel = k - (a.nxp + (Kl - mlp->dims[mlp->n_layers]));
+              if (bias_k && kb == kdata) bsel = k - kb * 64;
+              if (ng < Nl && (bsel == 0 || bsel == 1)) {
+                const float b = (float)mlp->b[l][ng];
+                uint32_t hb = (uint32_t)f32_to_bf16(b) << 16;
+                float bhi;
+                memcpy(&bhi, &hb, 4);
+                v = (bsel == 0) ? bhi : (b - bhi);
+              }
               img[byte / 2 + e] = f32_to_bf16(v);
             }
           }

@@ -61,6 +61,9 @@ if __name__ == "__main__":
         ok = run_case("cartpole [64,64] K256 H20", 4, 1, [64, 64], "relu", 256, 20, 1) and ok
         ok = run_case("17-6 [128,128] K300 H10", 17, 6, [128, 128], "relu", 300, 10, 1) and ok
         ok = run_case("17-6 [64,64] tanh", 17, 6, [64, 64], "tanh", 300, 10, 1) and ok
+    if which == "shapes":
+        for hid in ([64, 64, 64], [128, 128, 128], [256, 256], [256, 128, 256], [256, 256, 256], [256, 256, 256, 256]):
+            run_case("17-6 %s K256 H6" % hid, 17, 6, hid, "relu", 256, 6, 0, nsolve=1)
     if ok and which in ("all", "cg2"):
         run_case("tiny 4-1 [32] K128 H3", 4, 1, [32], "relu", 128, 3, 2)
         run_case("cartpole [64,64] K256 H20", 4, 1, [64, 64], "relu", 256, 20, 2)
