@@ -31,6 +31,15 @@ from .mlp import MLPWeights
 from .plugin import Controller, ControllerFactory
 
 
+def shard_of(num_path, world, rank):
+    """Contiguous shard [k_offset, k_offset + K_local) of the samples owned by `rank`:
+    the first num_path % world ranks get one extra sample.  Returns (K_local, k_offset)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad world/rank %d/%d" % (world, rank))
+    base, rem = divmod(int(num_path), world)
+    return base + (1 if rank < rem else 0), rank * base + min(rank, rem)
+
+
 def _quad_cost_of(task, nx, nu):
     cost = task.get_cost()
     try:
@@ -74,9 +83,7 @@ class MPPI(Controller):
         if self.group is not None:
             import torch.distributed as dist
             self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        base, rem = divmod(self.num_path, self.world)
-        self.K_local = base + (1 if self.rank < rem else 0)
-        self.k_offset = self.rank * base + min(self.rank, rem)
+        self.K_local, self.k_offset = shard_of(self.num_path, self.world, self.rank)
         if self.K_local < 1:
             raise ValueError("num_path=%d cannot be sharded over %d ranks" % (self.num_path, self.world))
         # --- engine handle

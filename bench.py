@@ -63,6 +63,13 @@ def measured_peaks():
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="B200_PROFILING.md fallback (of fallback)")
 
 
+def ncu_traffic(precision, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the rollout kernel, from the committed
+    `ncu --set full` capture of this same command at N=1 (profiles/r01_mppi_tc_v8_ncu_full.md: 491 008 B read,
+    0 B written -- the clipped-noise scratch stays in L2).  None when no capture exists for the configuration."""
+    return 491008 if (precision == "bf16" and world == 1) else None
+
+
 # --------------------------------------------------------------------------- CPU arm ---
 def cpu_port_rate(wl, budget_s, min_solves=2):
     """Times the float64 NumPy oracle (vectorised restatement of mppi.py:110-168) on the host.
@@ -281,7 +288,7 @@ def gpu_arm(args, wl, rank, world, local_rank):
                     "d2h_bytes_per_step": 4 * nu, "api": "autompc_b200.MPPI.run(state, new_obs) with NumPy float64 buffers"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_burst"], "traffic": None,
+                         "frac": achieved / peaks["bf16_burst"], "traffic": ncu_traffic(ctl.precision, world),
                          "flop_per_launch": flops / world, "peak_source": "bf16 dense burst, " + peaks["source"],
                          "kernel": "mppi_rollout (%s)" % ctl.precision},
         }
