@@ -56,6 +56,10 @@ EXPORTS = {
     "ampc_mppi_record_floats": [C.c_void_p],
     "ampc_mppi_rollout_partial": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p],
     "ampc_mppi_merge": [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p],
+    "ampc_mppi_mailbox_ipc": [C.c_void_p, C.c_int32, C.c_void_p],
+    "ampc_mppi_connect_peers_ipc": [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p],
+    "ampc_mppi_connect_peers_local": [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)],
+    "ampc_mppi_solve_fused": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p],
     "ampc_mppi_debug_trace": [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32],
     "ampc_mlp_create": [C.POINTER(C.c_void_p), C.POINTER(MlpDesc), C.c_int32, C.c_int32, C.c_int32],
     "ampc_mlp_destroy": [C.c_void_p],

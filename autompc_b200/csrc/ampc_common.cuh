@@ -165,6 +165,10 @@ struct AmpcMppiParams {
   float *partials;        // (gridDim.x, 2 + H*nu)
   unsigned int *ticket;   // grid completion counter
   float *record_out;      // NULL: update act_seq in-kernel;  else write [m, s, W] here
+  // NVLink peer-memory exchange (multi-GPU, fused into the rollout kernel's tail); peer_mail == NULL: off.
+  float *const *peer_mail;  // device array of `world` mailbox base pointers (own mailbox at index `rank`)
+  int world, rank;
+  unsigned int seq;         // solve sequence number (> 0), identical on all ranks; selects the mailbox slot
   float *u_out;           // (nu,)
 };
 
@@ -222,4 +226,46 @@ __device__ __forceinline__ void ampc_merge_records(const float *recs, int n_recs
     record_out[0] = m;
     record_out[1] = s;
   }
+}
+
+// ------------------------------------------------------- NVLink peer exchange ---
+// Mailbox of a rank (in its own HBM, mapped into every peer): 2 slots x [ world records of `rec` floats ]
+// followed by 2 x world 32-bit flags.  Called by ONE CTA per GPU (the last to finish) once the shard's record
+// [m, s, W(HN)] is in `rec_local` (global): store it into slot seq&1 / column `rank` of EVERY rank's mailbox
+// over NVLink, publish with a system-scope fence + flag = seq, wait for the `world` flags of the own mailbox,
+// then merge the records in rank order (identical arithmetic on all ranks) and apply mppi.py:115-118.
+__device__ __forceinline__ size_t ampc_mail_floats(int world, int rec) { return (size_t)2 * world * rec + 2 * world; }
+
+__device__ __forceinline__ void ampc_peer_exchange_merge(const AmpcMppiParams &p, const float *rec_local, int HN,
+                                                         const float *s_act_shift, const float *scale,
+                                                         float *s_scratch) {
+  const int rec = 2 + HN, world = p.world, slot = (int)(p.seq & 1u);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  __syncthreads();
+  __threadfence();                                       // rec_local was written by this CTA's other threads
+  for (int r = 0; r < world; ++r) {
+    float *dst = p.peer_mail[r] + ((size_t)slot * world + p.rank) * rec;
+    for (int e = tid; e < rec; e += nthr) dst[e] = __ldcg(rec_local + e);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < world) {
+    unsigned int *flags = reinterpret_cast<unsigned int *>(p.peer_mail[tid] + (size_t)2 * world * rec);
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags + slot * world + p.rank), "r"(p.seq) : "memory");
+  }
+  if (tid < world) {
+    const unsigned int *flags = reinterpret_cast<const unsigned int *>(p.peer_mail[p.rank] + (size_t)2 * world * rec);
+    unsigned int v = 0, spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + slot * world + tid) : "memory");
+      if (++spins > (1u << 26)) {
+        printf("ampc: peer exchange timeout (rank %d waiting for rank %d, seq %u, saw %u)\n", p.rank, tid, p.seq, v);
+        __trap();
+      }
+    } while (v != p.seq);
+  }
+  __syncthreads();
+  __threadfence_system();
+  ampc_merge_records(p.peer_mail[p.rank] + (size_t)slot * world * rec, world, rec, HN, p.nu, p.inv_lmda, s_act_shift,
+                     scale, p.act_seq, p.u_out, nullptr, s_scratch);
 }

@@ -53,6 +53,13 @@ struct ampc_mppi {
   float *h_pin = nullptr;          // pinned staging: x0 (nx) | u (nu)
   float *h_eps = nullptr;          // pinned staging for external eps (lazily)
   size_t eps_elems = 0;
+  // NVLink peer exchange
+  float *d_mail = nullptr;         // own mailbox (cudaMalloc, exported over CUDA IPC)
+  float *d_rec = nullptr;          // staging of the shard's record
+  float **d_peer = nullptr;        // device array of the ranks' mailbox pointers
+  std::vector<void *> ipc_opened;  // peers' mailboxes opened with cudaIpcOpenMemHandle
+  int world = 1, rank = 0;
+  unsigned int seq = 0;
 };
 
 namespace {
@@ -153,6 +160,8 @@ void free_handle(ampc_mppi *h) {
   cudaFree(h->d_partials); cudaFree(h->d_x0); cudaFree(h->d_u); cudaFree(h->d_eps); cudaFree(h->d_ticket);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->h_eps) cudaFreeHost(h->h_eps);
+  for (void *q : h->ipc_opened) cudaIpcCloseMemHandle(q);
+  cudaFree(h->d_mail); cudaFree(h->d_rec); cudaFree(h->d_peer);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -166,6 +175,7 @@ int launch_rollout(ampc_mppi *h, const float *dev_x0, const float *dev_eps, uint
   p.ctr = counter;
   p.u_out = dev_u;
   p.record_out = dev_record;
+  p.peer_mail = nullptr;
   if (h->tc) return ampc_mppi_tc_launch(h->tc, p, stream);
   return ampc_mppi_fp32_launch(p, h->resident, h->smem, stream);
 }
@@ -350,6 +360,8 @@ extern "C" int ampc_mppi_solve_host(ampc_mppi *h, const double *host_x0, const d
     const size_t n = (size_t)h->cfg.H * h->cfg.K * nu;
     if (h->eps_elems < n) {
       if (h->h_eps) cudaFreeHost(h->h_eps);
+  for (void *q : h->ipc_opened) cudaIpcCloseMemHandle(q);
+  cudaFree(h->d_mail); cudaFree(h->d_rec); cudaFree(h->d_peer);
       cudaFree(h->d_eps);
       h->h_eps = nullptr; h->d_eps = nullptr; h->eps_elems = 0;
       AMPC_CUDA_CHECK(cudaMallocHost(&h->h_eps, n * sizeof(float)));
@@ -426,4 +438,95 @@ extern "C" int ampc_mppi_debug_trace(ampc_mppi *h, unsigned long long *host, int
   if (!h || !h->tc || !host) return 0;
   DeviceGuard g(h->device);
   return ampc_mppi_tc_trace(h->tc, host, max_words);
+}
+
+// ------------------------------------------------------------ NVLink peer exchange ---
+namespace {
+size_t mail_floats(int world, int rec) { return (size_t)2 * world * rec + 2 * world; }
+
+int ensure_mailbox(ampc_mppi *h, int world) {
+  if (h->d_mail) return AMPC_OK;
+  const size_t n = mail_floats(world, 2 + h->HN);
+  AMPC_CUDA_CHECK(cudaMalloc(&h->d_mail, n * sizeof(float)));
+  AMPC_CUDA_CHECK(cudaMemset(h->d_mail, 0, n * sizeof(float)));
+  AMPC_CUDA_CHECK(cudaMalloc(&h->d_rec, (2 + h->HN) * sizeof(float)));
+  AMPC_CUDA_CHECK(cudaMalloc(&h->d_peer, world * sizeof(float *)));
+  AMPC_CUDA_CHECK(cudaDeviceSynchronize());
+  return AMPC_OK;
+}
+}  // namespace
+
+extern "C" int ampc_mppi_mailbox_ipc(ampc_mppi *h, int32_t world, void *ipc_handle_64) {
+  AMPC_REQUIRE(h && ipc_handle_64 && world >= 1 && world <= 64, AMPC_ERR_INVALID, "bad argument");
+  AMPC_REQUIRE(sizeof(cudaIpcMemHandle_t) == 64, AMPC_ERR_UNSUPPORTED, "unexpected cudaIpcMemHandle_t size");
+  DeviceGuard g(h->device);
+  int rc = ensure_mailbox(h, world);
+  if (rc) return rc;
+  cudaIpcMemHandle_t hd;
+  AMPC_CUDA_CHECK(cudaIpcGetMemHandle(&hd, h->d_mail));
+  memcpy(ipc_handle_64, &hd, 64);
+  return AMPC_OK;
+}
+
+static int finish_connect(ampc_mppi *h, int world, int rank, const std::vector<float *> &ptrs) {
+  AMPC_CUDA_CHECK(cudaMemcpy(h->d_peer, ptrs.data(), world * sizeof(float *), cudaMemcpyHostToDevice));
+  h->world = world;
+  h->rank = rank;
+  h->seq = 0;
+  return AMPC_OK;
+}
+
+extern "C" int ampc_mppi_connect_peers_ipc(ampc_mppi *h, int32_t world, int32_t rank, const void *ipc_handles) {
+  AMPC_REQUIRE(h && ipc_handles && world >= 1 && world <= 64 && rank >= 0 && rank < world, AMPC_ERR_INVALID, "bad argument");
+  DeviceGuard g(h->device);
+  int rc = ensure_mailbox(h, world);
+  if (rc) return rc;
+  std::vector<float *> ptrs(world, nullptr);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { ptrs[r] = h->d_mail; continue; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, (const char *)ipc_handles + (size_t)r * 64, 64);
+    void *q = nullptr;
+    AMPC_CUDA_CHECK(cudaIpcOpenMemHandle(&q, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(q);
+    ptrs[r] = (float *)q;
+  }
+  return finish_connect(h, world, rank, ptrs);
+}
+
+// same-process variant: the ranks' handles live in this process (tests; multi-GPU from one process)
+extern "C" int ampc_mppi_connect_peers_local(ampc_mppi *h, int32_t world, int32_t rank, ampc_mppi *const *handles) {
+  AMPC_REQUIRE(h && handles && world >= 1 && world <= 64 && rank >= 0 && rank < world && handles[rank] == h,
+               AMPC_ERR_INVALID, "bad argument");
+  std::vector<float *> ptrs(world, nullptr);
+  for (int r = 0; r < world; ++r) {
+    AMPC_REQUIRE(handles[r] && handles[r]->HN == h->HN, AMPC_ERR_INVALID, "peer %d has a different horizon/ctrl_dim", r);
+    DeviceGuard gr(handles[r]->device);
+    int rc = ensure_mailbox(handles[r], world);
+    if (rc) return rc;
+    ptrs[r] = handles[r]->d_mail;
+    if (handles[r]->device != h->device) {
+      DeviceGuard gh(h->device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(handles[r]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) AMPC_CUDA_CHECK(e);
+      cudaGetLastError();
+    }
+  }
+  DeviceGuard g(h->device);
+  return finish_connect(h, world, rank, ptrs);
+}
+
+extern "C" int ampc_mppi_solve_fused(ampc_mppi *h, const float *dev_x0, const float *dev_eps, uint64_t seed,
+                                     uint64_t counter, float *dev_u, void *stream) {
+  AMPC_REQUIRE(h && dev_x0 && dev_u, AMPC_ERR_INVALID, "null argument");
+  AMPC_REQUIRE(h->d_peer && h->world >= 1, AMPC_ERR_INVALID, "ampc_mppi_connect_peers_* has not been called");
+  DeviceGuard g(h->device);
+  AmpcMppiParams p = h->p;
+  p.x0 = dev_x0; p.eps = dev_eps; p.seed = seed; p.ctr = counter; p.u_out = dev_u;
+  p.record_out = h->d_rec;
+  p.peer_mail = h->d_peer;
+  p.world = h->world; p.rank = h->rank;
+  p.seq = ++h->seq;
+  if (h->tc) return ampc_mppi_tc_launch(h->tc, p, (cudaStream_t)stream);
+  return ampc_mppi_fp32_launch(p, h->resident, h->smem, (cudaStream_t)stream);
 }

@@ -242,8 +242,9 @@ __global__ void __launch_bounds__(NTHR) mppi_rollout_fp32_kernel(const AmpcMppiP
   __syncthreads();
   if (s_last) {
     __threadfence();
-    ampc_merge_records(p.partials, (int)gridDim.x, 2 + HN, HN, nu, p.inv_lmda, s_act, c_scale, p.act_seq,
-                       p.u_out, p.record_out, s_misc);
+    ampc_merge_records(p.partials, (int)gridDim.x, 2 + HN, HN, nu, p.inv_lmda, s_act, c_scale, p.act_seq, p.u_out,
+                       p.record_out, s_misc);
+    if (p.peer_mail != nullptr) ampc_peer_exchange_merge(p, p.record_out, HN, s_act, c_scale, s_misc);
     if (tid == 0) *p.ticket = 0u;
   }
 }

@@ -613,6 +613,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
     __threadfence();
     ampc_merge_records(p.partials, (int)gridDim.x, 2 + HN, HN, nu, p.inv_lmda, s_act, c_scale, p.act_seq, p.u_out,
                        p.record_out, s_misc);
+    if (p.peer_mail != nullptr) ampc_peer_exchange_merge(p, p.record_out, HN, s_act, c_scale, s_misc);
     if (tid == 0) *p.ticket = 0u;
   }
   // ---- teardown

@@ -19,8 +19,12 @@ Engine-only keyword arguments (all optional):
                all samples, ``mppi.py:79-82``) or ``"per_sample"``.
 ``device``     CUDA ordinal.
 ``group``      a ``torch.distributed`` process group: samples are sharded over
-               its ranks and one all-gather of the softmax partial record is
-               done per solve.
+               its ranks.
+``exchange``   how the ranks' softmax partial records meet: ``"nvlink"`` (default;
+               fused into the rollout kernel's tail: peer-memory stores + flags over
+               NVLink, one launch per solve, mailboxes shared through CUDA IPC) or
+               ``"nccl"`` (rollout kernel, one all-gather, merge kernel).  Falls back to
+               ``"nccl"`` on every rank if any rank cannot map its peers.
 """
 import ctypes as C
 
@@ -71,6 +75,9 @@ class MPPI(Controller):
             raise ValueError("terminal must be 'reference' or 'per_sample'")
         self.device = int(kwargs.get("device", 0))
         self.group = kwargs.get("group", None)
+        self.exchange = kwargs.get("exchange", "nvlink")
+        if self.exchange not in ("nvlink", "nccl"):
+            raise ValueError("exchange must be 'nvlink' or 'nccl'")
         self.weights = MLPWeights.from_model(model)
         nx, nu = self.weights.nx, self.weights.nu
         if nx != system.obs_dim or nu != system.ctrl_dim:
@@ -111,7 +118,29 @@ class MPPI(Controller):
         if self._h is None:
             _abi.check(err)
         self._dev_bufs = None
+        if self.world > 1 and self.exchange == "nvlink":
+            self._connect_peers()
         self._init_act_sequence()
+
+    def _connect_peers(self):
+        """Export this rank's mailbox over CUDA IPC, gather the handles, map the peers' mailboxes."""
+        import torch
+        import torch.distributed as dist
+        lib = _abi.lib()
+        ok = 1
+        try:
+            mine = C.create_string_buffer(64)
+            _abi.check(lib.ampc_mppi_mailbox_ipc(self._h, self.world, mine))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine.raw, group=self.group)
+            blob = C.create_string_buffer(b"".join(handles), 64 * self.world)
+            _abi.check(lib.ampc_mppi_connect_peers_ipc(self._h, self.world, self.rank, blob))
+        except Exception as e:           # all ranks must take the same path: agree below
+            ok, self._peer_error = 0, e
+        flag = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", self.device))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            self.exchange = "nccl"
 
     def _init_act_sequence(self):
         # mppi.py:97-99 -- N(0, sqrt(sigma)) draw from the global NumPy stream; trailing dim is
@@ -191,13 +220,20 @@ class MPPI(Controller):
         return self._dev_bufs
 
     def solve_device_sharded(self, x0_dev, u_dev, eps_dev=None):
-        """Sharded solve on device tensors, asynchronous on torch's current stream: local rollouts ->
-        one all-gather of the (min, sum w, sum w*eps) record -> merge on every rank."""
+        """Sharded solve on device tensors, asynchronous on torch's current stream.  exchange="nvlink": one
+        launch (rollouts + peer-memory exchange + merge).  exchange="nccl": local rollouts -> one all-gather
+        of the (min, sum w, sum w*eps) record -> merge kernel on every rank."""
         import torch
         import torch.distributed as dist
         lib = _abi.lib()
         b = self._shard_bufs()
         stream = torch.cuda.current_stream().cuda_stream
+        if self.exchange == "nvlink":
+            _abi.check(lib.ampc_mppi_solve_fused(self._h, x0_dev.data_ptr(),
+                                                 None if eps_dev is None else eps_dev.data_ptr(), self.seed,
+                                                 self.cur_step, u_dev.data_ptr(), stream))
+            self.cur_step += 1
+            return
         _abi.check(lib.ampc_mppi_rollout_partial(self._h, x0_dev.data_ptr(),
                                                  None if eps_dev is None else eps_dev.data_ptr(), self.seed,
                                                  self.cur_step, b["rec"].data_ptr(), stream))

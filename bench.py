@@ -209,7 +209,8 @@ def gpu_arm(args, wl, rank, world, local_rank):
     model = B200MLP(system, w, device=local_rank)
     np.random.seed(0)
     ctl = MPPI(system, task, model, horizon=wl["H"], num_path=wl["K"], sigma=wl["sigma"], lmda=wl["lmda"],
-               seed=0, noise="philox", precision=args.precision, device=local_rank, group=group)
+               seed=0, noise="philox", precision=args.precision, device=local_rank, group=group,
+               exchange=args.exchange)
     nx, nu = w.nx, w.nu
     x0_dev = torch.tensor(wl["x0"], dtype=torch.float32, device=dev)
     u_dev = torch.zeros(nu, dtype=torch.float32, device=dev)
@@ -277,8 +278,11 @@ def gpu_arm(args, wl, rank, world, local_rank):
             "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16" if ctl.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": wl["label"], "noise": "in-kernel Philox4x32-10", "precision": ctl.precision,
-                       "parallelism": "samples sharded over %d GPU(s), one all-gather of the %d-float softmax record"
-                                      % (world, 2 + wl["H"] * nu) if world > 1 else "1 GPU, one kernel per solve",
+                       "parallelism": ("samples sharded over %d GPU(s), %d-float softmax record exchanged by %s"
+                                       % (world, 2 + wl["H"] * nu,
+                                          "NVLink peer stores + flags inside the rollout kernel (one launch per solve)"
+                                          if ctl.exchange == "nvlink" else "one NCCL all-gather + merge kernel"))
+                       if world > 1 else "1 GPU, one kernel per solve",
                        "timing": "CUDA events per step on the launch stream, sum over steps, max over ranks",
                        "l2": "256 MiB memset between timed steps (L2 flushed)",
                        "ms_per_step_min_median_max": [float(per_step_ms.min()), float(np.median(per_step_ms)),
@@ -311,6 +315,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c2"])
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--exchange", default="nvlink", choices=["nvlink", "nccl"],
+                    help="N>1: how the ranks' softmax records meet (fused NVLink peer stores, or NCCL all-gather)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

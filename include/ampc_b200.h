@@ -132,6 +132,18 @@ int ampc_mppi_rollout_partial(ampc_mppi *h, const float *dev_x0, const float *de
 int ampc_mppi_merge(ampc_mppi *h, const float *dev_records, int32_t n_records, float *dev_u,
                     void *stream);
 
+/* Multi-GPU fast path: the exchange above fused into the rollout kernel's tail over NVLink peer memory.
+ * Each rank allocates a mailbox (2 slots x world records + flags) and exports it (CUDA IPC, 64-byte handle);
+ * after the handles of all ranks are gathered (any transport) connect_peers_ipc maps them.  solve_fused then is
+ * ONE launch per solve: rollouts -> shard record -> stores into every rank's mailbox + system-scope flag ->
+ * wait for the world's flags -> merge in rank order -> update (mppi.py:115-118).  connect_peers_local is the
+ * same for handles living in one process.                                                                */
+int ampc_mppi_mailbox_ipc(ampc_mppi *h, int32_t world, void *ipc_handle_64);
+int ampc_mppi_connect_peers_ipc(ampc_mppi *h, int32_t world, int32_t rank, const void *ipc_handles);
+int ampc_mppi_connect_peers_local(ampc_mppi *h, int32_t world, int32_t rank, ampc_mppi *const *handles);
+int ampc_mppi_solve_fused(ampc_mppi *h, const float *dev_x0, const float *dev_eps, uint64_t seed,
+                          uint64_t counter, float *dev_u, void *stream);
+
 /* Debug tap, no reference counterpart: when the handle was created with AMPC_TC_TRACE=1 in the environment,
  * copies the tcgen05 kernel's timeline of CTA 0 ([warp][64] words = clock64 << 8 | tag) to host.       */
 int ampc_mppi_debug_trace(ampc_mppi *h, unsigned long long *host, int32_t max_words);

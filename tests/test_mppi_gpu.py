@@ -356,3 +356,50 @@ def test_mppi_full_size_c3_properties():
     np.testing.assert_allclose(u1, u2, rtol=0, atol=1e-6)      # merge order of CTA partials may differ
     for e in (big, small, again):
         e.close()
+
+
+def test_fused_peer_exchange_two_shards_one_device():
+    """The NVLink peer-exchange tail (stores into every rank's mailbox + flags + merge, ampc_mppi_solve_fused)
+    exercised on ONE device: two shard handles connected in-process, launched on two streams so that both
+    kernels are resident together; both must reproduce the single-handle solve."""
+    import ctypes as C
+    import torch
+    from autompc_b200 import _abi
+    p = synthetic_mlp(17, 6, [64, 64], seed=2)
+    cost = QuadCostParams(np.eye(17), 0.01 * np.eye(6), 10 * np.eye(17))
+    K, H = 600, 10
+    np.random.seed(0)
+    full = _engine(p, cost, -np.ones(6), np.ones(6), horizon=H, num_path=K, seed=5, precision="bf16")
+    act0 = np.ascontiguousarray(full.act_sequence)
+    x0 = np.random.default_rng(1).normal(size=17)
+    lib = _abi.lib()
+    dev = torch.device("cuda", 0)
+    x0_d = torch.tensor(x0, dtype=torch.float32, device=dev)
+    hs = (C.c_void_p * 2)()
+    for r, (off, n) in enumerate([(0, 300), (300, 300)]):
+        cfg = _abi.MppiCfg(n, H, 17, 6, 1.0, 1.0, 0, _abi.PREC_CODES["bf16"], off, K, 0)
+        h = C.c_void_p()
+        _abi.check(lib.ampc_mppi_create(C.byref(h), C.byref(cfg), C.byref(full._mlp_holder.desc),
+                                        C.byref(full._cost_holder.desc)))
+        _abi.check(lib.ampc_mppi_set_act_seq(h, _abi.dptr(act0)))
+        hs[r] = h
+    for r in range(2):
+        _abi.check(lib.ampc_mppi_connect_peers_local(hs[r], 2, r, hs))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    us = [torch.zeros(6, dtype=torch.float32, device=dev) for _ in range(2)]
+    torch.cuda.synchronize()
+    u_ref = []
+    for step in range(3):                                  # consecutive solves: both mailbox slots get reused
+        u_ref.append(full.solve(x0))
+        for r in range(2):
+            _abi.check(lib.ampc_mppi_solve_fused(hs[r], x0_d.data_ptr(), None, 5, step, us[r].data_ptr(),
+                                                 streams[r].cuda_stream))
+        torch.cuda.synchronize()
+        for r in range(2):
+            np.testing.assert_allclose(us[r].cpu().numpy(), u_ref[-1], rtol=0, atol=2e-6)
+    for r in range(2):
+        a = np.empty((H, 6))
+        _abi.check(lib.ampc_mppi_get_act_seq(hs[r], _abi.dptr(a)))
+        np.testing.assert_allclose(a, full.act_sequence, rtol=0, atol=2e-6)
+        lib.ampc_mppi_destroy(hs[r])
+    full.close()
