@@ -7,5 +7,7 @@ through the C ABI in include/ampc_b200.h (libampc_b200.so).  No CPU fallback.
 from .mlp import B200MLP, MLPWeights  # noqa: F401
 from .mppi import MPPI, MPPIFactory  # noqa: F401
 from .ilqr import IterativeLQR, IterativeLQRFactory  # noqa: F401
+from .closed_loop import simulate, evaluate_candidates  # noqa: F401
 
-__all__ = ["MPPI", "MPPIFactory", "IterativeLQR", "IterativeLQRFactory", "B200MLP", "MLPWeights"]
+__all__ = ["MPPI", "MPPIFactory", "IterativeLQR", "IterativeLQRFactory", "B200MLP", "MLPWeights", "simulate",
+           "evaluate_candidates"]

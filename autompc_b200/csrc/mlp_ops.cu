@@ -68,7 +68,81 @@ __global__ void __launch_bounds__(NT) pred_diff_kernel(const AmpcMlpF64 net, int
   }
 }
 
+// One closed-loop plant step on the device: x <- sim.pred(x, u) (mlp.py:219-227, float64), plus the float32 copy the
+// next solve reads, the trajectory record and the running trajectory cost of Cost.__call__ (cost.py:27-41).
+__global__ void __launch_bounds__(NT) sim_step_kernel(const AmpcMlpF64 net, double *x, const float *u, float *x32,
+                                                      double *obs_next, double *ctrl_t, const double *Q, const double *R,
+                                                      const double *goal, double *cost) {
+  extern __shared__ double sm_d[];
+  double *h0 = sm_d, *h1 = sm_d + net.max_width;
+  const int nx = net.nx, nu = net.nu;
+  for (int j = threadIdx.x; j < nx + nu; j += NT) {
+    const double v = j < nx ? x[j] : (double)u[j - nx];
+    h0[j] = (v - net.xu_mean[j]) / net.xu_std[j];
+  }
+  if (cost != nullptr && threadIdx.x == 0) {             // stage cost of (x_t, u_t): obst^T Q obst + u^T R u
+    double c = 0.0;
+    for (int j = 0; j < nx; ++j) {
+      double col = 0.0;
+      for (int i = 0; i < nx; ++i) col += (x[i] - goal[i]) * Q[i * nx + j];
+      c += col * (x[j] - goal[j]);
+    }
+    for (int j = 0; j < nu; ++j) {
+      double col = 0.0;
+      for (int i = 0; i < nu; ++i) col += (double)u[i] * R[i * nu + j];
+      c += col * (double)u[j];
+    }
+    *cost += c;
+  }
+  __syncthreads();
+  const double *out = ampc_mlp_f64_forward(net, h0, h1, nullptr, threadIdx.x, NT);
+  for (int j = threadIdx.x; j < nx; j += NT) {
+    const double xn = x[j] + (out[j] * net.dy_std[j] + net.dy_mean[j]);
+    obs_next[j] = xn;
+    x32[j] = (float)xn;
+  }
+  for (int j = threadIdx.x; j < nu; j += NT) ctrl_t[j] = (double)u[j];
+  __syncthreads();
+  for (int j = threadIdx.x; j < nx; j += NT) x[j] = obs_next[j];
+}
+
+// terminal part of Cost.__call__: obs cost of the last state (its control is zero) + terminal cost
+__global__ void traj_cost_final_kernel(int nx, const double *x, const double *Q, const double *F, const double *goal,
+                                       double *cost) {
+  if (threadIdx.x != 0) return;
+  double c = 0.0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const double *M = pass == 0 ? Q : F;
+    for (int j = 0; j < nx; ++j) {
+      double col = 0.0;
+      for (int i = 0; i < nx; ++i) col += (x[i] - goal[i]) * M[i * nx + j];
+      c += col * (x[j] - goal[j]);
+    }
+  }
+  *cost += c;
+}
+
 }  // namespace
+
+int ampc_mlp_device(const ampc_mlp *m) { return m->device; }
+int ampc_mlp_nx(const ampc_mlp *m) { return m->net.nx; }
+int ampc_mlp_nu(const ampc_mlp *m) { return m->net.nu; }
+
+int ampc_mlp_sim_step_launch(ampc_mlp *m, double *d_x, const float *d_u, float *d_x32, double *d_obs_next, double *d_ctrl_t,
+                             const double *d_Q, const double *d_R, const double *d_goal, double *d_cost, cudaStream_t s) {
+  sim_step_kernel<<<1, NT, m->smem_pred, s>>>(m->net, d_x, d_u, d_x32, d_obs_next, d_ctrl_t, d_Q, d_R, d_goal, d_cost);
+  ampc_count_launch();
+  AMPC_CUDA_CHECK(cudaGetLastError());
+  return AMPC_OK;
+}
+
+int ampc_traj_cost_final_launch(int nx, const double *d_x, const double *d_Q, const double *d_F, const double *d_goal,
+                                double *d_cost, cudaStream_t s) {
+  traj_cost_final_kernel<<<1, 32, 0, s>>>(nx, d_x, d_Q, d_F, d_goal, d_cost);
+  ampc_count_launch();
+  AMPC_CUDA_CHECK(cudaGetLastError());
+  return AMPC_OK;
+}
 
 int ampc_mlp_f64_upload(const ampc_mlp_desc *mlp, int nx, int nu, AmpcMlpF64 *net, double **blob_out) {
   AMPC_REQUIRE(mlp && mlp->n_layers >= 2 && mlp->n_layers <= AMPC_MAX_LAYERS, AMPC_ERR_UNSUPPORTED,

@@ -60,6 +60,10 @@ struct ampc_mppi {
   std::vector<void *> ipc_opened;  // peers' mailboxes opened with cudaIpcOpenMemHandle
   int world = 1, rank = 0;
   unsigned int seq = 0;
+  // device-resident closed loop
+  double *d_cl = nullptr;          // [ x (nx) | cost (1) | Q | R | F | goal | obs (T+1, nx) | ctrl (T, nu) ]
+  int cl_T = 0;
+  std::vector<double> h_cost;      // Q, R, F, goal as given at create (float64)
 };
 
 namespace {
@@ -161,7 +165,7 @@ void free_handle(ampc_mppi *h) {
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->h_eps) cudaFreeHost(h->h_eps);
   for (void *q : h->ipc_opened) cudaIpcCloseMemHandle(q);
-  cudaFree(h->d_mail); cudaFree(h->d_rec); cudaFree(h->d_peer);
+  cudaFree(h->d_mail); cudaFree(h->d_rec); cudaFree(h->d_peer); cudaFree(h->d_cl);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -223,6 +227,10 @@ extern "C" int ampc_mppi_create(ampc_mppi **out, const ampc_mppi_cfg *cfg, const
   p.sqrt_sigma = (float)sqrt(cfg->sigma);
   p.lam_over_sigma = (float)(cfg->lmda / cfg->sigma);
 
+  h->h_cost.assign(cost->Q, cost->Q + nx * nx);
+  h->h_cost.insert(h->h_cost.end(), cost->R, cost->R + nu * nu);
+  h->h_cost.insert(h->h_cost.end(), cost->F, cost->F + nx * nx);
+  h->h_cost.insert(h->h_cost.end(), cost->goal, cost->goal + nx);
   // constants block
   const AmpcConstLayout cl(nx, nu);
   std::vector<float> hc(cl.total, 0.f);
@@ -361,7 +369,7 @@ extern "C" int ampc_mppi_solve_host(ampc_mppi *h, const double *host_x0, const d
     if (h->eps_elems < n) {
       if (h->h_eps) cudaFreeHost(h->h_eps);
   for (void *q : h->ipc_opened) cudaIpcCloseMemHandle(q);
-  cudaFree(h->d_mail); cudaFree(h->d_rec); cudaFree(h->d_peer);
+  cudaFree(h->d_mail); cudaFree(h->d_rec); cudaFree(h->d_peer); cudaFree(h->d_cl);
       cudaFree(h->d_eps);
       h->h_eps = nullptr; h->d_eps = nullptr; h->eps_elems = 0;
       AMPC_CUDA_CHECK(cudaMallocHost(&h->h_eps, n * sizeof(float)));
@@ -529,4 +537,64 @@ extern "C" int ampc_mppi_solve_fused(ampc_mppi *h, const float *dev_x0, const fl
   p.seq = ++h->seq;
   if (h->tc) return ampc_mppi_tc_launch(h->tc, p, (cudaStream_t)stream);
   return ampc_mppi_fp32_launch(p, h->resident, h->smem, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------ device-resident closed loop ---
+struct ampc_mlp;
+int ampc_mlp_device(const ampc_mlp *m);
+int ampc_mlp_nx(const ampc_mlp *m);
+int ampc_mlp_nu(const ampc_mlp *m);
+int ampc_mlp_sim_step_launch(ampc_mlp *m, double *d_x, const float *d_u, float *d_x32, double *d_obs_next, double *d_ctrl_t,
+                             const double *d_Q, const double *d_R, const double *d_goal, double *d_cost, cudaStream_t s);
+int ampc_traj_cost_final_launch(int nx, const double *d_x, const double *d_Q, const double *d_F, const double *d_goal,
+                                double *d_cost, cudaStream_t s);
+
+extern "C" int ampc_mppi_closed_loop_start(ampc_mppi *h, ampc_mlp *sim, const double *x0, int32_t T, uint64_t seed,
+                                           uint64_t counter0) {
+  AMPC_REQUIRE(h && sim && x0 && T >= 1, AMPC_ERR_INVALID, "bad argument");
+  AMPC_REQUIRE(ampc_mlp_device(sim) == h->device && ampc_mlp_nx(sim) == h->cfg.nx && ampc_mlp_nu(sim) == h->cfg.nu,
+               AMPC_ERR_INVALID, "simulation model and controller disagree on device / dimensions");
+  AMPC_REQUIRE(h->cfg.k_offset == 0 && h->cfg.K_global == h->cfg.K, AMPC_ERR_UNSUPPORTED,
+               "the device-resident closed loop runs on one GPU (unsharded controller)");
+  DeviceGuard g(h->device);
+  const int nx = h->cfg.nx, nu = h->cfg.nu;
+  const size_t fixed = (size_t)nx + 1 + (size_t)2 * nx * nx + (size_t)nu * nu + nx;
+  if (h->cl_T < T) {
+    cudaFree(h->d_cl);
+    h->d_cl = nullptr;
+    h->cl_T = 0;
+    AMPC_CUDA_CHECK(cudaMalloc(&h->d_cl, (fixed + (size_t)(T + 1) * nx + (size_t)T * nu) * sizeof(double)));
+    h->cl_T = T;
+  }
+  double *d_x = h->d_cl, *d_cost = d_x + nx, *d_Q = d_cost + 1, *d_R = d_Q + nx * nx, *d_F = d_R + nu * nu,
+         *d_goal = d_F + nx * nx, *d_obs = d_goal + nx, *d_ctrl = d_obs + (size_t)(h->cl_T + 1) * nx;
+  std::vector<double> init(fixed, 0.0);
+  for (int j = 0; j < nx; ++j) init[j] = x0[j];
+  for (size_t i = 0; i < h->h_cost.size(); ++i) init[nx + 1 + i] = h->h_cost[i];
+  AMPC_CUDA_CHECK(cudaMemcpyAsync(d_x, init.data(), fixed * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  AMPC_CUDA_CHECK(cudaMemcpyAsync(d_obs, x0, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  for (int j = 0; j < nx; ++j) h->h_pin[j] = (float)x0[j];
+  AMPC_CUDA_CHECK(cudaMemcpyAsync(h->d_x0, h->h_pin, nx * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  AMPC_CUDA_CHECK(cudaStreamSynchronize(h->stream));      // `init` and h_pin are reused by the caller / next call
+  for (int t = 0; t < T; ++t) {
+    int rc = launch_rollout(h, h->d_x0, nullptr, seed, counter0 + (uint64_t)t, h->d_u, nullptr, h->stream);
+    if (rc) return rc;
+    rc = ampc_mlp_sim_step_launch(sim, d_x, h->d_u, h->d_x0, d_obs + (size_t)(t + 1) * nx, d_ctrl + (size_t)t * nu, d_Q,
+                                  d_R, d_goal, d_cost, h->stream);
+    if (rc) return rc;
+  }
+  return ampc_traj_cost_final_launch(nx, d_x, d_Q, d_F, d_goal, d_cost, h->stream);
+}
+
+extern "C" int ampc_mppi_closed_loop_finish(ampc_mppi *h, int32_t T, double *obs_out, double *ctrl_out, double *cost_out) {
+  AMPC_REQUIRE(h && h->d_cl && T >= 1 && T <= h->cl_T, AMPC_ERR_INVALID, "no closed loop of that length in flight");
+  DeviceGuard g(h->device);
+  const int nx = h->cfg.nx, nu = h->cfg.nu;
+  double *d_x = h->d_cl, *d_cost = d_x + nx, *d_obs = d_cost + 1 + 2 * nx * nx + nu * nu + nx,
+         *d_ctrl = d_obs + (size_t)(h->cl_T + 1) * nx;
+  AMPC_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (obs_out) AMPC_CUDA_CHECK(cudaMemcpy(obs_out, d_obs, (size_t)(T + 1) * nx * sizeof(double), cudaMemcpyDeviceToHost));
+  if (ctrl_out) AMPC_CUDA_CHECK(cudaMemcpy(ctrl_out, d_ctrl, (size_t)T * nu * sizeof(double), cudaMemcpyDeviceToHost));
+  if (cost_out) AMPC_CUDA_CHECK(cudaMemcpy(cost_out, d_cost, sizeof(double), cudaMemcpyDeviceToHost));
+  return AMPC_OK;
 }

@@ -161,6 +161,19 @@ int ampc_mlp_pred_batch(ampc_mlp *m, int32_t batch, const double *X, const doubl
 int ampc_mlp_pred_diff_batch(ampc_mlp *m, int32_t batch, const double *X, const double *U,
                              double *Xn, double *Jx, double *Ju);
 
+/* ------------------------------------------------- device-resident closed loop --- */
+/* Replaces autompc.utils.simulation.simulate (autompc/utils/simulation.py:11-64) for an MPPI controller and an
+ * MLP simulation model when term_cond is None:  T x [ u = controller.run(x) ; x = sim_model.pred(x, u) ]
+ * (mppi.py:154-168, sysid/mlp.py:219-227) with no host round trip, plus the trajectory cost of Cost.__call__
+ * (autompc/costs/cost.py:27-41) for the controller's QuadCost.  start() enqueues the T solves and plant steps on
+ * the handle's own stream and returns; finish() waits and copies obs (T+1,nx), ctrl (T,nu), cost (1) to host
+ * float64 buffers (any may be NULL).  Handles are independent: many closed loops can be in flight at once
+ * (the tuner's candidate evaluations, tuning/pipeline_tuner.py:213-239).  Noise: in-kernel Philox, solve
+ * counters counter0 .. counter0+T-1.                                                                        */
+int ampc_mppi_closed_loop_start(ampc_mppi *h, ampc_mlp *sim, const double *x0, int32_t T, uint64_t seed,
+                                uint64_t counter0);
+int ampc_mppi_closed_loop_finish(ampc_mppi *h, int32_t T, double *obs_out, double *ctrl_out, double *cost_out);
+
 /* ------------------------------------------------------------------ iLQR --- */
 /* Replaces autompc.control.ilqr.IterativeLQR.compute_ilqr_default
  * (autompc/control/ilqr.py:100-265) for MLP dynamics + QuadCost: the whole
