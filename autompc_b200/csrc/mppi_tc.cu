@@ -53,7 +53,7 @@ constexpr int BAR_FULL = 1, BAR_EMPTY = 3;   // named barriers 1,2 / 3,4: hand-o
 constexpr int TMEM_COLS = 512;
 constexpr int TMEM_BUF = 256;        // two accumulator / activation buffers: columns [0,256) and [256,512)
 constexpr int MAXL = AMPC_MAX_LAYERS;
-constexpr int TRACE_EV = 64;
+constexpr int TRACE_EV = 128;
 // upper word of the K-major SWIZZLE_128B descriptor: SBO = 1024 B (bits 32-45), version 1 (bit 46), layout 2 (bits 61-63)
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 constexpr int MAXG = 2;              // N-halves of a GEMM = K-pairs of the next one
@@ -148,34 +148,38 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   else
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(TMEM_COLS) : "memory");
 }
-// D[tmem] (+)= A[tmem, packed bf16] . B[smem desc]^T ; executed by a converged warp, one elected lane issues
+// D[tmem] (+)= A[tmem, packed bf16] . B[smem desc]^T ; executed by ONE thread (the elected issuer).
+// b_desc_lo = low word of the K-major SWIZZLE_128B descriptor (start address >> 4 | LBO); the high word is constant.
 template <int CG>
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_desc_lo, uint32_t idesc,
                                         uint32_t accumulate) {
+  const uint64_t b_desc = ((uint64_t)DESC_HI << 32) | (uint64_t)b_desc_lo;
   if constexpr (CG == 1)
     asm volatile(
-        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
   else
     asm volatile(
-        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   if constexpr (CG == 1)
-    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
   else
-    asm volatile(
-        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar),
-        "h"((uint16_t)3)
-        : "memory");
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t e;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(e));
+  return e != 0;
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -213,11 +217,6 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
-// K-major SWIZZLE_128B shared-memory matrix descriptor: 128-byte rows, 8-row (1024 B) swizzle atoms
-__device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-
 // d^T M d for this thread's sample; v laid out [i][TM]
 __device__ __forceinline__ float quad_full(const float *M, const float *v, const float *off, int n, bool diag, int t) {
   float c = 0.f;
@@ -255,12 +254,12 @@ __device__ __forceinline__ void epi_pack(const uint32_t (&r)[NV], int act, uint3
 // the pair's K elements sit in two sub-halves (one per epilogue warp of a lane quarter), each packed at the
 // start of its own KSP*8 accumulator columns.
 template <int CG, int KSP>
-__device__ __forceinline__ void issue_pair(uint32_t dh, uint32_t a_pair, uint64_t desc_pair, uint32_t kb_stride,
+__device__ __forceinline__ void issue_pair(uint32_t dh, uint32_t a_pair, uint32_t desc_pair, uint32_t kb_stride,
                                            uint32_t idesc, bool first_pair) {
 #pragma unroll
   for (int j = 0; j < KSP; ++j) {
     const uint32_t acol = (uint32_t)((j / (KSP / 2)) * (KSP * 8) + (j % (KSP / 2)) * 8);
-    const uint64_t d = desc_pair + (uint64_t)((uint32_t)(j >> 2) * kb_stride + (uint32_t)(j & 3) * 2u);
+    const uint32_t d = desc_pair + (uint32_t)(j >> 2) * kb_stride + (uint32_t)(j & 3) * 2u;
     umma_ts<CG>(dh, a_pair + acol, d, idesc, (j == 0 && first_pair) ? 0u : 1u);
   }
 }
@@ -353,59 +352,78 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
 
   if (warp == MMA_WARP) {
     // =========================== MMA issuer (leader CTA of the pair) ===========================
-    // The whole warp runs this loop with warp-uniform operands; one elected lane issues.
+    // ONE elected thread runs this loop (tcgen05.mma / .commit are single-thread instructions).
     // GEMM n = (step, layer).  Its N is issued as nh halves (one commit each: bar_d[h]); its K as nkp
     // pairs, pair kp being exactly what the epilogue of half kp of GEMM n-1 produced (bar_a[kp]).
     // Issue order (h0,kp0) (h1,kp0) | (h0,kp1)+commit (h1,kp1)+commit keeps the tensor pipe busy with the
     // kp0 work of GEMM n while the epilogue of half 1 of GEMM n-1 is still running.
-    if (cta_rank == 0) {
+    // All 512 TMEM columns are allocated, so the base is column 0 / lane 0 (checked below): accumulator and
+    // operand addresses are literals, the per-layer descriptor words are hoisted out of the horizon loop, and
+    // the K-steps of a pair are unrolled with compile-time offsets -> the SASS is a dense run of UTCHMMA fed by
+    // uniform-datapath adds (v8 spent 55-90 cycles per MMA on ELECT/VOTEU/R2UR sequences; a N=128 MMA executes in 66).
+    if (cta_rank == 0 && elect_one()) {
+      if (tmem_base != 0u) {
+        printf("ampc mppi_tc: unexpected TMEM base %u\n", tmem_base);
+        __trap();
+      }
       uint32_t pa = 0;                                  // parity bit kp of bar_a[kp]
       uint32_t n = 0;                                   // GEMM counter: D_n in buffer n&1, A_n in the other one
       const uint32_t w_addr = smem_u32(s_w);
+      uint32_t lo_l[MAXL], kbs_l[MAXL], hro_l[MAXL], id_l[MAXL];
+      int nh_l[MAXL], nkp_l[MAXL], ksp_l[MAXL], hw_l[MAXL], aw_l[MAXL];
+#pragma unroll
+      for (int l = 0; l < MAXL; ++l) {
+        const int rows = a.npad[l] / CG;                // B rows held by each CTA (per 64-wide K block)
+        lo_l[l] = (((w_addr + a.w_off[l]) >> 4) & 0x3FFFu) | (1u << 16);
+        kbs_l[l] = (uint32_t)(rows * 128) >> 4;
+        hro_l[l] = (uint32_t)((a.hwid[l] / CG) * 128) >> 4;   // B rows of one N-half (descriptor units)
+        id_l[l] = a.idesc[l];
+        nh_l[l] = a.nh[l];
+        nkp_l[l] = a.nkp[l];
+        ksp_l[l] = a.awid[l] >> 4;                      // K-steps per pair
+        hw_l[l] = a.hwid[l];
+        aw_l[l] = a.awid[l];
+      }
+      const int nks0 = a.kpad[0] >> 4;
       for (int i = 0; i < H; ++i) {
 #pragma unroll
         for (int l = 0; l < MAXL; ++l) {
           if (l >= L) break;
-          const int rows = a.npad[l] / CG;              // B rows held by each CTA (per 64-wide K block)
-          const int nks = a.kpad[l] >> 4, nh = a.nh[l], nkp = a.nkp[l];
-          const int ksp = a.awid[l] >> 4;               // K-steps per pair
-          const uint32_t hrow_off = (uint32_t)((a.hwid[l] / CG) * 128) >> 4;   // B rows of one N-half (descriptor units)
-          const uint32_t idesc = a.idesc[l];
-          const uint32_t d_addr = tmem_base + (n & 1u) * TMEM_BUF;
-          const uint32_t a_addr = tmem_base + ((n + 1u) & 1u) * TMEM_BUF;
-          const uint32_t kb_stride = (uint32_t)(rows * 128) >> 4;
-          const uint64_t lbase = make_b_desc(w_addr + a.w_off[l]);
+          const int nh = nh_l[l], nkp = nkp_l[l];
+          const uint32_t idesc = id_l[l], kb_stride = kbs_l[l];
+          const uint32_t d_addr = (n & 1u) * TMEM_BUF;
+          const uint32_t a_addr = ((n + 1u) & 1u) * TMEM_BUF;
           for (int kp = 0; kp < nkp; ++kp) {
             mbar_wait(bar_a0 + 8u * kp, (pa >> kp) & 1u);
             pa ^= (1u << kp);
             tc_fence_after();
             trace(i, 0x10 + l * 2 + kp);                // bar_a[kp] of layer l observed
-            const uint32_t a_pair = a_addr + (uint32_t)(kp * a.awid[l]);
-            const uint32_t pair_off = (uint32_t)((kp * ksp) >> 2) * kb_stride;
+            const uint32_t a_pair = a_addr + (uint32_t)(kp * aw_l[l]);
+            const uint32_t pair_off = (uint32_t)((kp * ksp_l[l]) >> 2) * kb_stride;
             for (int h = 0; h < nh; ++h) {
-              const uint32_t dh = d_addr + (uint32_t)(h * a.hwid[l]);
-              const uint64_t hb = lbase + (uint64_t)(hrow_off * (uint32_t)h + pair_off);
+              const uint32_t dh = d_addr + (uint32_t)(h * hw_l[l]);
+              const uint32_t hb = lo_l[l] + hro_l[l] * (uint32_t)h + pair_off;
               if (l == 0) {                           // input layer: 1..4 K-steps at columns {0, 8, 32, 40}
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                  if (ks < nks)
-                    umma_ts<CG>(dh, a_pair + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8), hb + (uint64_t)(ks * 2), idesc,
+                  if (ks < nks0)
+                    umma_ts<CG>(dh, a_pair + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8), hb + (uint32_t)(ks * 2), idesc,
                                 ks > 0 ? 1u : 0u);
               } else {
-                if (ksp == 8) issue_pair<CG, 8>(dh, a_pair, hb, kb_stride, idesc, kp == 0);
+                if (ksp_l[l] == 8) issue_pair<CG, 8>(dh, a_pair, hb, kb_stride, idesc, kp == 0);
                 else issue_pair<CG, 4>(dh, a_pair, hb, kb_stride, idesc, kp == 0);
                 if (l < L - 1 && kp == 0)             // constant-one K-step: the layer's bias (extra K block of the image)
-                  umma_ts<CG>(dh, a_addr + (uint32_t)(a.awid[l] >> 2),
-                              lbase + (uint64_t)(hrow_off * (uint32_t)h + (uint32_t)(nks >> 2) * kb_stride), idesc, 1u);
+                  umma_ts<CG>(dh, a_addr + (uint32_t)(aw_l[l] >> 2),
+                              lo_l[l] + hro_l[l] * (uint32_t)h + (uint32_t)(a.kpad[l] >> 6) * kb_stride, idesc, 1u);
               }
               if (kp == nkp - 1) { umma_commit<CG>(bar_d0 + 8u * h); trace(i, 0x20 + l * 2 + h); }   // half h committed
             }
           }
-          __syncwarp();
           ++n;
         }
       }
     }
+    __syncwarp();
   } else if (warp >= NEPI / 32) {
     // =========================== control warps (8-11): one horizon step ahead ===========================
     const uint32_t kg = (uint32_t)(p.k_offset + k_local);
@@ -517,14 +535,17 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
           uint32_t ra[32], pk[16];
           tmem_ld32(dbuf + c0, ra);
           tc_wait_ld();
+          trace(i, 0x60 + h);                           // first 32 columns in registers
           if (sw == 64) {
             uint32_t rb[32];
             tmem_ld32(dbuf + c0 + 32, rb);
             epi_pack<32>(ra, p.act, pk);
             tmem_st16(dbuf + c0, pk);
             tc_wait_ld();
+            trace(i, 0x70 + h);                         // second 32 columns in registers
             epi_pack<32>(rb, p.act, pk);
             tmem_st16(dbuf + c0 + 16, pk);
+            trace(i, 0x80 + h);                         // both stores issued
           } else {
             epi_pack<32>(ra, p.act, pk);
             tmem_st16(dbuf + c0, pk);
@@ -548,12 +569,15 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
         uint32_t r[32];
         tmem_ld32(dbuf, r);
         tc_wait_ld();
+        trace(i, 0x90);                                 // y in registers
 #pragma unroll
         for (int j = 0; j < NXP; ++j) {
           const float2 ic = s_ic[j];
           x[j] = fmaf(__uint_as_float(r[j]), ic.x, x[j] + ic.y);
         }
+        trace(i, 0x91);                                 // integrated
         if (i + 1 < H) write_input(n & 1u, i + 1);      // GEMM n+1 reads A from buffer n&1
+        trace(i, 0x92);                                 // input stores issued
       }
       if (i + 1 < H) signal_a(0);
       trace(i, 0x50);                                   // next input released
@@ -688,6 +712,9 @@ void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg) {
 typedef void (*TcKernel)(const AmpcMppiParams, const TcArgs);
 static TcKernel tc_kernel_ptr(int cg, int nxp) {
 #define AMPC_TC_K(N) (cg == 1 ? (TcKernel)mppi_rollout_tc_kernel<1, N> : (TcKernel)mppi_rollout_tc_kernel<2, N>)
+#ifdef AMPC_TC_FAST_BUILD   // local SASS experiments only: one instantiation
+  return (TcKernel)mppi_rollout_tc_kernel<2, 24>;
+#else
   switch (nxp) {
     case 4: return AMPC_TC_K(4);
     case 8: return AMPC_TC_K(8);
@@ -695,6 +722,7 @@ static TcKernel tc_kernel_ptr(int cg, int nxp) {
     case 24: return AMPC_TC_K(24);
     default: return AMPC_TC_K(32);
   }
+#endif
 #undef AMPC_TC_K
 }
 
