@@ -206,7 +206,16 @@ __device__ __forceinline__ void ampc_merge_records(const float *recs, int n_recs
   for (int e = tid; e < HN; e += nthr) {
     float acc = 0.f;
     if (cached) {
-      for (int b = 0; b < n_recs; ++b)
+      constexpr int MU = 16;                           // record loads in flight per thread (they come from L2)
+      int b0 = 0;
+      for (; b0 + MU <= n_recs; b0 += MU) {
+        float v[MU];
+#pragma unroll
+        for (int u = 0; u < MU; ++u) v[u] = __ldcg(recs + (size_t)(b0 + u) * rec_stride + 2 + e);
+#pragma unroll
+        for (int u = 0; u < MU; ++u) acc = fmaf(v[u], s_rs[b0 + u], acc);
+      }
+      for (int b = b0; b < n_recs; ++b)
         acc = fmaf(__ldcg(recs + (size_t)b * rec_stride + 2 + e), s_rs[b], acc);
     } else {
       for (int b = 0; b < n_recs; ++b) {

@@ -50,12 +50,14 @@ constexpr int NCTL = 128;            // 4 control warps (noise / clipping / cont
 constexpr int NTHR = NEPI + NCTL + 32;   // + 1 MMA warp
 constexpr int MMA_WARP = (NEPI + NCTL) / 32;
 constexpr int BAR_FULL = 1, BAR_EMPTY = 3;   // named barriers 1,2 / 3,4: hand-over of the two control buffers
+constexpr int BAR_X = 5;             // owners -> helpers: the shared copy of the state is up to date
 constexpr int TMEM_COLS = 512;
 constexpr int TMEM_BUF = 256;        // two accumulator / activation buffers: columns [0,256) and [256,512)
 constexpr int MAXL = AMPC_MAX_LAYERS;
 constexpr int TRACE_EV = 128;
 // upper word of the K-major SWIZZLE_128B descriptor: SBO = 1024 B (bits 32-45), version 1 (bit 46), layout 2 (bits 61-63)
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr int YCOL = 64;             // accumulator columns of the output-layer GEMM inside its buffer (clear of the next input block)
 constexpr int MAXG = 2;              // N-halves of a GEMM = K-pairs of the next one
 
 struct TcArgs {
@@ -238,9 +240,9 @@ __device__ __forceinline__ float quad_full(const float *M, const float *v, const
 
 // activation + bf16 pack of NV consecutive accumulator columns (the bias is already in the accumulator:
 // it enters every hidden GEMM through a constant-one K-step, split in two bf16 terms)
-template <int NV>
+template <int NV, bool RELU>
 __device__ __forceinline__ void epi_pack(const uint32_t (&r)[NV], int act, uint32_t (&pk)[NV / 2]) {
-  if (act == AMPC_ACT_RELU) {
+  if constexpr (RELU) {
 #pragma unroll
     for (int q = 0; q < NV / 2; ++q) pk[q] = pack_bf16_relu(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]));
   } else {
@@ -264,10 +266,15 @@ __device__ __forceinline__ void issue_pair(uint32_t dh, uint32_t a_pair, uint32_
   }
 }
 
-template <int CG, int NXP>
+// RELU: the activation is compiled in (the reference's default, mlp.py:44-53); the other activations share one
+// instantiation with a runtime switch.  Keeping their code out of the ReLU kernel matters: inlined, it put 43 KB
+// of cold instructions between the LDTM, the packs and the STTM of every epilogue (instruction-cache misses on
+// the critical path).
+template <int CG, int NXP, bool RELU, bool TRACE>
 __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppiParams p, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t t_entry = (uint32_t)clock();
   const int nx = p.nx, nu = p.nu, H = p.H, HN = H * nu, L = a.n_layers;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const AmpcConstLayout cl(nx, nu);
@@ -282,7 +289,8 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   float *s_u = s_x + nx * TM;                          // scaled control, two buffers of [nu][128]
   float2 *s_zc = reinterpret_cast<float2 *>(s_u + 2 * nu * TM);   // input z-score as (scale, bias) per K column [64]
   float2 *s_ic = s_zc + 64;                            // integration as (dy_std, b_out*dy_std + dy_mean) per state [32]
-  float *s_wgt = reinterpret_cast<float *>(s_ic + 32); // helper cost share, then softmax numerators [128]
+  float2 *s_xc = s_ic + 32;                            // x = z * std + mean per state [32]
+  float *s_wgt = reinterpret_cast<float *>(s_xc + 32); // helper cost share, then softmax numerators [128]
   float *s_cc = s_wgt + TM;                            // control warps' cost share [128]
   float *s_red = s_cc + TM;                            // 32
   float *s_misc = s_red + 32;                          // 64 + AMPC_MERGE_CACHE
@@ -293,7 +301,17 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(a.wimg + (size_t)cta_rank * a.w_bytes);
     uint4 *dst = reinterpret_cast<uint4 *>(s_w);
-    for (int i = tid; i < (int)(a.w_bytes >> 4); i += NTHR) dst[i] = __ldg(src + i);
+    const int nv = (int)(a.w_bytes >> 4);
+    constexpr int WU = 8;                               // 16-byte loads in flight per thread
+    for (int i0 = tid; i0 < nv; i0 += NTHR * WU) {
+      uint4 v[WU];
+#pragma unroll
+      for (int u = 0; u < WU; ++u)
+        if (i0 + u * NTHR < nv) v[u] = __ldg(src + i0 + u * NTHR);
+#pragma unroll
+      for (int u = 0; u < WU; ++u)
+        if (i0 + u * NTHR < nv) dst[i0 + u * NTHR] = v[u];
+    }
   }
   for (int i = tid; i < cl.total; i += NTHR) s_const[i] = p.consts[i];
   for (int e = tid; e < HN; e += NTHR) {               // mppi.py:122-123
@@ -315,13 +333,18 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
     if (k == NXP + nu || k == NXP + nu + 1) zc = make_float2(0.f, 1.f);   // constant one: carries the layer-0 bias
     s_zc[k] = zc;
   }
-  for (int j = tid; j < 32; j += NTHR) {                // x' = x + (y + b) * dy_std + dy_mean   (mlp.py:26-30, :236)
-    float2 ic = make_float2(0.f, 0.f);
+  // The owner keeps the NORMALISED state z = (x - mean) / std in registers (it is what the input layer eats):
+  //   x' = x + (y + b_out) * dy_std + dy_mean  (mlp.py:26-30, :236)   <=>   z' = z + y * k1 + k2,
+  //   k1 = dy_std / std, k2 = (b_out * dy_std + dy_mean) / std;  x = z * std + mean is recovered off the critical path.
+  for (int j = tid; j < 32; j += NTHR) {
+    float2 ic = make_float2(0.f, 0.f), xc = make_float2(0.f, 0.f);
     if (j < nx) {
-      const float ds = p.consts[cl.dy_std + j];
-      ic = make_float2(ds, fmaf(a.bias[a.b_off[L - 1] + j], ds, p.consts[cl.dy_mean + j]));
+      const float ds = p.consts[cl.dy_std + j], inv = p.consts[cl.xu_inv + j];
+      ic = make_float2(ds * inv, fmaf(a.bias[a.b_off[L - 1] + j], ds, p.consts[cl.dy_mean + j]) * inv);
+      xc = make_float2(1.f / inv, p.consts[cl.xu_mean + j]);
     }
     s_ic[j] = ic;
+    s_xc[j] = xc;
   }
   const uint32_t bar_d0 = smem_u32(&s_bar[0]), bar_a0 = smem_u32(&s_bar[MAXG]);
   if (tid == 0) {
@@ -335,13 +358,18 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  // debug timeline of CTA 0: up to TRACE_EV events per warp (steps 10 and 11), tag = kind*16 + index
+  // debug timeline of CTA 0 (AMPC_TC_TRACE=1): up to TRACE_EV events per warp, steps 10 and 11 plus the kernel
+  // phases (step -1), kept in shared memory while the kernel runs (a clock read + one STS per event) and copied
+  // to global at the end; event = clock << 8 | tag, tag = kind*16 + index
+  uint32_t *s_trace = reinterpret_cast<uint32_t *>(s_tmem + 4);
   int trace_n = 0;
   auto trace = [&](int step, int tag) {
-    if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && step >= 10 && step < 12 && trace_n < TRACE_EV)
-      a.trace[warp * TRACE_EV + trace_n++] = ((unsigned long long)clock64() << 8) | (unsigned long long)(tag & 255);
+    if constexpr (TRACE) {
+      if (blockIdx.x == 0 && lane == 0 && (step < 0 || (step >= 10 && step < 12)) && trace_n < TRACE_EV)
+        s_trace[warp * TRACE_EV + trace_n++] = ((uint32_t)clock() << 8) | (uint32_t)(tag & 255);
+    }
   };
-
+  trace(-1, 0xA1);                                      // setup done (weights resident, TMEM allocated)
   const float *c_goal = s_const + cl.goal, *c_Q = s_const + cl.Q, *c_R = s_const + cl.R, *c_F = s_const + cl.F;
   const float *c_lo = s_const + cl.lo, *c_hi = s_const + cl.hi, *c_scale = s_const + cl.scale;
 
@@ -391,7 +419,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
           if (l >= L) break;
           const int nh = nh_l[l], nkp = nkp_l[l];
           const uint32_t idesc = id_l[l], kb_stride = kbs_l[l];
-          const uint32_t d_addr = (n & 1u) * TMEM_BUF;
+          const uint32_t d_addr = (n & 1u) * TMEM_BUF + (l == L - 1 ? (uint32_t)YCOL : 0u);
           const uint32_t a_addr = ((n + 1u) & 1u) * TMEM_BUF;
           for (int kp = 0; kp < nkp; ++kp) {
             mbar_wait(bar_a0 + 8u * kp, (pa >> kp) & 1u);
@@ -468,6 +496,10 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
     s_cc[t] = cost_acc;                                 // action + control costs of the sample
   } else {
     // =========================== epilogue warps: owners (0-3) and helpers (4-7) ===========================
+    // Everything between "accumulator complete" and "activations released" is on the critical path of the
+    // dependent GEMM chain, so this code is kept short: layers and halves are unrolled at compile time (their
+    // shapes come straight from the constant bank), both TMEM loads of a half are issued before the one wait,
+    // and no debug code is compiled in unless TRACE.
     const bool owner = warp < 4;
     const int hf = warp >> 2;                           // which 32 of every 64 columns this warp serves
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -486,112 +518,149 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
         if constexpr (CG == 2) mbar_arrive_cluster(bar_a0 + 8u * g, 0u); else mbar_arrive_local(bar_a0 + 8u * g);
       }
     };
-    // the sample's state lives in its owner's registers (a shared-memory copy feeds the cost evaluations)
-    float x[NXP];
+    // the sample's normalised state lives in its owner's registers
+    float z[NXP];
 #pragma unroll
-    for (int j = 0; j < NXP; ++j) x[j] = (owner && j < nx) ? s_x[j * TM + t] : 0.f;
-    // layer-0 input: z-score (mlp.py:20-24) -> bf16 -> A operand columns of buffer `buf`
-    auto write_input = [&](uint32_t buf, int step) {
+    for (int j = 0; j < NXP; ++j) {
+      const float2 zc = s_zc[j];
+      z[j] = (owner && j < nx) ? fmaf(s_x[j * TM + t], zc.x, zc.y) : 0.f;
+    }
+    const int kpad0 = a.kpad[0];
+    // Input-layer A operand (bf16, K columns [0,NXP) = z, [NXP,NXP+nu) = z-scored controls, then the constant ones):
+    // K-step g (16 columns) -> 8 TMEM columns at {0, 8, 32, 40}.  K-steps that hold no state are written as soon as the
+    // controls are known (pack_controls, in the shadow of the output-layer MMAs, whose accumulator sits at YCOL and
+    // does not overlap them); the control half of the K-step that straddles NXP waits in cpk; store_input adds the
+    // state once y has arrived.
+    constexpr int NMIX = (NXP % 16) ? (16 - NXP % 16) / 2 : 1;
+    uint32_t cpk[NMIX];
+    auto zctl = [&](const float *su, int k) -> float {  // z-scored control / constant-one column k >= NXP
+      const float2 zc = s_zc[k];
+      return fmaf((k - NXP < nu) ? su[(k - NXP) * TM + t] : 0.f, zc.x, zc.y);
+    };
+    auto pack_controls = [&](int step, uint32_t buf) {
       const int b = step & 1;
       const float *su = s_u + b * nu * TM;
       asm volatile("bar.sync %0, %1;" ::"r"(BAR_FULL + b), "n"(NEPI / 2 + NCTL) : "memory");   // controls of `step` are ready
+      if constexpr (NXP % 16 != 0) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if (g * 16 < a.kpad[0]) {
+        for (int q = 0; q < NMIX; ++q) cpk[q] = pack_bf16(zctl(su, NXP + 2 * q), zctl(su, NXP + 2 * q + 1));
+      }
+#pragma unroll
+      for (int g = (NXP + 15) / 16; g < 4; ++g) {
+        if (g * 16 < kpad0) {
           uint32_t pk[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float z[2];
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const int k = g * 16 + q * 2 + hh;
-              const float2 zc = s_zc[k];
-              float v;
-              if (k < NXP) v = x[k < NXP ? k : 0];
-              else v = (k - NXP < nu) ? su[(k - NXP) * TM + t] : 0.f;
-              z[hh] = fmaf(v, zc.x, zc.y);
-            }
-            pk[q] = pack_bf16(z[0], z[1]);
-          }
+          for (int q = 0; q < 8; ++q) pk[q] = pack_bf16(zctl(su, g * 16 + 2 * q), zctl(su, g * 16 + 2 * q + 1));
           tmem_st8(lane_base + buf * TMEM_BUF + (uint32_t)((g >> 1) * 32 + (g & 1) * 8), pk);
         }
       }
       if (step + 2 < H) asm volatile("bar.arrive %0, %1;" ::"r"(BAR_EMPTY + b), "n"(NEPI / 2 + NCTL) : "memory");
     };
-    if (owner) write_input(1u, 0);                      // GEMM 0 reads A from buffer 1
+    auto store_input = [&](uint32_t buf) {
+#pragma unroll
+      for (int g = 0; g * 16 < NXP; ++g) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int k = g * 16 + q * 2;                 // NXP is even: a pair is all state or all control
+          if (k < NXP) pk[q] = pack_bf16(z[k < NXP ? k : 0], z[k + 1 < NXP ? k + 1 : 0]);
+          else pk[q] = cpk[(k - NXP) / 2 < NMIX ? (k - NXP) / 2 : 0];
+        }
+        tmem_st8(lane_base + buf * TMEM_BUF + (uint32_t)((g >> 1) * 32 + (g & 1) * 8), pk);
+      }
+    };
+    auto store_x = [&]() {
+#pragma unroll
+      for (int j = 0; j < NXP; ++j)
+        if (j < nx) {
+          const float2 xc = s_xc[j];
+          s_x[j * TM + t] = fmaf(z[j], xc.x, xc.y);
+        }
+    };
+    if (owner) {
+      pack_controls(0, 1u);
+      store_input(1u);                                  // GEMM 0 reads A from buffer 1
+    }
     signal_a(0);
 
     for (int i = 0; i < H; ++i) {
-      // ---- hidden layers: D (buffer n&1) -> bias + activation -> bf16, written IN PLACE over the consumed
-      //      accumulator columns; each 64-column group is released to the next GEMM as soon as it is packed
-      for (int l = 0; l < L - 1; ++l, ++n) {
-        const int nh = a.nh[l], hwid = a.hwid[l], sw = hwid >> 1;
+      // ---- hidden layers: D (buffer n&1) -> activation -> bf16, written IN PLACE over the consumed accumulator
+      //      columns; each N-half is one K-pair of the next GEMM
+#pragma unroll
+      for (int l = 0; l < MAXL - 1; ++l) {
+        if (l >= L - 1) break;
+        const int nh = a.nh[l], hwid = a.hwid[l];
         const uint32_t dbuf = lane_base + (n & 1u) * TMEM_BUF;
-        for (int h = 0; h < nh; ++h) {
+#pragma unroll
+        for (int h = 0; h < MAXG; ++h) {
+          if (h >= nh) break;
           wait_d(h);
           trace(i, 0x30 + l * 2 + h);                   // bar_d[h] of layer l observed
-          if (l == 0 && h == 0 && !owner && L < 3) cost_acc += quad_full(c_Q, s_x, c_goal, nx, p.q_diag, t);   // mppi.py:142
-          const int c0 = h * hwid + hf * sw;            // this warp's sw (32 or 64) columns of the half
           uint32_t ra[32], pk[16];
-          tmem_ld32(dbuf + c0, ra);
-          tc_wait_ld();
-          trace(i, 0x60 + h);                           // first 32 columns in registers
-          if (sw == 64) {
+          if (hwid == 128) {                            // this warp's 64 columns of the half
+            const uint32_t c0 = dbuf + (uint32_t)(h * 128 + hf * 64);
             uint32_t rb[32];
-            tmem_ld32(dbuf + c0 + 32, rb);
-            epi_pack<32>(ra, p.act, pk);
-            tmem_st16(dbuf + c0, pk);
+            tmem_ld32(c0, ra);
+            tmem_ld32(c0 + 32, rb);
             tc_wait_ld();
-            trace(i, 0x70 + h);                         // second 32 columns in registers
-            epi_pack<32>(rb, p.act, pk);
-            tmem_st16(dbuf + c0 + 16, pk);
-            trace(i, 0x80 + h);                         // both stores issued
-          } else {
-            epi_pack<32>(ra, p.act, pk);
-            tmem_st16(dbuf + c0, pk);
+            epi_pack<32, RELU>(ra, p.act, pk);
+            tmem_st16(c0, pk);
+            epi_pack<32, RELU>(rb, p.act, pk);
+            tmem_st16(c0 + 16, pk);
+          } else {                                      // hwid == 64: 32 columns
+            const uint32_t c0 = dbuf + (uint32_t)(h * 64 + hf * 32);
+            tmem_ld32(c0, ra);
+            tc_wait_ld();
+            epi_pack<32, RELU>(ra, p.act, pk);
+            tmem_st16(c0, pk);
           }
           if (h == 0 && hf == 0 && a.ones[l]) {         // constant-one K-step of the next GEMM (its bias), in free columns
-            const uint32_t one[8] = {0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            uint32_t one[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) one[q] = q == 0 ? 0x3F803F80u : 0u;
             tmem_st8(dbuf + (uint32_t)(hwid >> 2), one);
           }
           signal_a(h);
           trace(i, 0x40 + l * 2 + h);                   // half h packed and released
         }
-        if (l == 0) {                                   // off the critical path: the layer-1 MMAs are running
-          if (!owner && L >= 3) cost_acc += quad_full(c_Q, s_x, c_goal, nx, p.q_diag, t);               // mppi.py:142
+        if (l == 0) {                                   // off the critical path: the next GEMM's MMAs are running
+          if (owner) {                                  // x_i = z * std + mean -> shared copy for the stage cost
+            store_x();
+            asm volatile("bar.arrive %0, %1;" ::"n"(BAR_X), "n"(NEPI) : "memory");
+          } else {
+            asm volatile("bar.sync %0, %1;" ::"n"(BAR_X), "n"(NEPI) : "memory");
+            cost_acc += quad_full(c_Q, s_x, c_goal, nx, p.q_diag, t);                                   // mppi.py:142
+          }
         }
+        ++n;
       }
-      // ---- output layer: un-z-score + integrate (mlp.py:235-236), then the next step's input in place
+      // ---- output layer: integrate in z space (mlp.py:235-236), then the next step's input in place.
+      //      The control columns of that input are packed while the output-layer MMAs run.
+      if (owner && i + 1 < H) pack_controls(i + 1, n & 1u);
       wait_d(0);
       trace(i, 0x30 + (L - 1) * 2);
       if (owner) {
         const uint32_t dbuf = lane_base + (n & 1u) * TMEM_BUF;
         uint32_t r[32];
-        tmem_ld32(dbuf, r);
+        tmem_ld32(dbuf + YCOL, r);
         tc_wait_ld();
-        trace(i, 0x90);                                 // y in registers
 #pragma unroll
         for (int j = 0; j < NXP; ++j) {
           const float2 ic = s_ic[j];
-          x[j] = fmaf(__uint_as_float(r[j]), ic.x, x[j] + ic.y);
+          z[j] = fmaf(__uint_as_float(r[j]), ic.x, z[j] + ic.y);
         }
-        trace(i, 0x91);                                 // integrated
-        if (i + 1 < H) write_input(n & 1u, i + 1);      // GEMM n+1 reads A from buffer n&1
-        trace(i, 0x92);                                 // input stores issued
+        if (i + 1 < H) store_input(n & 1u);             // GEMM n+1 reads A from buffer n&1
       }
       if (i + 1 < H) signal_a(0);
       trace(i, 0x50);                                   // next input released
-      if (owner) {                                      // shared copy for the helpers' stage cost / the terminal cost
-#pragma unroll
-        for (int j = 0; j < NXP; ++j)
-          if (j < nx) s_x[j * TM + t] = x[j];
-      }
       ++n;
     }
+    if (owner) store_x();                               // x_H for the terminal cost
     if (!owner) s_wgt[t] = cost_acc;                    // helper's share (state costs)
   }
 
   // =========================== softmax partials of this CTA (mppi.py:110-118) ===========================
+  trace(-1, 0xA2);                                      // this warp left the horizon loop
   __syncthreads();
   float c = INFINITY;
   if (tid < TM) {
@@ -617,15 +686,32 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
     rec[0] = m_cta;
     rec[1] = (s_red[8] + s_red[9]) + (s_red[10] + s_red[11]);
   }
-  for (int e = warp; e < HN; e += NTHR / 32) {                            // mppi.py:117 (per-CTA share)
-    const float *src = a.epsc + (size_t)e * a.Kc + (size_t)blockIdx.x * TM;
-    float v = 0.f;
+  {                                                                       // mppi.py:117 (per-CTA share)
+    constexpr int EU = 8;                                                 // entries per warp iteration: 32 L2 loads in flight per lane
+    float wq[TM / 32];
 #pragma unroll
-    for (int q = 0; q < TM / 32; ++q) v = fmaf(s_wgt[lane + 32 * q], __ldcg(src + lane + 32 * q), v);
-    v = ampc_warp_sum(v);
-    if (lane == 0) rec[2 + e] = v;
+    for (int q = 0; q < TM / 32; ++q) wq[q] = s_wgt[lane + 32 * q];
+    for (int e0 = warp * EU; e0 < HN; e0 += (NTHR / 32) * EU) {
+      float ld[EU][TM / 32];
+#pragma unroll
+      for (int u = 0; u < EU; ++u) {
+        const int e = (e0 + u < HN) ? e0 + u : HN - 1;
+        const float *src = a.epsc + (size_t)e * a.Kc + (size_t)blockIdx.x * TM;
+#pragma unroll
+        for (int q = 0; q < TM / 32; ++q) ld[u][q] = __ldcg(src + lane + 32 * q);
+      }
+#pragma unroll
+      for (int u = 0; u < EU; ++u) {
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < TM / 32; ++q) v = fmaf(wq[q], ld[u][q], v);
+        v = ampc_warp_sum(v);
+        if (lane == 0 && e0 + u < HN) rec[2 + e0 + u] = v;
+      }
+    }
   }
   // ---- last CTA to finish merges all partials and applies the update
+  trace(-1, 0xA3);                                      // per-CTA softmax record written
   __threadfence();
   __syncthreads();
   if (tid == 0) {
@@ -641,9 +727,19 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
     if (tid == 0) *p.ticket = 0u;
   }
   // ---- teardown
+  trace(-1, 0xA4);                                      // ticket taken / merge done (if this was the last CTA)
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == MMA_WARP) tmem_dealloc<CG>(tmem_base);
+  if (TRACE && blockIdx.x == 0) {
+    if (lane == 0 && trace_n < TRACE_EV) s_trace[warp * TRACE_EV + trace_n++] = ((uint32_t)clock() << 8) | 0xA5u;   // end
+    __syncwarp();
+    for (int e = lane; e < TRACE_EV; e += 32) {
+      const int cnt = __shfl_sync(0xffffffffu, trace_n, 0);
+      const uint32_t v = e < cnt ? s_trace[warp * TRACE_EV + e] : 0u;
+      a.trace[warp * TRACE_EV + e] = v ? ((unsigned long long)(((v >> 8) - (t_entry & 0xFFFFFFu)) & 0xFFFFFFu) << 8) | (v & 255u) : 0ull;
+    }
+  }
 }
 
 uint16_t f32_to_bf16(float f) {
@@ -657,8 +753,9 @@ uint16_t f32_to_bf16(float f) {
 size_t tc_smem_bytes(const TcArgs &a, int nx, int nu, int H) {
   const AmpcConstLayout cl(nx, nu);
   const size_t floats = (size_t)cl.total + ((H * nu + 3) & ~3) + (size_t)nx * TM +
-                        (size_t)2 * nu * TM + 2 * 64 + 2 * 32 + 2 * TM + 32 + 64 + AMPC_MERGE_CACHE;
-  return 1024 + a.w_bytes + floats * sizeof(float) + 2 * MAXG * sizeof(uint64_t) + 16;
+                        (size_t)2 * nu * TM + 2 * 64 + 3 * 2 * 32 + 2 * TM + 32 + 64 + AMPC_MERGE_CACHE;
+  return 1024 + a.w_bytes + floats * sizeof(float) + 2 * MAXG * sizeof(uint64_t) + 16 +
+         (getenv("AMPC_TC_TRACE") ? (NTHR / 32) * TRACE_EV * sizeof(uint32_t) + 16 : 0);
 }
 
 int roundup(int v, int m) { return (v + m - 1) / m * m; }
@@ -710,10 +807,11 @@ void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg) {
 }  // namespace
 
 typedef void (*TcKernel)(const AmpcMppiParams, const TcArgs);
-static TcKernel tc_kernel_ptr(int cg, int nxp) {
-#define AMPC_TC_K(N) (cg == 1 ? (TcKernel)mppi_rollout_tc_kernel<1, N> : (TcKernel)mppi_rollout_tc_kernel<2, N>)
+template <bool RELU>
+static TcKernel tc_kernel_ptr_act(int cg, int nxp) {
+#define AMPC_TC_K(N) (cg == 1 ? (TcKernel)mppi_rollout_tc_kernel<1, N, RELU, false> : (TcKernel)mppi_rollout_tc_kernel<2, N, RELU, false>)
 #ifdef AMPC_TC_FAST_BUILD   // local SASS experiments only: one instantiation
-  return (TcKernel)mppi_rollout_tc_kernel<2, 24>;
+  return (TcKernel)mppi_rollout_tc_kernel<2, 24, true, false>;
 #else
   switch (nxp) {
     case 4: return AMPC_TC_K(4);
@@ -725,10 +823,21 @@ static TcKernel tc_kernel_ptr(int cg, int nxp) {
 #endif
 #undef AMPC_TC_K
 }
+// the timeline build (AMPC_TC_TRACE=1) exists for the headline shape only: CTA pairs, NXP = 24, ReLU
+static bool tc_trace_available(int cg, int nxp, int act) { return cg == 2 && nxp == 24 && act == AMPC_ACT_RELU; }
+static TcKernel tc_kernel_ptr(int cg, int nxp, int act, bool traced) {
+#ifdef AMPC_TC_FAST_BUILD
+  return tc_kernel_ptr_act<true>(cg, nxp);
+#else
+  if (traced && tc_trace_available(cg, nxp, act)) return (TcKernel)mppi_rollout_tc_kernel<2, 24, true, true>;
+  return act == AMPC_ACT_RELU ? tc_kernel_ptr_act<true>(cg, nxp) : tc_kernel_ptr_act<false>(cg, nxp);
+#endif
+}
 
 struct AmpcTcPlan {
   TcArgs args;
   int cg = 1;
+  int act = AMPC_ACT_RELU;
   int grid = 0;
   size_t smem = 0;
   uint8_t *d_wimg = nullptr;
@@ -806,6 +915,7 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
     return AMPC_ERR_UNSUPPORTED;
   }
   pl->cg = cg;
+  pl->act = mlp->act;
   TcArgs &a = pl->args;
   const int tiles = (cfg->K + TM - 1) / TM;
   pl->grid = roundup(tiles, cg);
@@ -856,7 +966,7 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
   if (e == cudaSuccess) e = cudaMemcpy(pl->d_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_epsc, (size_t)cfg->H * cfg->nu * a.Kc * sizeof(float));
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(tc_kernel_ptr(cg, a.nxp), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
+    e = cudaFuncSetAttribute(tc_kernel_ptr(cg, a.nxp, mlp->act, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
   if (e != cudaSuccess) {
     ampc_set_error("tcgen05 MPPI path create: %s", cudaGetErrorString(e));
     ampc_mppi_tc_destroy(pl);
@@ -866,7 +976,8 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
   a.bias = pl->d_bias;
   a.epsc = pl->d_epsc;
   a.trace = nullptr;
-  if (getenv("AMPC_TC_TRACE")) {
+  if (getenv("AMPC_TC_TRACE") && tc_trace_available(cg, a.nxp, mlp->act)) {
+    cudaFuncSetAttribute(tc_kernel_ptr(cg, a.nxp, mlp->act, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
     if (cudaMalloc(&pl->d_trace, (NTHR / 32) * TRACE_EV * sizeof(unsigned long long)) == cudaSuccess) {
       cudaMemset(pl->d_trace, 0, (NTHR / 32) * TRACE_EV * sizeof(unsigned long long));
       a.trace = pl->d_trace;
@@ -892,7 +1003,7 @@ int ampc_mppi_tc_launch(AmpcTcPlan *plan, const AmpcMppiParams &p, cudaStream_t 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_kernel_ptr(plan->cg, plan->args.nxp), p, plan->args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_kernel_ptr(plan->cg, plan->args.nxp, plan->act, plan->args.trace != nullptr), p, plan->args);
   ampc_count_launch();
   AMPC_CUDA_CHECK(e);
   return AMPC_OK;

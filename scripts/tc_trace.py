@@ -15,14 +15,17 @@ for wp in range(13):
     for e in buf[wp * 128:(wp + 1) * 128]:
         if e: ev.append((int(e) >> 8, wp, int(e) & 255))
 ev.sort()
-t0 = ev[0][0]
+t0 = 0   # cycles since kernel entry (CTA 0)
+phase = {1: "setup done", 2: "left the horizon loop", 3: "CTA softmax record written", 4: "ticket / merge done", 5: "kernel end"}
 names = {1: "MMA  saw bar_a", 2: "MMA  commit   ", 3: "EPI  saw bar_d", 4: "EPI  released ", 5: "EPI  next input",
          6: "EPI    ld#1 done (half = idx)", 7: "EPI    ld#2 done (half = idx)", 8: "EPI    stores issued (half = idx)",
          9: "OWN    y loaded(0) / integrated(1) / input stored(2): idx ="}
 for t, wp, tag in ev:
     if wp in (0, 4, 12):
         k, idx = tag >> 4, tag & 15
-        if k >= 6:
+        if k == 10:
+            print("%8d  warp %d  PHASE  %s" % (t - t0, wp, phase.get(idx, "?")))
+        elif k >= 6:
             print("%8d  warp %d  %s %d" % (t - t0, wp, names.get(k, "?"), idx))
         else:
             print("%8d  warp %d  %s layer %d half/pair %d" % (t - t0, wp, names.get(k, "?"), idx >> 1, idx & 1))

@@ -125,6 +125,137 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(int N, int R, int alt, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Epilogue primitives: cycles per tcgen05.ld 32x32b.x32 (+wait::ld) and per tcgen05.st x16 (+wait::st) as a
+// function of the number of warps per SM sub-partition doing it concurrently, with the tensor pipe idle or
+// busy with N=128 MMAs accumulating into other TMEM columns (the rollout kernel's situation).
+__global__ void __launch_bounds__(32 * 17, 1) epi_bench(int wps, int mma_on, int R, int dcol, int acol, long long *out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t *base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint32_t *w = reinterpret_cast<uint32_t *>(base);
+  for (int i = threadIdx.x; i < (4 * 128 * 128) / 4; i += blockDim.x) w[i] = 0x3c003c00u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = s_tmem;
+  if (warp == 16) {
+    if (mma_on && lane == 0) {   // keeps the tensor pipe busy: D = columns [256,384), A = columns [384, 448)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t blo = ((smem_u32(base) >> 4) & 0x3FFFu) | (1u << 16);
+      const long long m0 = clock64();
+      for (int r0 = 0; r0 < 320; r0 += 16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint64_t bd = ((uint64_t)DESC_HI << 32) | (uint64_t)(blo + (uint32_t)(j >> 2) * 1024u + (uint32_t)(j & 3) * 2u);
+          mma<1, true>(tb + (uint32_t)dcol, tb + (uint32_t)acol + (uint32_t)(j & 7) * 8u, 0ull, bd, idesc, (r0 + j) > 0 ? 1u : 0u);
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+      while (!mbar_try_wait(smem_u32(&bar), 0)) {}
+      if (blockIdx.x == 0) out[4] = clock64() - m0;
+    }
+  } else if (warp < 4 * wps) {
+    const uint32_t la = tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp >> 2) & 1) * 64);   // columns [0,128)
+    uint32_t r[32];
+    long long t0 = clock64();
+    for (int it = 0; it < R; ++it) {
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+          "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(la + (uint32_t)((it & 1) * 32))
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    }
+    long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) acc ^= r[q];
+    for (int it = 0; it < R; ++it) {
+      asm volatile(
+          "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+          "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(la + (uint32_t)((it & 1) * 16)),
+          "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+          : "memory");
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    long long t2 = clock64();
+    // two loads in flight before one wait
+    for (int it = 0; it < R; ++it) {
+      uint32_t q2[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+          "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(la)
+          : "memory");
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+          "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          : "=r"(q2[0]), "=r"(q2[1]), "=r"(q2[2]), "=r"(q2[3]), "=r"(q2[4]), "=r"(q2[5]), "=r"(q2[6]), "=r"(q2[7]), "=r"(q2[8]),
+            "=r"(q2[9]), "=r"(q2[10]), "=r"(q2[11]), "=r"(q2[12]), "=r"(q2[13]), "=r"(q2[14]), "=r"(q2[15]), "=r"(q2[16]),
+            "=r"(q2[17]), "=r"(q2[18]), "=r"(q2[19]), "=r"(q2[20]), "=r"(q2[21]), "=r"(q2[22]), "=r"(q2[23]), "=r"(q2[24]),
+            "=r"(q2[25]), "=r"(q2[26]), "=r"(q2[27]), "=r"(q2[28]), "=r"(q2[29]), "=r"(q2[30]), "=r"(q2[31])
+          : "r"(la + 32u)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int q = 0; q < 32; ++q) acc ^= r[q] ^ q2[q];
+    }
+    long long t3 = clock64();
+    if (warp == 0 && lane == 0 && blockIdx.x == 0) {
+      out[0] = t1 - t0;
+      out[1] = t2 - t1;
+      out[2] = t3 - t2;
+      out[3] = (long long)acc;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
+}
+
+void run_epi(int wps, int mma_on, int dcol, int acol, long long *d_out) {
+  const int smem = 1024 + 4 * 128 * 128 + 64, R = 200;
+  cudaFuncSetAttribute(epi_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  long long h[5] = {0, 0, 0, 0, 0};
+  for (int it = 0; it < 3; ++it) {
+    cudaMemset(d_out, 0, 40);
+    epi_bench<<<128, 32 * 17, smem>>>(wps, mma_on, R, dcol, acol, d_out);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("epi_bench: CUDA error %s\n", cudaGetErrorString(e));
+      exit(1);
+    }
+    cudaMemcpy(h, d_out, 40, cudaMemcpyDeviceToHost);
+  }
+  printf("epilogue(ld/st cols [0,128)) warps/SMSP=%d mma=%d D@%d A@%d : ld.x32+wait %.0f cyc, st.x16+wait %.0f cyc, 2 x ld.x32 + 64 LOP + wait %.0f cyc; concurrent N=128 MMA %.1f cyc/MMA\n", wps, mma_on, dcol, acol,
+         (double)h[0] / R, (double)h[1] / R, (double)h[2] / R, (double)h[4] / 320);
+}
+
 template <int CG, bool TS>
 void run(int N, int R, int alt, int nb, int grid, long long *d_out) {
   const int smem = 1024 + nb * (N / CG) * 128 + 16384 + 64;
@@ -157,7 +288,13 @@ void run(int N, int R, int alt, int nb, int grid, long long *d_out) {
 
 int main() {
   long long *d_out;
-  cudaMalloc(&d_out, 16);
+  cudaMalloc(&d_out, 64);
+  for (int wps : {1, 2}) run_epi(wps, 0, 256, 384, d_out);
+  for (int wps : {0, 2, 4})
+    for (int cfg = 0; cfg < 4; ++cfg) {
+      const int dcols[4] = {256, 128, 128, 384}, acols[4] = {384, 384, 0, 0};   // A@0 overlaps the ld/st columns (garbage data is fine)
+      run_epi(wps, 1, dcols[cfg], acols[cfg], d_out);
+    }
   const int Ns[3] = {64, 128, 256};
   for (int grid : {128})
     for (int alt = 0; alt < 2; ++alt)
