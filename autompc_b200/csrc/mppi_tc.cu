@@ -223,6 +223,7 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
 __device__ __forceinline__ float quad_full(const float *M, const float *v, const float *off, int n, bool diag, int t) {
   float c = 0.f;
   if (diag) {
+#pragma unroll 8
     for (int i = 0; i < n; ++i) {
       const float di = v[i * TM + t] - (off ? off[i] : 0.f);
       c = fmaf(M[i * n + i] * di, di, c);
@@ -288,8 +289,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   float *s_x = s_act + ((HN + 3) & ~3);                // state [nx][128]
   float *s_u = s_x + nx * TM;                          // scaled control, two buffers of [nu][128]
   float2 *s_zc = reinterpret_cast<float2 *>(s_u + 2 * nu * TM);   // input z-score as (scale, bias) per K column [64]
-  float2 *s_ic = s_zc + 64;                            // integration as (dy_std, b_out*dy_std + dy_mean) per state [32]
-  float2 *s_xc = s_ic + 32;                            // x = z * std + mean per state [32]
+  float2 *s_xc = s_zc + 64;                            // x = z * std + mean per state [32]
   float *s_wgt = reinterpret_cast<float *>(s_xc + 32); // helper cost share, then softmax numerators [128]
   float *s_cc = s_wgt + TM;                            // control warps' cost share [128]
   float *s_red = s_cc + TM;                            // 32
@@ -335,15 +335,12 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   }
   // The owner keeps the NORMALISED state z = (x - mean) / std in registers (it is what the input layer eats):
   //   x' = x + (y + b_out) * dy_std + dy_mean  (mlp.py:26-30, :236)   <=>   z' = z + y * k1 + k2,
-  //   k1 = dy_std / std, k2 = (b_out * dy_std + dy_mean) / std;  x = z * std + mean is recovered off the critical path.
+  //   k1 = dy_std / std, k2 = (b_out * dy_std + dy_mean) / std, both folded into the output layer's weight image
+  //   (rows scaled by k1, k2 on the constant-one K-step), so the accumulator IS the increment of z;
+  //   x = z * std + mean is recovered off the critical path.
   for (int j = tid; j < 32; j += NTHR) {
-    float2 ic = make_float2(0.f, 0.f), xc = make_float2(0.f, 0.f);
-    if (j < nx) {
-      const float ds = p.consts[cl.dy_std + j], inv = p.consts[cl.xu_inv + j];
-      ic = make_float2(ds * inv, fmaf(a.bias[a.b_off[L - 1] + j], ds, p.consts[cl.dy_mean + j]) * inv);
-      xc = make_float2(1.f / inv, p.consts[cl.xu_mean + j]);
-    }
-    s_ic[j] = ic;
+    float2 xc = make_float2(0.f, 0.f);
+    if (j < nx) xc = make_float2(1.f / p.consts[cl.xu_inv + j], p.consts[cl.xu_mean + j]);
     s_xc[j] = xc;
   }
   const uint32_t bar_d0 = smem_u32(&s_bar[0]), bar_a0 = smem_u32(&s_bar[MAXG]);
@@ -440,7 +437,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
               } else {
                 if (ksp_l[l] == 8) issue_pair<CG, 8>(dh, a_pair, hb, kb_stride, idesc, kp == 0);
                 else issue_pair<CG, 4>(dh, a_pair, hb, kb_stride, idesc, kp == 0);
-                if (l < L - 1 && kp == 0)             // constant-one K-step: the layer's bias (extra K block of the image)
+                if (kp == 0)                          // constant-one K-step: the layer's bias (extra K block of the image)
                   umma_ts<CG>(dh, a_addr + (uint32_t)(aw_l[l] >> 2),
                               lo_l[l] + hro_l[l] * (uint32_t)h + (uint32_t)(a.kpad[l] >> 6) * kb_stride, idesc, 1u);
               }
@@ -645,10 +642,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
         tmem_ld32(dbuf + YCOL, r);
         tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < NXP; ++j) {
-          const float2 ic = s_ic[j];
-          z[j] = fmaf(__uint_as_float(r[j]), ic.x, z[j] + ic.y);
-        }
+        for (int j = 0; j < NXP; ++j) z[j] += __uint_as_float(r[j]);   // the image carries dy_std / std and the constants
         if (i + 1 < H) store_input(n & 1u);             // GEMM n+1 reads A from buffer n&1
       }
       if (i + 1 < H) signal_a(0);
@@ -753,7 +747,7 @@ uint16_t f32_to_bf16(float f) {
 size_t tc_smem_bytes(const TcArgs &a, int nx, int nu, int H) {
   const AmpcConstLayout cl(nx, nu);
   const size_t floats = (size_t)cl.total + ((H * nu + 3) & ~3) + (size_t)nx * TM +
-                        (size_t)2 * nu * TM + 2 * 64 + 3 * 2 * 32 + 2 * TM + 32 + 64 + AMPC_MERGE_CACHE;
+                        (size_t)2 * nu * TM + 2 * 64 + 2 * 2 * 32 + 2 * TM + 32 + 64 + AMPC_MERGE_CACHE;
   return 1024 + a.w_bytes + floats * sizeof(float) + 2 * MAXG * sizeof(uint64_t) + 16 +
          (getenv("AMPC_TC_TRACE") ? (NTHR / 32) * TRACE_EV * sizeof(uint32_t) + 16 : 0);
 }
@@ -783,8 +777,8 @@ void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg) {
       const int nl = mlp->dims[l + 1];
       a.npad[l] = (l == mlp->n_layers - 1) ? roundup(nl, 32) : (nl <= 64 ? 64 : (nl <= 128 ? 128 : 256));
     }
-    const bool bias_k = (l >= 1 && l <= mlp->n_layers - 2);
-    a.ones[l] = (l + 1 >= 1 && l + 1 <= mlp->n_layers - 2) ? 1 : 0;
+    const bool bias_k = (l >= 1);                 // layers 1..L-1 take their bias through an extra constant-one K block
+    a.ones[l] = (l <= mlp->n_layers - 2) ? 1 : 0;  // ... written by the epilogue of the layer before them
     const int rows = a.npad[l] / cg, kblk = (a.kpad[l] + 63) / 64 + (bias_k ? 1 : 0);
     a.w_off[l] = off;
     off += (uint32_t)kblk * rows * 128;
@@ -925,7 +919,8 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
   std::vector<float> bias(a.bias_floats, 0.f);
   for (int l = 0; l < mlp->n_layers; ++l) {
     const int Kl = mlp->dims[l], Nl = mlp->dims[l + 1];
-    const bool bias_k = (l >= 1 && l <= mlp->n_layers - 2);
+    const bool bias_k = (l >= 1);
+    const bool outl = (l == mlp->n_layers - 1);
     const int kdata = (a.kpad[l] + 63) / 64;      // K blocks of data; the bias block (if any) follows
     const int rows = a.npad[l] / cg, kblk = kdata + (bias_k ? 1 : 0);
     for (int r = 0; r < cg; ++r)
@@ -943,13 +938,17 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
                 const int nx = mlp->dims[mlp->n_layers], nu = Kl - nx;
                 kin = (k < a.nxp) ? (k < nx ? k : -1) : (k - a.nxp < nu ? nx + (k - a.nxp) : -1);
               }
-              float v = (ng < Nl && kin >= 0 && kin < Kl && kb < kdata) ? (float)mlp->W[l][(size_t)ng * Kl + kin] : 0.f;
+              // output layer: rows scaled so that the GEMM yields the increment of the NORMALISED state directly:
+              //   z' = z + k1 * (W h + b) + dy_mean / std,  k1 = dy_std / std   (mlp.py:26-30, :236 in z space)
+              const double k1 = (outl && ng < Nl) ? mlp->dy_std[ng] / mlp->xu_std[ng] : 1.0;
+              float v = (ng < Nl && kin >= 0 && kin < Kl && kb < kdata) ? (float)(mlp->W[l][(size_t)ng * Kl + kin] * k1) : 0.f;
               // bias of hidden layers: two bf16 terms (hi + lo) against the constant-one inputs
               int bsel = -1;
               if (l == 0 && l <= mlp->n_layers - 2) bsel = k - (a.nxp + (Kl - mlp->dims[mlp->n_layers]));
               if (bias_k && kb == kdata) bsel = k - kb * 64;
               if (ng < Nl && (bsel == 0 || bsel == 1)) {
-                const float b = (float)mlp->b[l][ng];
+                const float b = outl ? (float)((mlp->b[l][ng] * mlp->dy_std[ng] + mlp->dy_mean[ng]) / mlp->xu_std[ng])
+                                     : (float)mlp->b[l][ng];
                 uint32_t hb = (uint32_t)f32_to_bf16(b) << 16;
                 float bhi;
                 memcpy(&bhi, &hb, 4);

@@ -26,6 +26,10 @@ pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": dict(cost_rtol=2e-5, act_atol=2e-3), "bf16": dict(cost_rtol=2e-3, act_atol=5e-2)}
 
+# sharded vs unsharded solves run the same per-sample arithmetic (Philox is keyed by the global sample index);
+# they differ only in the fp32 summation order of the softmax merge: a few ulp of O(1) controls
+SHARD_ATOL = 5e-6
+
 
 def _engine(p, cost, umin, umax, **kw):
     from autompc_b200 import MPPI
@@ -225,11 +229,11 @@ def test_sharded_partials_merge_equals_single_handle():
     for h in shards:
         _abi.check(lib.ampc_mppi_merge(h, allrec.data_ptr(), len(shards), u_d.data_ptr(), None))
     torch.cuda.synchronize()
-    np.testing.assert_allclose(u_d.cpu().numpy(), u_full, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(u_d.cpu().numpy(), u_full, rtol=0, atol=SHARD_ATOL)
     for h in shards:
         a = np.empty((H, 6))
         _abi.check(lib.ampc_mppi_get_act_seq(h, _abi.dptr(a)))
-        np.testing.assert_allclose(a, full.act_sequence, rtol=0, atol=2e-6)
+        np.testing.assert_allclose(a, full.act_sequence, rtol=0, atol=SHARD_ATOL)
         lib.ampc_mppi_destroy(h)
     full.close()
 
@@ -396,10 +400,10 @@ def test_fused_peer_exchange_two_shards_one_device():
                                                  streams[r].cuda_stream))
         torch.cuda.synchronize()
         for r in range(2):
-            np.testing.assert_allclose(us[r].cpu().numpy(), u_ref[-1], rtol=0, atol=2e-6)
+            np.testing.assert_allclose(us[r].cpu().numpy(), u_ref[-1], rtol=0, atol=SHARD_ATOL)
     for r in range(2):
         a = np.empty((H, 6))
         _abi.check(lib.ampc_mppi_get_act_seq(hs[r], _abi.dptr(a)))
-        np.testing.assert_allclose(a, full.act_sequence, rtol=0, atol=2e-6)
+        np.testing.assert_allclose(a, full.act_sequence, rtol=0, atol=SHARD_ATOL)
         lib.ampc_mppi_destroy(hs[r])
     full.close()
