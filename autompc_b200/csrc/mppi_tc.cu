@@ -15,13 +15,13 @@
 // With CG=2 the kernel runs as CTA pairs (cta_group::2, UMMA M=256): each CTA keeps HALF of the
 // output neurons of every layer in its shared memory, which is what lets the 3x256 network
 // (283 KB of bf16 weights) stay resident; the leader CTA's single MMA thread issues for both.
-// Warps 0-3 ("owners", thread t <-> sample t, state in registers): integration, z-score, next input.
-// Warps 4-7 ("helpers", thread 128+t <-> sample t): stage cost of the state.  Both groups share the
-// layer epilogues: warp w serves TMEM lane quarter w%4 and one 32/64-column half of every N-half.
-// Warps 8-11 ("control", thread 256+t <-> sample t): Philox noise, clipping, clipped-noise write-back,
+// Warps 0-3 ("control", thread t <-> sample t): Philox noise, clipping, clipped-noise write-back,
 // action and control cost -- run one horizon step AHEAD of the GEMM chain through a double-buffered
 // shared array handed over with named barriers, so none of it is on the critical path.
-// Warp 12: MMA issue + TMEM allocation.
+// Warps 4-7 ("owners", thread 128+t <-> sample t, normalised state in registers): integration, next input.
+// Warps 8-11 ("helpers", thread 256+t <-> sample t): stage cost of the state.  Both groups share the
+// layer epilogues: warp w serves TMEM lane quarter w%4 and one 32/64-column half of every N-half.
+// Warp 12: MMA issue + TMEM allocation.  (Role order = issue priority: highest warp id first.)
 // Pipelining inside the dependent GEMM chain.  Every GEMM is issued at full width (N up to 256: 16
 // tcgen05.mma of K=16 per 256-wide layer), accumulating alternately into two 256-column TMEM
 // buffers.  The epilogue of GEMM n reads D_n 64 columns at a time and writes the packed bf16
@@ -256,11 +256,11 @@ __device__ __forceinline__ void epi_pack(const uint32_t (&r)[NV], int act, uint3
 // Issues the KSP K-steps of one K-pair of one N-half, fully unrolled with compile-time column offsets:
 // the pair's K elements sit in two sub-halves (one per epilogue warp of a lane quarter), each packed at the
 // start of its own KSP*8 accumulator columns.
-template <int CG, int KSP>
+template <int CG, int KSP, int J0 = 0, int J1 = KSP>
 __device__ __forceinline__ void issue_pair(uint32_t dh, uint32_t a_pair, uint32_t desc_pair, uint32_t kb_stride,
                                            uint32_t idesc, bool first_pair) {
 #pragma unroll
-  for (int j = 0; j < KSP; ++j) {
+  for (int j = J0; j < J1; ++j) {
     const uint32_t acol = (uint32_t)((j / (KSP / 2)) * (KSP * 8) + (j % (KSP / 2)) * 8);
     const uint32_t d = desc_pair + (uint32_t)(j >> 2) * kb_stride + (uint32_t)(j & 3) * 2u;
     umma_ts<CG>(dh, a_pair + acol, d, idesc, (j == 0 && first_pair) ? 0u : 1u);
@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   float *s_x = s_act + ((HN + 3) & ~3);                // state [nx][128]
   float *s_u = s_x + nx * TM;                          // scaled control, two buffers of [nu][128]
   float2 *s_zc = reinterpret_cast<float2 *>(s_u + 2 * nu * TM);   // input z-score as (scale, bias) per K column [64]
-  float2 *s_xc = s_zc + 64;                            // x = z * std + mean per state [32]
+  float4 *s_qc = reinterpret_cast<float4 *>(s_zc + 64);   // stage cost from z: (std, mean - goal, Q_jj, 0) per state [32]
+  float2 *s_xc = reinterpret_cast<float2 *>(s_qc + 32);                            // x = z * std + mean per state [32]
   float *s_wgt = reinterpret_cast<float *>(s_xc + 32); // helper cost share, then softmax numerators [128]
   float *s_cc = s_wgt + TM;                            // control warps' cost share [128]
   float *s_red = s_cc + TM;                            // 32
@@ -340,8 +341,13 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   //   x = z * std + mean is recovered off the critical path.
   for (int j = tid; j < 32; j += NTHR) {
     float2 xc = make_float2(0.f, 0.f);
-    if (j < nx) xc = make_float2(1.f / p.consts[cl.xu_inv + j], p.consts[cl.xu_mean + j]);
+    float4 qc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < nx) {
+      xc = make_float2(1.f / p.consts[cl.xu_inv + j], p.consts[cl.xu_mean + j]);
+      qc = make_float4(xc.x, xc.y - p.consts[cl.goal + j], p.consts[cl.Q + j * nx + j], 0.f);
+    }
     s_xc[j] = xc;
+    s_qc[j] = qc;
   }
   const uint32_t bar_d0 = smem_u32(&s_bar[0]), bar_a0 = smem_u32(&s_bar[MAXG]);
   if (tid == 0) {
@@ -418,6 +424,11 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
           const uint32_t idesc = id_l[l], kb_stride = kbs_l[l];
           const uint32_t d_addr = (n & 1u) * TMEM_BUF + (l == L - 1 ? (uint32_t)YCOL : 0u);
           const uint32_t a_addr = ((n + 1u) & 1u) * TMEM_BUF;
+          // Full-width hidden GEMMs (two N-halves, two K-pairs of 8 K-steps) are issued as
+          //   (h0,kp0) (h1,kp0: first 4 K-steps) | wait kp1 | (h0,kp1)+commit0 (h1,kp0: last 4) (h1,kp1)+commit1
+          // so that 12 MMAs (~800 cycles) are still queued behind commit0: the epilogue of half 0 and both hand-overs
+          // (~700 cycles) finish before the pipe drains, while the 14 MMAs of the first phase cover the wait for kp1.
+          const bool defer = (l > 0 && nh == 2 && nkp == 2 && ksp_l[l] == 8);
           for (int kp = 0; kp < nkp; ++kp) {
             mbar_wait(bar_a0 + 8u * kp, (pa >> kp) & 1u);
             pa ^= (1u << kp);
@@ -427,20 +438,27 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
             const uint32_t pair_off = (uint32_t)((kp * ksp_l[l]) >> 2) * kb_stride;
             for (int h = 0; h < nh; ++h) {
               const uint32_t dh = d_addr + (uint32_t)(h * hw_l[l]);
-              const uint32_t hb = lo_l[l] + hro_l[l] * (uint32_t)h + pair_off;
+              const uint32_t hb0 = lo_l[l] + hro_l[l] * (uint32_t)h;
+              const uint32_t hb = hb0 + pair_off;
               if (l == 0) {                           // input layer: 1..4 K-steps at columns {0, 8, 32, 40}
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                   if (ks < nks0)
                     umma_ts<CG>(dh, a_pair + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8), hb + (uint32_t)(ks * 2), idesc,
                                 ks > 0 ? 1u : 0u);
+              } else if (defer && h == 1) {
+                if (kp == 0) {
+                  issue_pair<CG, 8, 0, 4>(dh, a_pair, hb, kb_stride, idesc, true);
+                } else {
+                  issue_pair<CG, 8, 4, 8>(dh, a_addr, hb0, kb_stride, idesc, false);   // rest of K-pair 0
+                  issue_pair<CG, 8>(dh, a_pair, hb, kb_stride, idesc, false);
+                }
               } else {
                 if (ksp_l[l] == 8) issue_pair<CG, 8>(dh, a_pair, hb, kb_stride, idesc, kp == 0);
                 else issue_pair<CG, 4>(dh, a_pair, hb, kb_stride, idesc, kp == 0);
-                if (kp == 0)                          // constant-one K-step: the layer's bias (extra K block of the image)
-                  umma_ts<CG>(dh, a_addr + (uint32_t)(aw_l[l] >> 2),
-                              lo_l[l] + hro_l[l] * (uint32_t)h + (uint32_t)(a.kpad[l] >> 6) * kb_stride, idesc, 1u);
               }
+              if (l > 0 && kp == 0)                   // constant-one K-step: the layer's bias (extra K block of the image)
+                umma_ts<CG>(dh, a_addr + (uint32_t)(aw_l[l] >> 2), hb0 + (uint32_t)(a.kpad[l] >> 6) * kb_stride, idesc, 1u);
               if (kp == nkp - 1) { umma_commit<CG>(bar_d0 + 8u * h); trace(i, 0x20 + l * 2 + h); }   // half h committed
             }
           }
@@ -449,8 +467,12 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
       }
     }
     __syncwarp();
-  } else if (warp >= NEPI / 32) {
-    // =========================== control warps (8-11): one horizon step ahead ===========================
+  } else if (warp < NCTL / 32) {
+    // =========================== control warps (0-3): one horizon step ahead ===========================
+    // Lowest warp ids on purpose: the SM sub-partition's arbiter favours the highest eligible warp id, so the
+    // long ALU streams of the noise generator only take issue slots the latency-critical warps (epilogue 4-11,
+    // MMA issuer 12) leave free.  (With the control warps on ids 8-11 the owners' and helpers' short critical
+    // sections ran 3-5x slower whenever Philox was in flight.)
     const uint32_t kg = (uint32_t)(p.k_offset + k_local);
     const int nblk = (nu + 3) >> 2;
     // controls of step i: noise, clip, write-back (mppi.py:134-139), action cost (:143), control cost (:142)
@@ -497,8 +519,8 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
     // dependent GEMM chain, so this code is kept short: layers and halves are unrolled at compile time (their
     // shapes come straight from the constant bank), both TMEM loads of a half are issued before the one wait,
     // and no debug code is compiled in unless TRACE.
-    const bool owner = warp < 4;
-    const int hf = warp >> 2;                           // which 32 of every 64 columns this warp serves
+    const bool owner = warp < 8;                        // warps 4-7: owners, 8-11: helpers
+    const int hf = (warp >> 2) - 1;                     // which 32 of every 64 columns this warp serves
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t pd = 0;                                    // parity bit h of bar_d[h]
     uint32_t n = 0;                                     // GEMM counter (see the issuer)
@@ -621,12 +643,33 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
           trace(i, 0x40 + l * 2 + h);                   // half h packed and released
         }
         if (l == 0) {                                   // off the critical path: the next GEMM's MMAs are running
-          if (owner) {                                  // x_i = z * std + mean -> shared copy for the stage cost
-            store_x();
+          if (owner) {                                  // hand the (normalised) state to the helper: plain stores
+#pragma unroll
+            for (int j = 0; j < NXP; ++j)
+              if (j < nx) s_x[j * TM + t] = z[j];
             asm volatile("bar.arrive %0, %1;" ::"n"(BAR_X), "n"(NEPI) : "memory");
-          } else {
+            trace(i, 0xB0);                             // state copy stored
+          } else {                                      // stage cost (x_i - g)^T Q (x_i - g), x_i = z * std + mean   (mppi.py:142)
             asm volatile("bar.sync %0, %1;" ::"n"(BAR_X), "n"(NEPI) : "memory");
-            cost_acc += quad_full(c_Q, s_x, c_goal, nx, p.q_diag, t);                                   // mppi.py:142
+            trace(i, 0xB1);                             // state copy visible
+            if (p.q_diag) {
+              float c = 0.f;
+#pragma unroll 8
+              for (int j = 0; j < nx; ++j) {
+                const float4 qc = s_qc[j];
+                const float d = fmaf(s_x[j * TM + t], qc.x, qc.y);
+                c = fmaf(qc.z * d, d, c);
+              }
+              cost_acc += c;
+            } else {                                    // dense Q: x - g in place (column t is this sample's own), then the full form
+#pragma unroll 8
+              for (int j = 0; j < nx; ++j) {
+                const float4 qc = s_qc[j];
+                s_x[j * TM + t] = fmaf(s_x[j * TM + t], qc.x, qc.y);
+              }
+              cost_acc += quad_full(c_Q, s_x, nullptr, nx, false, t);
+            }
+            trace(i, 0xB2);                             // stage cost done
           }
         }
         ++n;
@@ -659,7 +702,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   float c = INFINITY;
   if (tid < TM) {
     const float term = quad_full(c_F, s_x, c_goal, nx, p.f_diag, tid);   // mppi.py:79-82, :146-148
-    c = cost_acc + s_wgt[tid] + s_cc[tid];
+    c = s_wgt[tid] + s_cc[tid];                      // helpers' state costs + control warps' action/control costs
     if (p.terminal_mode == 1) c += term;
     else if (valid && (p.k_offset + k_local) == p.K_global - 1) *p.term_out = term;
     if (valid) p.costs[k_local] = c; else c = INFINITY;
@@ -747,7 +790,7 @@ uint16_t f32_to_bf16(float f) {
 size_t tc_smem_bytes(const TcArgs &a, int nx, int nu, int H) {
   const AmpcConstLayout cl(nx, nu);
   const size_t floats = (size_t)cl.total + ((H * nu + 3) & ~3) + (size_t)nx * TM +
-                        (size_t)2 * nu * TM + 2 * 64 + 2 * 2 * 32 + 2 * TM + 32 + 64 + AMPC_MERGE_CACHE;
+                        (size_t)2 * nu * TM + 2 * 64 + 2 * 2 * 32 + 4 * 32 + 2 * TM + 32 + 64 + AMPC_MERGE_CACHE;
   return 1024 + a.w_bytes + floats * sizeof(float) + 2 * MAXG * sizeof(uint64_t) + 16 +
          (getenv("AMPC_TC_TRACE") ? (NTHR / 32) * TRACE_EV * sizeof(uint32_t) + 16 : 0);
 }

@@ -21,9 +21,11 @@ names = {1: "MMA  saw bar_a", 2: "MMA  commit   ", 3: "EPI  saw bar_d", 4: "EPI 
          6: "EPI    ld#1 done (half = idx)", 7: "EPI    ld#2 done (half = idx)", 8: "EPI    stores issued (half = idx)",
          9: "OWN    y loaded(0) / integrated(1) / input stored(2): idx ="}
 for t, wp, tag in ev:
-    if wp in (0, 4, 12):
+    if wp in (4, 8, 12):
         k, idx = tag >> 4, tag & 15
-        if k == 10:
+        if k == 11:
+            print("%8d  warp %d  COST   %s" % (t - t0, wp, {0: "owner: state copy stored", 1: "helper: state copy visible", 2: "helper: stage cost done"}.get(idx, "?")))
+        elif k == 10:
             print("%8d  warp %d  PHASE  %s" % (t - t0, wp, phase.get(idx, "?")))
         elif k >= 6:
             print("%8d  warp %d  %s %d" % (t - t0, wp, names.get(k, "?"), idx))
