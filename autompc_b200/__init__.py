@@ -8,6 +8,7 @@ from .mlp import B200MLP, MLPWeights  # noqa: F401
 from .mppi import MPPI, MPPIFactory  # noqa: F401
 from .ilqr import IterativeLQR, IterativeLQRFactory  # noqa: F401
 from .closed_loop import simulate, evaluate_candidates  # noqa: F401
+from .evaluation import get_model_rmse  # noqa: F401
 
 __all__ = ["MPPI", "MPPIFactory", "IterativeLQR", "IterativeLQRFactory", "B200MLP", "MLPWeights", "simulate",
-           "evaluate_candidates"]
+           "evaluate_candidates", "get_model_rmse"]

@@ -27,7 +27,7 @@ class MlpDesc(C.Structure):
 
 
 class QuadCost(C.Structure):
-    _fields_ = [("Q", _dp), ("R", _dp), ("F", _dp), ("goal", _dp), ("umin", _dp), ("umax", _dp)]
+    _fields_ = [("Q", _dp), ("R", _dp), ("F", _dp), ("goal", _dp), ("umin", _dp), ("umax", _dp), ("goal_term", _dp)]
 
 
 class MppiCfg(C.Structure):
@@ -66,6 +66,7 @@ EXPORTS = {
     "ampc_mlp_create": [C.POINTER(C.c_void_p), C.POINTER(MlpDesc), C.c_int32, C.c_int32, C.c_int32],
     "ampc_mlp_destroy": [C.c_void_p],
     "ampc_mlp_pred_batch": [C.c_void_p, C.c_int32, _dp, _dp, _dp],
+    "ampc_mlp_rollout_batch": [C.c_void_p, C.c_int32, C.c_int32, _dp, _dp, _dp],
     "ampc_mlp_pred_diff_batch": [C.c_void_p, C.c_int32, _dp, _dp, _dp, _dp, _dp],
     "ampc_ilqr_create": [C.POINTER(C.c_void_p), C.POINTER(IlqrCfg), C.POINTER(MlpDesc), C.POINTER(QuadCost)],
     "ampc_ilqr_destroy": [C.c_void_p],
@@ -140,7 +141,10 @@ class MlpDescHolder:
 
 
 class QuadCostHolder:
-    def __init__(self, Q, R, F, goal, umin, umax, nx, nu):
+    def __init__(self, Q, R, F, goal, umin, umax, nx, nu, goal_term=None):
         self.keep = [f64(Q, (nx, nx)), f64(R, (nu, nu)), f64(F, (nx, nx)), f64(goal, (nx,)),
                      f64(umin, (nu,)), f64(umax, (nu,))]
         self.desc = QuadCost(*[dptr(x) for x in self.keep])
+        if goal_term is not None:
+            self.keep.append(f64(goal_term, (nx,)))
+            self.desc.goal_term = dptr(self.keep[-1])

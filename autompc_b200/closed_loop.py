@@ -54,7 +54,9 @@ def _finish(controller, T):
     obs, ctrls, cost = np.empty((T + 1, nx)), np.zeros((T + 1, nu)), C.c_double(0.0)
     _abi.check(_abi.lib().ampc_mppi_closed_loop_finish(controller._h, T, _abi.dptr(obs), _abi.dptr(ctrls[:T]),
                                                        C.byref(cost)))
-    return SimResult(obs, ctrls, cost.value)       # like the reference trajectory: last control row is zero
+    # constants of a folded SumCost: Cost.__call__ (cost.py:27-41) adds the stage cost of all T+1 states + one terminal
+    total = cost.value + (T + 1) * controller._stage_const + controller._term_const
+    return SimResult(obs, ctrls, total)            # like the reference trajectory: last control row is zero
 
 
 def simulate(controller, init_obs, term_cond=None, dynamics=None, sim_model=None, max_steps=10000, silent=True):

@@ -124,7 +124,7 @@ __device__ __forceinline__ float ampc_warp_min(float v) {
 // ----------------------------------------------------- MPPI kernel params ---
 // Layout of the fp32 constant block both rollout kernels stage into shared memory.
 struct AmpcConstLayout {
-  int xu_mean, xu_inv, dy_mean, dy_std, goal, Q, R, F, lo, hi, scale, total;
+  int xu_mean, xu_inv, dy_mean, dy_std, goal, goalF, Q, R, F, lo, hi, scale, total;
   __host__ __device__ AmpcConstLayout(int nx, int nu) {
     int o = 0;
     xu_mean = o; o += nx + nu;
@@ -132,6 +132,7 @@ struct AmpcConstLayout {
     dy_mean = o; o += nx;
     dy_std = o; o += nx;
     goal = o; o += nx;
+    goalF = o; o += nx;   // goal of the terminal term (== goal unless a SumCost was folded)
     Q = o; o += nx * nx;
     R = o; o += nu * nu;
     F = o; o += nx * nx;

@@ -68,6 +68,32 @@ __global__ void __launch_bounds__(NT) pred_diff_kernel(const AmpcMlpF64 net, int
   }
 }
 
+// k-step open-loop prediction: window s starts at X0[s] and is advanced `horizon` times with the recorded controls
+// U[k][s] -- the inner loop of get_model_rmse (autompc/evaluation/model_metrics.py:33-35) as one launch.  Each step
+// is pred_batch_kernel's arithmetic, so the result equals `horizon` chained pred_batch calls bit for bit.
+__global__ void __launch_bounds__(NT) rollout_batch_kernel(const AmpcMlpF64 net, int batch, int horizon, const double *X0,
+                                                           const double *U, double *Xh) {
+  extern __shared__ double sm_d[];
+  const int s = blockIdx.x;
+  if (s >= batch) return;
+  const int nx = net.nx, nu = net.nu;
+  double *h0 = sm_d, *h1 = sm_d + net.max_width, *x = h1 + net.max_width;
+  for (int j = threadIdx.x; j < nx; j += NT) x[j] = X0[(size_t)s * nx + j];
+  __syncthreads();
+  for (int k = 0; k < horizon; ++k) {
+    const double *u = U + ((size_t)k * batch + s) * nu;
+    for (int j = threadIdx.x; j < nx + nu; j += NT) {
+      const double v = j < nx ? x[j] : u[j - nx];
+      h0[j] = (v - net.xu_mean[j]) / net.xu_std[j];
+    }
+    __syncthreads();
+    const double *out = ampc_mlp_f64_forward(net, h0, h1, nullptr, threadIdx.x, NT);
+    for (int j = threadIdx.x; j < nx; j += NT) x[j] = x[j] + (out[j] * net.dy_std[j] + net.dy_mean[j]);
+    __syncthreads();
+  }
+  for (int j = threadIdx.x; j < nx; j += NT) Xh[(size_t)s * nx + j] = x[j];
+}
+
 // One closed-loop plant step on the device: x <- sim.pred(x, u) (mlp.py:219-227, float64), plus the float32 copy the
 // next solve reads, the trajectory record and the running trajectory cost of Cost.__call__ (cost.py:27-41).
 __global__ void __launch_bounds__(NT) sim_step_kernel(const AmpcMlpF64 net, double *x, const float *u, float *x32,
@@ -108,15 +134,17 @@ __global__ void __launch_bounds__(NT) sim_step_kernel(const AmpcMlpF64 net, doub
 
 // terminal part of Cost.__call__: obs cost of the last state (its control is zero) + terminal cost
 __global__ void traj_cost_final_kernel(int nx, const double *x, const double *Q, const double *F, const double *goal,
+                                       const double *goalF,
                                        double *cost) {
   if (threadIdx.x != 0) return;
   double c = 0.0;
   for (int pass = 0; pass < 2; ++pass) {
     const double *M = pass == 0 ? Q : F;
+    const double *goal_p = pass == 0 ? goal : goalF;
     for (int j = 0; j < nx; ++j) {
       double col = 0.0;
-      for (int i = 0; i < nx; ++i) col += (x[i] - goal[i]) * M[i * nx + j];
-      c += col * (x[j] - goal[j]);
+      for (int i = 0; i < nx; ++i) col += (x[i] - goal_p[i]) * M[i * nx + j];
+      c += col * (x[j] - goal_p[j]);
     }
   }
   *cost += c;
@@ -137,8 +165,8 @@ int ampc_mlp_sim_step_launch(ampc_mlp *m, double *d_x, const float *d_u, float *
 }
 
 int ampc_traj_cost_final_launch(int nx, const double *d_x, const double *d_Q, const double *d_F, const double *d_goal,
-                                double *d_cost, cudaStream_t s) {
-  traj_cost_final_kernel<<<1, 32, 0, s>>>(nx, d_x, d_Q, d_F, d_goal, d_cost);
+                                const double *d_goalF, double *d_cost, cudaStream_t s) {
+  traj_cost_final_kernel<<<1, 32, 0, s>>>(nx, d_x, d_Q, d_F, d_goal, d_goalF, d_cost);
   ampc_count_launch();
   AMPC_CUDA_CHECK(cudaGetLastError());
   return AMPC_OK;
@@ -262,4 +290,27 @@ extern "C" int ampc_mlp_pred_diff_batch(ampc_mlp *m, int32_t batch, const double
                                         double *Jx, double *Ju) {
   AMPC_REQUIRE(Jx && Ju, AMPC_ERR_INVALID, "null Jacobian output");
   return run_mlp(m, batch, X, U, Xn, Jx, Ju);
+}
+
+extern "C" int ampc_mlp_rollout_batch(ampc_mlp *m, int32_t batch, int32_t horizon, const double *X0, const double *U,
+                                      double *Xh) {
+  AMPC_REQUIRE(m && X0 && U && Xh && batch >= 0 && horizon >= 1, AMPC_ERR_INVALID, "bad argument");
+  if (batch == 0) return AMPC_OK;
+  AMPC_CUDA_CHECK(cudaSetDevice(m->device));
+  const int nx = m->net.nx, nu = m->net.nu;
+  const size_t nX = (size_t)batch * nx, nU = (size_t)horizon * batch * nu;
+  double *d = nullptr;
+  AMPC_CUDA_CHECK(cudaMalloc(&d, (2 * nX + nU) * sizeof(double)));
+  double *dX = d, *dU = dX + nX, *dXh = dU + nU;
+  cudaError_t e = cudaMemcpy(dX, X0, nX * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dU, U, nU * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rollout_batch_kernel<<<batch, NT, m->smem_pred + nx * sizeof(double)>>>(m->net, batch, horizon, dX, dU, dXh);
+    ampc_count_launch();
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(Xh, dXh, nX * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  AMPC_CUDA_CHECK(e);
+  return AMPC_OK;
 }

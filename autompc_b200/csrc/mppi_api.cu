@@ -61,9 +61,9 @@ struct ampc_mppi {
   int world = 1, rank = 0;
   unsigned int seq = 0;
   // device-resident closed loop
-  double *d_cl = nullptr;          // [ x (nx) | cost (1) | Q | R | F | goal | obs (T+1, nx) | ctrl (T, nu) ]
+  double *d_cl = nullptr;          // [ x (nx) | cost (1) | Q | R | F | goal | goal_term | obs (T+1, nx) | ctrl (T, nu) ]
   int cl_T = 0;
-  std::vector<double> h_cost;      // Q, R, F, goal as given at create (float64)
+  std::vector<double> h_cost;      // Q, R, F, goal, goal_term as given at create (float64)
 };
 
 namespace {
@@ -231,6 +231,10 @@ extern "C" int ampc_mppi_create(ampc_mppi **out, const ampc_mppi_cfg *cfg, const
   h->h_cost.insert(h->h_cost.end(), cost->R, cost->R + nu * nu);
   h->h_cost.insert(h->h_cost.end(), cost->F, cost->F + nx * nx);
   h->h_cost.insert(h->h_cost.end(), cost->goal, cost->goal + nx);
+  {
+    const double *gt = cost->goal_term ? cost->goal_term : cost->goal;
+    h->h_cost.insert(h->h_cost.end(), gt, gt + nx);
+  }
   // constants block
   const AmpcConstLayout cl(nx, nu);
   std::vector<float> hc(cl.total, 0.f);
@@ -242,6 +246,7 @@ extern "C" int ampc_mppi_create(ampc_mppi **out, const ampc_mppi_cfg *cfg, const
     hc[cl.dy_mean + j] = (float)mlp->dy_mean[j];
     hc[cl.dy_std + j] = (float)mlp->dy_std[j];
     hc[cl.goal + j] = (float)cost->goal[j];
+    hc[cl.goalF + j] = (float)(cost->goal_term ? cost->goal_term[j] : cost->goal[j]);
   }
   for (int i = 0; i < nx * nx; ++i) { hc[cl.Q + i] = (float)cost->Q[i]; hc[cl.F + i] = (float)cost->F[i]; }
   for (int i = 0; i < nu * nu; ++i) hc[cl.R + i] = (float)cost->R[i];
@@ -547,6 +552,7 @@ int ampc_mlp_nu(const ampc_mlp *m);
 int ampc_mlp_sim_step_launch(ampc_mlp *m, double *d_x, const float *d_u, float *d_x32, double *d_obs_next, double *d_ctrl_t,
                              const double *d_Q, const double *d_R, const double *d_goal, double *d_cost, cudaStream_t s);
 int ampc_traj_cost_final_launch(int nx, const double *d_x, const double *d_Q, const double *d_F, const double *d_goal,
+                                const double *d_goalF,
                                 double *d_cost, cudaStream_t s);
 
 extern "C" int ampc_mppi_closed_loop_start(ampc_mppi *h, ampc_mlp *sim, const double *x0, int32_t T, uint64_t seed,
@@ -558,7 +564,7 @@ extern "C" int ampc_mppi_closed_loop_start(ampc_mppi *h, ampc_mlp *sim, const do
                "the device-resident closed loop runs on one GPU (unsharded controller)");
   DeviceGuard g(h->device);
   const int nx = h->cfg.nx, nu = h->cfg.nu;
-  const size_t fixed = (size_t)nx + 1 + (size_t)2 * nx * nx + (size_t)nu * nu + nx;
+  const size_t fixed = (size_t)nx + 1 + (size_t)2 * nx * nx + (size_t)nu * nu + 2 * (size_t)nx;
   if (h->cl_T < T) {
     cudaFree(h->d_cl);
     h->d_cl = nullptr;
@@ -567,7 +573,8 @@ extern "C" int ampc_mppi_closed_loop_start(ampc_mppi *h, ampc_mlp *sim, const do
     h->cl_T = T;
   }
   double *d_x = h->d_cl, *d_cost = d_x + nx, *d_Q = d_cost + 1, *d_R = d_Q + nx * nx, *d_F = d_R + nu * nu,
-         *d_goal = d_F + nx * nx, *d_obs = d_goal + nx, *d_ctrl = d_obs + (size_t)(h->cl_T + 1) * nx;
+         *d_goal = d_F + nx * nx, *d_goalF = d_goal + nx, *d_obs = d_goalF + nx,
+         *d_ctrl = d_obs + (size_t)(h->cl_T + 1) * nx;
   std::vector<double> init(fixed, 0.0);
   for (int j = 0; j < nx; ++j) init[j] = x0[j];
   for (size_t i = 0; i < h->h_cost.size(); ++i) init[nx + 1 + i] = h->h_cost[i];
@@ -583,14 +590,14 @@ extern "C" int ampc_mppi_closed_loop_start(ampc_mppi *h, ampc_mlp *sim, const do
                                   d_R, d_goal, d_cost, h->stream);
     if (rc) return rc;
   }
-  return ampc_traj_cost_final_launch(nx, d_x, d_Q, d_F, d_goal, d_cost, h->stream);
+  return ampc_traj_cost_final_launch(nx, d_x, d_Q, d_F, d_goal, d_goalF, d_cost, h->stream);
 }
 
 extern "C" int ampc_mppi_closed_loop_finish(ampc_mppi *h, int32_t T, double *obs_out, double *ctrl_out, double *cost_out) {
   AMPC_REQUIRE(h && h->d_cl && T >= 1 && T <= h->cl_T, AMPC_ERR_INVALID, "no closed loop of that length in flight");
   DeviceGuard g(h->device);
   const int nx = h->cfg.nx, nu = h->cfg.nu;
-  double *d_x = h->d_cl, *d_cost = d_x + nx, *d_obs = d_cost + 1 + 2 * nx * nx + nu * nu + nx,
+  double *d_x = h->d_cl, *d_cost = d_x + nx, *d_obs = d_cost + 1 + 2 * nx * nx + nu * nu + 2 * nx,
          *d_ctrl = d_obs + (size_t)(h->cl_T + 1) * nx;
   AMPC_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   if (obs_out) AMPC_CUDA_CHECK(cudaMemcpy(obs_out, d_obs, (size_t)(T + 1) * nx * sizeof(double), cudaMemcpyDeviceToHost));

@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(NTHR) mppi_rollout_fp32_kernel(const AmpcMppiP
   }
 
   // ---- terminal cost (mppi.py:79-82, :146-148)
-  const float term_acc = quad_rows(c_F, s_x, c_goal, nx, p.f_diag, warp, lane);
+  const float term_acc = quad_rows(c_F, s_x, s_const + cl.goalF, nx, p.f_diag, warp, lane);
   s_red[warp * BM + lane] = cost_acc;
   s_red[(NWARP + warp) * BM + lane] = term_acc;
   __syncthreads();

@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   __syncthreads();
   float c = INFINITY;
   if (tid < TM) {
-    const float term = quad_full(c_F, s_x, c_goal, nx, p.f_diag, tid);   // mppi.py:79-82, :146-148
+    const float term = quad_full(c_F, s_x, s_const + cl.goalF, nx, p.f_diag, tid);   // mppi.py:79-82, :146-148
     c = s_wgt[tid] + s_cc[tid];                      // helpers' state costs + control warps' action/control costs
     if (p.terminal_mode == 1) c += term;
     else if (valid && (p.k_offset + k_local) == p.K_global - 1) *p.term_out = term;

@@ -138,6 +138,21 @@ class B200MLP(Model):
         _abi.check(_abi.lib().ampc_mlp_pred_batch(self._h, X.shape[0], _abi.dptr(X), _abi.dptr(U), _abi.dptr(out)))
         return out
 
+    def rollout_batch(self, state, ctrls):
+        """``pred_batch`` applied ``len(ctrls)`` times in ONE launch: state (N,nx), ctrls (horizon,N,nu) -> (N,nx).
+        The inner loop of ``get_model_rmse`` (autompc/evaluation/model_metrics.py:33-35)."""
+        self._need()
+        X = _abi.f64(state)
+        U = _abi.f64(ctrls)
+        if X.ndim != 2 or U.ndim != 3 or U.shape[0] < 1 or U.shape[1] != X.shape[0] \
+                or X.shape[1] != self.weights.nx or U.shape[2] != self.weights.nu:
+            raise ValueError("rollout_batch expects state (N,%d) and ctrls (horizon,N,%d)"
+                             % (self.weights.nx, self.weights.nu))
+        out = np.empty_like(X)
+        _abi.check(_abi.lib().ampc_mlp_rollout_batch(self._h, X.shape[0], U.shape[0], _abi.dptr(X), _abi.dptr(U),
+                                                     _abi.dptr(out)))
+        return out
+
     def pred(self, state, ctrl):                         # mlp.py:219-227
         return self.pred_batch(np.asarray(state)[None, :], np.asarray(ctrl)[None, :])[0]
 

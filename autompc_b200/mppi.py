@@ -44,15 +44,45 @@ def shard_of(num_path, world, rank):
     return base + (1 if rank < rem else 0), rank * base + min(rank, rem)
 
 
+def fold_quadratic_terms(terms):
+    """Folds sum_i (x - g_i)^T M_i (x - g_i) into (x - g)^T M (x - g) + const  (M = sum M_i).
+
+    The linear terms match iff (M + M^T) g = sum_i (M_i + M_i^T) g_i, which always has a solution when the symmetric
+    parts are positive semi-definite (range of a sum of PSD matrices = sum of the ranges); the minimum-norm one is
+    taken.  Returns (M, g, const).  Raises ValueError if the system is inconsistent (indefinite terms)."""
+    M = sum(m for m, _ in terms)
+    rhs = sum((m + m.T) @ g for m, g in terms)
+    S = M + M.T
+    g = np.linalg.pinv(S) @ rhs
+    if not np.allclose(S @ g, rhs, rtol=1e-9, atol=1e-9 * max(1.0, float(np.abs(rhs).max()))):
+        raise ValueError("this sum of quadratic costs has no single-quadratic form (indefinite terms)")
+    const = float(sum(g_i @ m @ g_i for m, g_i in terms) - g @ M @ g)
+    return M, g, const
+
+
 def _quad_cost_of(task, nx, nu):
+    """Reads the task's cost as ONE quadratic (Q, R, F, goal [, terminal goal]) plus constants.
+
+    * a ``QuadCost`` (autompc/costs/quad_cost.py:7-51) is taken as is;
+    * a ``SumCost`` (autompc/costs/sum_cost.py:9-81) of quadratic terms -- e.g. ``QuadCostFactory + GaussRegFactory``,
+      whose goals differ so that the reference evaluates the sum term by term -- is folded
+      (``fold_quadratic_terms``): the engine's kernels see one quadratic, the constants ride along on the host
+      (they are common to all samples, i.e. they cancel in the MPPI weights, mppi.py:115-116).
+    Returns (holder, stage_const, term_const)."""
     cost = task.get_cost()
-    try:
-        Q, R, F = cost.get_cost_matrices()
-        goal = cost.get_goal()
-    except Exception as e:
-        raise ValueError("the B200 MPPI engine supports quadratic costs only (QuadCost): %s" % e)
     bounds = np.asarray(task.get_ctrl_bounds(), dtype=np.float64)
-    return _abi.QuadCostHolder(Q, R, F, goal, bounds[:, 0], bounds[:, 1], nx, nu)
+    terms = list(cost.costs) if hasattr(cost, "costs") else [cost]
+    try:
+        parts = [(t.get_cost_matrices(), np.asarray(t.get_goal(), dtype=np.float64)) for t in terms]
+    except Exception as e:
+        raise ValueError("the B200 MPPI engine supports quadratic costs only (QuadCost, or a SumCost of them): %s" % e)
+    if len(parts) == 1:
+        (Q, R, F), goal = parts[0]
+        return _abi.QuadCostHolder(Q, R, F, goal, bounds[:, 0], bounds[:, 1], nx, nu), 0.0, 0.0
+    Q, g, c_stage = fold_quadratic_terms([(np.asarray(m[0], dtype=np.float64), gl) for m, gl in parts])
+    F, gF, c_term = fold_quadratic_terms([(np.asarray(m[2], dtype=np.float64), gl) for m, gl in parts])
+    R = sum(np.asarray(m[1], dtype=np.float64) for m, _ in parts)
+    return _abi.QuadCostHolder(Q, R, F, g, bounds[:, 0], bounds[:, 1], nx, nu, goal_term=gF), c_stage, c_term
 
 
 class MPPI(Controller):
@@ -95,7 +125,7 @@ class MPPI(Controller):
             raise ValueError("num_path=%d cannot be sharded over %d ranks" % (self.num_path, self.world))
         # --- engine handle
         self._mlp_holder = _abi.MlpDescHolder(self.weights)
-        self._cost_holder = _quad_cost_of(task, nx, nu)
+        self._cost_holder, self._stage_const, self._term_const = _quad_cost_of(task, nx, nu)
         lib = _abi.lib()
         self._h = None
         order = {"auto": ["bf16", "fp32"], "fp32": ["fp32"], "bf16": ["bf16"]}.get(precision)
@@ -170,7 +200,8 @@ class MPPI(Controller):
         c = np.empty(self.K_local)
         t = C.c_double(0.0)
         _abi.check(_abi.lib().ampc_mppi_get_costs(self._h, _abi.dptr(c), C.byref(t)))
-        return c, t.value
+        # constants of a folded SumCost (zero for a plain QuadCost): H stage constants per sample, one terminal constant
+        return c + self.H * self._stage_const, t.value + self._term_const
 
     def philox_noise(self, counter=None):
         """(H, K_local, nu) unclipped noise the Philox path uses for solve `counter`."""

@@ -11,6 +11,7 @@ behaviour are defined so the same host code runs:
 * ``System``                              <- ``autompc/system.py:3-79``
 * ``Task`` (cost + control bounds only)   <- ``autompc/tasks/task.py:5-267``
 * ``QuadCost``                            <- ``autompc/costs/quad_cost.py:7-51``, ``cost.py:43-64``
+* ``SumCost`` (``+`` of costs)            <- ``autompc/costs/sum_cost.py:9-137``, ``cost.py:213-220``
 """
 from abc import ABC, abstractmethod
 
@@ -102,7 +103,33 @@ try:
     from autompc.system import System  # type: ignore
     from autompc.tasks.task import Task  # type: ignore
     from autompc.costs.quad_cost import QuadCost  # type: ignore
+    from autompc.costs.sum_cost import SumCost  # type: ignore
 except Exception:  # pragma: no cover
+
+    class SumCost:
+        """Sum of cost terms, built with ``+`` (sum_cost.py:9-29, :125-137)."""
+
+        def __init__(self, system, costs):
+            self.system = system
+            self._costs = list(costs)
+
+        @property
+        def costs(self):
+            return self._costs[:]
+
+        def get_cost_matrices(self):                     # sum_cost.py:30-44: only for a common goal
+            goals = [c.get_goal() for c in self._costs]
+            if any(not np.array_equal(goals[0], g) for g in goals[1:]):
+                raise NotImplementedError
+            mats = [c.get_cost_matrices() for c in self._costs]
+            return tuple(sum(m[i] for m in mats) for i in range(3))
+
+        def get_goal(self):
+            return self._costs[0].get_goal()
+
+        def __add__(self, other):
+            more = other.costs if isinstance(other, SumCost) else [other]
+            return SumCost(self.system, [*self._costs, *more])
 
     class System:
         def __init__(self, observations, controls, dt=None):
@@ -136,6 +163,10 @@ except Exception:  # pragma: no cover
 
         def get_goal(self):
             return np.copy(self._goal)
+
+        def __add__(self, other):                        # cost.py:213-220
+            more = other.costs if isinstance(other, SumCost) else [other]
+            return SumCost(self.system, [self, *more])
 
     class Task:
         def __init__(self, system):

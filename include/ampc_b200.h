@@ -69,6 +69,9 @@ typedef struct ampc_quad_cost {
   const double *goal; /* (nx,)   */
   const double *umin; /* (nu,)   */
   const double *umax; /* (nu,)   must be finite and > 0: the reference normalises by umax, mppi.py:102 */
+  const double *goal_term; /* (nx,) goal of the terminal term, NULL = goal.  A reference SumCost of quadratics with
+                              different goals (autompc/costs/sum_cost.py) folds to ONE quadratic per term type plus a
+                              constant; the stage and terminal folds have different goals in general.            */
 } ampc_quad_cost;
 
 /* ------------------------------------------------------------------ MPPI --- */
@@ -157,6 +160,9 @@ int ampc_mlp_create(ampc_mlp **out, const ampc_mlp_desc *mlp, int32_t nx, int32_
 int ampc_mlp_destroy(ampc_mlp *m);
 /* X (m,nx), U (m,nu) -> Xn (m,nx) */
 int ampc_mlp_pred_batch(ampc_mlp *m, int32_t batch, const double *X, const double *U, double *Xn);
+/* k-step open-loop prediction, the inner loop of get_model_rmse (autompc/evaluation/model_metrics.py:33-35):
+ * X0 (m,nx) window starts, U (horizon,m,nu) recorded controls -> Xh (m,nx) = pred_batch applied `horizon` times. */
+int ampc_mlp_rollout_batch(ampc_mlp *m, int32_t batch, int32_t horizon, const double *X0, const double *U, double *Xh);
 /* + Jx (m,nx,nx) = d Xn / d X, Ju (m,nx,nu) = d Xn / d U */
 int ampc_mlp_pred_diff_batch(ampc_mlp *m, int32_t batch, const double *X, const double *U,
                              double *Xn, double *Jx, double *Ju);

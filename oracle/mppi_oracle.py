@@ -11,6 +11,8 @@ What is restated, with the reference lines each function follows
   (chain rule through the layer stack instead of autograd).
 * ``QuadCostParams`` methods <- ``autompc/costs/cost.py:66-83``, ``:118-134``,
   ``:166-183`` for a ``QuadCost`` (``autompc/costs/quad_cost.py:7-51``).
+* ``SumQuadCostParams`` <- ``autompc/costs/sum_cost.py:9-81``;  ``model_rmse`` <-
+  ``autompc/evaluation/model_metrics.py:12-43``.
 * ``MPPIOracle`` <- ``autompc/control/mppi.py:66-181``: ctor draw ``:97-99``,
   ``do_rollouts`` ``:120-152``, ``update`` ``:110-118``, ``run`` ``:154-168``.
 
@@ -178,6 +180,44 @@ class QuadCostParams:
 
     def ctrl_cost_batch(self, U):
         return np.einsum("ki,ij,kj->k", U, self.R, U)
+
+
+class SumQuadCostParams:
+    """A reference ``SumCost`` (autompc/costs/sum_cost.py:9-81) whose terms are ``QuadCost`` objects, possibly with
+    different goals: every ``eval_*`` is the sum of the terms' values (``_sum_results``, sum_cost.py:52-57)."""
+
+    def __init__(self, terms):
+        self.terms = list(terms)
+
+    def eval_obs_cost(self, obs):                       # sum_cost.py:59-60
+        return sum(t.eval_obs_cost(obs) for t in self.terms)
+
+    def eval_ctrl_cost(self, ctrl):                     # sum_cost.py:68-69
+        return sum(t.eval_ctrl_cost(ctrl) for t in self.terms)
+
+    def eval_term_obs_cost(self, obs):                  # sum_cost.py:77-78
+        return sum(t.eval_term_obs_cost(obs) for t in self.terms)
+
+    def obs_cost_batch(self, X):
+        return sum(t.obs_cost_batch(X) for t in self.terms)
+
+    def ctrl_cost_batch(self, U):
+        return sum(t.ctrl_cost_batch(U) for t in self.terms)
+
+
+def model_rmse(p, obs_list, ctrl_list, horizon=1):
+    """``get_model_rmse`` (autompc/evaluation/model_metrics.py:12-43) for an MLP (no ``traj_to_states``):
+    every window start ``obs[:-horizon]`` is rolled ``horizon`` times through ``pred_batch`` with the recorded
+    controls ``ctrls[k:-(horizon-k)]`` and compared with ``obs[horizon:]``;
+    rmse = sqrt(mean(all squared errors) * obs_dim)."""
+    sq = []
+    for obs, ctrls in zip(obs_list, ctrl_list):
+        state = obs[:-horizon, :]                                        # model_metrics.py:33
+        for k in range(horizon):                                         # :34-35
+            state = mlp_pred_batch(p, state, ctrls[k:len(ctrls) - (horizon - k), :])
+        sq.append((state - obs[horizon:]) ** 2)                          # :38-40
+    sq = np.concatenate(sq)
+    return float(np.sqrt(np.mean(sq, axis=None) * p.nx))                 # :42
 
 
 class MPPIOracle:

@@ -102,3 +102,20 @@ def test_many_closed_loops_in_flight():
         solo.close()
     for ctl in ctls:
         ctl.close()
+
+
+def test_closed_loop_cost_of_folded_sumcost():
+    """A SumCost of two quadratics with different goals (folded on the host): the device-side trajectory cost plus the
+    fold's constants equals Cost.__call__ (cost.py:27-41) summed over the terms on the returned trajectory."""
+    from autompc_b200 import MPPI, simulate
+    from oracle.mppi_oracle import QuadCostParams, SumQuadCostParams
+    from tests.test_mppi_gpu import _sumcost_problem
+    z = np.load(os.path.join(GOLDEN, "mppi_cartpole_sumcost_K256_H20.npz"))
+    system, task, model = _sumcost_problem(z)
+    np.random.seed(0)
+    ctl = MPPI(system, task, model, horizon=12, num_path=256, seed=3, precision="fp32")
+    res = simulate(ctl, np.array([0.4, 0.0, 0.1, 0.0]), sim_model=model, max_steps=15)
+    cost = SumQuadCostParams([QuadCostParams(z["Q1"], z["R1"], z["F1"], z["g1"]),
+                              QuadCostParams(z["Q2"], z["R2"], z["F2"], z["g2"])])
+    np.testing.assert_allclose(res.cost, _traj_cost(cost, res.obs, res.ctrls), rtol=1e-10)
+    ctl.close()

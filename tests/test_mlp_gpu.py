@@ -69,3 +69,32 @@ def test_mlp_parameter_round_trip_and_errors():
         m.pred_batch(np.ones((3, 5)), U)
     with pytest.raises(NotImplementedError):
         m.train([])
+
+
+def test_kstep_rollout_and_model_rmse_match_reference_fixture():
+    """get_model_rmse (autompc/evaluation/model_metrics.py:12-43) on the device.  Checker: values the
+    unmodified reference computed on the same trajectories; and the fused k-step rollout equals chained pred_batch."""
+    from autompc_b200 import get_model_rmse
+    from oracle.mppi_oracle import model_rmse
+    from tests.helpers import load_cartpole
+    z = np.load(os.path.join(GOLDEN, "model_rmse_cartpole.npz"))
+    p = load_cartpole()[0]
+    m = _model(p)
+    obs, ctrls = list(z["obs"]), list(z["ctrls"])
+    for h in z["horizons"]:
+        r = get_model_rmse(m, list(zip(obs, ctrls)), horizon=int(h))
+        assert abs(r - float(z["rmse_h%d" % h])) < 1e-11
+        assert abs(r - model_rmse(p, obs, ctrls, int(h))) < 1e-11
+    lens = z["ragged_lens"]
+    ragged = [(obs[i][:n], ctrls[i][:n]) for i, n in enumerate(lens)]
+    assert abs(get_model_rmse(m, ragged, horizon=5) - float(z["rmse_ragged_h5"])) < 1e-11
+    # one launch == `horizon` chained launches, bit for bit (same per-step arithmetic)
+    X, U = obs[0][:40], np.stack([ctrls[0][k:k + 40] for k in range(7)])
+    chained = X
+    for k in range(7):
+        chained = m.pred_batch(chained, U[k])
+    np.testing.assert_array_equal(m.rollout_batch(X, U), chained)
+    with pytest.raises(ValueError):
+        get_model_rmse(m, [(obs[0][:3], ctrls[0][:3])], horizon=5)      # no trajectory longer than the horizon
+    with pytest.raises(ValueError):
+        m.rollout_batch(X, U[:, :5])

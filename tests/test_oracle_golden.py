@@ -123,3 +123,38 @@ def test_oracle_live_against_reference_three_solves():
         np.testing.assert_allclose(u_o, u_ref, rtol=0, atol=1e-10)
         np.testing.assert_allclose(o.act_sequence, ref.act_sequence, rtol=0, atol=1e-10)
         x = cartpole_step(x, u_ref)
+
+
+def _sumcost_terms(z):
+    return [QuadCostParams(z["Q1"], z["R1"], z["F1"], z["g1"]), QuadCostParams(z["Q2"], z["R2"], z["F2"], z["g2"])]
+
+
+def test_sumcost_oracle_matches_reference():
+    """the reference MPPI under a SumCost of two QuadCosts with different goals."""
+    from oracle.mppi_oracle import SumQuadCostParams
+    z = np.load(os.path.join(GOLDEN, "mppi_cartpole_sumcost_K256_H20.npz"))
+    mlp, _, umin, umax, _, _ = load_cartpole()
+    np.random.seed(int(z["seed"]))
+    o = MPPIOracle(mlp, SumQuadCostParams(_sumcost_terms(z)), umin, umax, horizon=int(z["H"]), num_path=int(z["K"]),
+                   sigma=float(z["sigma"]), lmda=float(z["lmda"]))
+    np.testing.assert_array_equal(o.act_sequence, z["act0"])
+    constate = np.zeros(5)
+    for s in range(int(z["n_steps"])):
+        u, constate = o.run(constate, z["x0_%d" % s])
+        np.testing.assert_allclose(o.last_costs, z["costs_%d" % s], rtol=1e-11, atol=1e-9)
+        assert int(np.argmin(o.last_costs)) == int(z["argmin_%d" % s])
+        np.testing.assert_allclose(o.act_sequence, z["act_%d" % s], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(u, z["u_%d" % s], rtol=0, atol=1e-8)
+
+
+def test_model_rmse_oracle_matches_reference():
+    """get_model_rmse (model_metrics.py:12-43) at several horizons, equal and ragged lengths."""
+    from oracle.mppi_oracle import model_rmse
+    z = np.load(os.path.join(GOLDEN, "model_rmse_cartpole.npz"))
+    mlp = load_cartpole()[0]
+    obs, ctrls = list(z["obs"]), list(z["ctrls"])
+    for h in z["horizons"]:
+        assert abs(model_rmse(mlp, obs, ctrls, int(h)) - float(z["rmse_h%d" % h])) < 1e-12
+    lens = z["ragged_lens"]
+    r = model_rmse(mlp, [obs[i][:n] for i, n in enumerate(lens)], [ctrls[i][:n] for i, n in enumerate(lens)], 5)
+    assert abs(r - float(z["rmse_ragged_h5"])) < 1e-12
