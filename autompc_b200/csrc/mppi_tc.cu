@@ -57,6 +57,7 @@ constexpr int MAXL = AMPC_MAX_LAYERS;
 constexpr int TRACE_EV = 128;
 // upper word of the K-major SWIZZLE_128B descriptor: SBO = 1024 B (bits 32-45), version 1 (bit 46), layout 2 (bits 61-63)
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr int DEFER_J = 4;           // K-steps of (half 1, K-pair 0) issued in the first phase; the other 8 - DEFER_J follow commit0
 constexpr int YCOL = 64;             // accumulator columns of the output-layer GEMM inside its buffer (clear of the next input block)
 constexpr int MAXG = 2;              // N-halves of a GEMM = K-pairs of the next one
 
@@ -77,6 +78,7 @@ struct TcArgs {
   int Kc;                            // grid * 128
   int nxp;                           // padded state width (kernel template): input K columns [0,nxp) = state
   int ones[MAXL];                    // layer l's epilogue also writes the constant-one K-step of layer l+1 (bias fold)
+  int defer_j;                       // K-steps of (half 1, K-pair 0) issued before the wait for K-pair 1 (2 | 4 | 6; 8 = no deferral)
   unsigned long long *trace;         // debug timeline (AMPC_TC_TRACE=1), else null: [warp][event] = clock<<8 | tag
 };
 
@@ -416,6 +418,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
         aw_l[l] = a.awid[l];
       }
       const int nks0 = a.kpad[0] >> 4;
+      const int defer_j = a.defer_j;
       for (int i = 0; i < H; ++i) {
 #pragma unroll
         for (int l = 0; l < MAXL; ++l) {
@@ -425,10 +428,12 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
           const uint32_t d_addr = (n & 1u) * TMEM_BUF + (l == L - 1 ? (uint32_t)YCOL : 0u);
           const uint32_t a_addr = ((n + 1u) & 1u) * TMEM_BUF;
           // Full-width hidden GEMMs (two N-halves, two K-pairs of 8 K-steps) are issued as
-          //   (h0,kp0) (h1,kp0: first 4 K-steps) | wait kp1 | (h0,kp1)+commit0 (h1,kp0: last 4) (h1,kp1)+commit1
-          // so that 12 MMAs (~800 cycles) are still queued behind commit0: the epilogue of half 0 and both hand-overs
-          // (~700 cycles) finish before the pipe drains, while the 14 MMAs of the first phase cover the wait for kp1.
-          const bool defer = (l > 0 && nh == 2 && nkp == 2 && ksp_l[l] == 8);
+          //   (h0,kp0) (h1,kp0: first DEFER_J K-steps) | wait kp1 | (h0,kp1)+commit0 (h1,kp0: the rest) (h1,kp1)+commit1
+          // so that 12 MMAs (~800 cycles) are still queued behind commit0 -- the MMA pipeline latency, the epilogue of
+          // half 0 and the cross-CTA hand-over (~800 cycles together) finish before the pipe drains -- while the 14
+          // MMAs of the first phase cover the wait for kp1.  Measured on one box (AMPC_TC_DEFER = 2 / 4 / 6 / 8):
+          // 0.2429 / 0.2404 / 0.2436 / 0.2538 ms per solve at C3.
+          const bool defer = (defer_j < 8 && l > 0 && nh == 2 && nkp == 2 && ksp_l[l] == 8);
           for (int kp = 0; kp < nkp; ++kp) {
             mbar_wait(bar_a0 + 8u * kp, (pa >> kp) & 1u);
             pa ^= (1u << kp);
@@ -448,9 +453,13 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
                                 ks > 0 ? 1u : 0u);
               } else if (defer && h == 1) {
                 if (kp == 0) {
-                  issue_pair<CG, 8, 0, 4>(dh, a_pair, hb, kb_stride, idesc, true);
-                } else {
-                  issue_pair<CG, 8, 4, 8>(dh, a_addr, hb0, kb_stride, idesc, false);   // rest of K-pair 0
+                  if (defer_j == 2) issue_pair<CG, 8, 0, 2>(dh, a_pair, hb, kb_stride, idesc, true);
+                  else if (defer_j == 4) issue_pair<CG, 8, 0, 4>(dh, a_pair, hb, kb_stride, idesc, true);
+                  else issue_pair<CG, 8, 0, 6>(dh, a_pair, hb, kb_stride, idesc, true);
+                } else {                                // rest of K-pair 0
+                  if (defer_j == 2) issue_pair<CG, 8, 2, 8>(dh, a_addr, hb0, kb_stride, idesc, false);
+                  else if (defer_j == 4) issue_pair<CG, 8, 4, 8>(dh, a_addr, hb0, kb_stride, idesc, false);
+                  else issue_pair<CG, 8, 6, 8>(dh, a_addr, hb0, kb_stride, idesc, false);
                   issue_pair<CG, 8>(dh, a_pair, hb, kb_stride, idesc, false);
                 }
               } else {
@@ -1018,6 +1027,11 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
   a.bias = pl->d_bias;
   a.epsc = pl->d_epsc;
   a.trace = nullptr;
+  a.defer_j = DEFER_J;
+  if (const char *dj = getenv("AMPC_TC_DEFER")) {   // tuning knob
+    const int v = atoi(dj);
+    if (v == 2 || v == 4 || v == 6 || v == 8) a.defer_j = v;
+  }
   if (getenv("AMPC_TC_TRACE") && tc_trace_available(cg, a.nxp, mlp->act)) {
     cudaFuncSetAttribute(tc_kernel_ptr(cg, a.nxp, mlp->act, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
     if (cudaMalloc(&pl->d_trace, (NTHR / 32) * TRACE_EV * sizeof(unsigned long long)) == cudaSuccess) {

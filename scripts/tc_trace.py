@@ -31,3 +31,20 @@ for t, wp, tag in ev:
             print("%8d  warp %d  %s %d" % (t - t0, wp, names.get(k, "?"), idx))
         else:
             print("%8d  warp %d  %s layer %d half/pair %d" % (t - t0, wp, names.get(k, "?"), idx >> 1, idx & 1))
+
+# spread of the epilogue warps of CTA 0 (4-11): when each saw bar_d / released a half
+print()
+print("# per event: min / max over epilogue warps 4..11 (cycles since kernel entry), spread")
+from collections import defaultdict
+grp = defaultdict(list)
+cnt = defaultdict(int)
+for t, wp, tag in ev:
+    if 4 <= wp <= 11 and (tag >> 4) in (3, 4, 5):
+        key = (tag, cnt[(wp, tag)])
+        cnt[(wp, tag)] += 1
+        grp[key].append((t, wp))
+for (tag, occ), lst in sorted(grp.items(), key=lambda kv: min(kv[1])):
+    ts = [x[0] for x in lst]
+    k, idx = tag >> 4, tag & 15
+    print("%8d .. %8d  (+%4d, last = warp %d)  %s layer %d half %d" % (min(ts), max(ts), max(ts) - min(ts), max(lst)[1],
+          names.get(k, "?"), idx >> 1, idx & 1))
