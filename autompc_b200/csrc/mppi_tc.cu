@@ -701,8 +701,15 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
       trace(i, 0x50);                                   // next input released
       ++n;
     }
-    if (owner) store_x();                               // x_H for the terminal cost
-    if (!owner) s_wgt[t] = cost_acc;                    // helper's share (state costs)
+    // x_H for the terminal cost goes into the same shared array the helpers read the last stage cost from: nothing
+    // in the GEMM chain orders the two at the LAST step (a one-hidden-layer network with a dense Q lost the race)
+    if (owner) {
+      asm volatile("bar.sync %0, %1;" ::"n"(BAR_X), "n"(NEPI) : "memory");
+      store_x();
+    } else {
+      s_wgt[t] = cost_acc;                              // helper's share (state costs)
+      asm volatile("bar.arrive %0, %1;" ::"n"(BAR_X), "n"(NEPI) : "memory");
+    }
   }
 
   // =========================== softmax partials of this CTA (mppi.py:110-118) ===========================

@@ -271,19 +271,29 @@ TC_CASES = [
     (17, 6, [100, 60], "sigmoid", 129, 9, 0.8, 2.0, "2"),             # widths padded to 32
     (3, 2, [48, 24, 16, 40], "selu", 77, 7, 0.3, 0.5, None),          # 4 hidden layers
     (4, 1, [32], "relu", 1, 2, 1.0, 1.0, None),                       # K=1, minimum horizon
+    # input-block layouts: NXP=32 with two control-only K-steps (stored ahead of the state), dense Q/R/F
+    (32, 20, [256, 128], "relu", 513, 6, 0.6, 1.5, None, True),
+    (16, 9, [64], "relu", 200, 5, 1.0, 1.0, None, True),              # NXP=16: no K-step mixes state and controls
+    (8, 3, [128, 128, 128], "relu", 640, 10, 0.7, 1.0, None, True),   # NXP=8: the mixed K-step is the first one
 ]
 
 
-@pytest.mark.parametrize("nx,nu,hidden,act,K,H,sigma,lmda,force_cg", TC_CASES)
-def test_mppi_bf16_tensor_core_matches_oracle(nx, nu, hidden, act, K, H, sigma, lmda, force_cg, monkeypatch):
+@pytest.mark.parametrize("case", TC_CASES)
+def test_mppi_bf16_tensor_core_matches_oracle(case, monkeypatch):
     """bf16 x bf16 -> fp32 tcgen05 products, fp32 state / cost / softmax: stated bf16 tolerance."""
+    nx, nu, hidden, act, K, H, sigma, lmda, force_cg = case[:9]
+    dense = len(case) > 9 and case[9]
     if force_cg:
         monkeypatch.setenv("AMPC_TC_FORCE_CG", force_cg)
     else:
         monkeypatch.delenv("AMPC_TC_FORCE_CG", raising=False)
     rng = np.random.default_rng(5)
     p = synthetic_mlp(nx, nu, hidden, act=act, seed=3)
-    cost = QuadCostParams(np.eye(nx), 0.01 * np.eye(nu), 10 * np.eye(nx), goal=0.05 * rng.normal(size=nx))
+    if dense:
+        A, B, C = rng.normal(size=(nx, nx)), rng.normal(size=(nu, nu)), rng.normal(size=(nx, nx))
+        cost = QuadCostParams(A @ A.T / nx, 0.01 * (B @ B.T) / nu, C @ C.T / nx, goal=0.1 * rng.normal(size=nx))
+    else:
+        cost = QuadCostParams(np.eye(nx), 0.01 * np.eye(nu), 10 * np.eye(nx), goal=0.05 * rng.normal(size=nx))
     umax = rng.uniform(0.5, 2.0, size=nu)
     umin = -umax * rng.uniform(0.5, 1.0, size=nu)
     np.random.seed(1)
