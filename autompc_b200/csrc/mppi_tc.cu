@@ -322,8 +322,9 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
     const int src = (i + 1 < H) ? i + 1 : H - 1;
     s_act[e] = p.act_seq[src * nu + j];
   }
-  if (tid < TM)
-    for (int j = 0; j < nx; ++j) s_x[j * TM + tid] = p.x0[j];   // mppi.py:129-130
+  // mppi.py:129-130: every sample starts from x0.  One load per state per CTA (x0 may live in mapped host memory:
+  // ampc_mppi_solve_host reads the observation zero-copy); s_misc is free until the merge at the end.
+  for (int j = tid; j < nx; j += NTHR) s_misc[j] = p.x0[j];
   // K column k of the input layer: k < NXP -> state k (zero beyond nx); NXP <= k < NXP+nu -> control k-NXP
   // (the weight image uses the same permutation).  z = v * scale + bias  (mlp.py:20-24).
   for (int k = tid; k < 64; k += NTHR) {
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
 #pragma unroll
     for (int j = 0; j < NXP; ++j) {
       const float2 zc = s_zc[j];
-      z[j] = (owner && j < nx) ? fmaf(s_x[j * TM + t], zc.x, zc.y) : 0.f;
+      z[j] = (owner && j < nx) ? fmaf(s_misc[j], zc.x, zc.y) : 0.f;
     }
     const int kpad0 = a.kpad[0];
     // Input-layer A operand (bf16, K columns [0,NXP) = z, [NXP,NXP+nu) = z-scored controls, then the constant ones):
