@@ -171,6 +171,9 @@ struct AmpcMppiParams {
   int world, rank;
   unsigned int seq;         // solve sequence number (> 0), identical on all ranks; selects the mailbox slot
   float *u_out;           // (nu,)
+  // host-buffer entry point: the observation rides in the kernel parameters (no H2D copy on the stream) ...
+  int x0_inline;          // != 0: use x0_val instead of x0
+  float x0_val[32];       // nx <= 32 on this path
 };
 
 // Merge softmax partial records [m, s, W(HN)] (block level or rank level) and either

@@ -51,6 +51,7 @@ struct ampc_mppi {
   float *d_partials = nullptr, *d_x0 = nullptr, *d_u = nullptr, *d_eps = nullptr;
   unsigned int *d_ticket = nullptr;
   float *h_pin = nullptr;          // pinned staging: x0 (nx) | u (nu)
+  float *d_pin = nullptr;          // the same buffer as the device sees it (mapped): the control is written straight to it
   float *h_eps = nullptr;          // pinned staging for external eps (lazily)
   size_t eps_elems = 0;
   // NVLink peer exchange
@@ -171,8 +172,13 @@ void free_handle(ampc_mppi *h) {
 }
 
 int launch_rollout(ampc_mppi *h, const float *dev_x0, const float *dev_eps, uint64_t seed, uint64_t counter,
-                   float *dev_u, float *dev_record, cudaStream_t stream) {
+                   float *dev_u, float *dev_record, cudaStream_t stream, const float *inline_x0 = nullptr) {
   AmpcMppiParams p = h->p;
+  p.x0_inline = 0;
+  if (inline_x0) {
+    p.x0_inline = 1;
+    for (int j = 0; j < h->cfg.nx && j < 32; ++j) p.x0_val[j] = inline_x0[j];
+  }
   p.x0 = dev_x0;
   p.eps = dev_eps;
   p.seed = seed;
@@ -279,7 +285,8 @@ extern "C" int ampc_mppi_create(ampc_mppi **out, const ampc_mppi_cfg *cfg, const
   AMPC_CREATE_CHECK(cudaMalloc(&h->d_u, nu * sizeof(float)));
   AMPC_CREATE_CHECK(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
   AMPC_CREATE_CHECK(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
-  AMPC_CREATE_CHECK(cudaMallocHost(&h->h_pin, (nx + nu) * sizeof(float)));
+  AMPC_CREATE_CHECK(cudaHostAlloc(&h->h_pin, (nx + nu) * sizeof(float), cudaHostAllocMapped));
+  AMPC_CREATE_CHECK(cudaHostGetDevicePointer((void **)&h->d_pin, h->h_pin, 0));
   p.consts = h->d_consts; p.act_seq = h->d_act; p.costs = h->d_costs; p.term_out = h->d_term;
   p.ticket = h->d_ticket;
 
@@ -367,6 +374,16 @@ extern "C" int ampc_mppi_solve_host(ampc_mppi *h, const double *host_x0, const d
   DeviceGuard g(h->device);
   const int nx = h->cfg.nx, nu = h->cfg.nu;
   for (int j = 0; j < nx; ++j) h->h_pin[j] = (float)host_x0[j];
+  if (!host_eps && nx <= 32 && !getenv("AMPC_NO_INLINE_IO")) {
+    // In-kernel noise: the only host traffic is the observation in (nx floats) and the control out (nu floats).
+    // The observation rides in the kernel parameters and the last CTA writes the control straight into the mapped
+    // pinned buffer: one launch + one synchronise instead of copy -> launch -> copy on the stream.
+    int rc = launch_rollout(h, h->d_x0, nullptr, seed, counter, h->d_pin + nx, nullptr, h->stream, h->h_pin);
+    if (rc) return rc;
+    AMPC_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    for (int j = 0; j < nu; ++j) host_u[j] = h->h_pin[nx + j];
+    return AMPC_OK;
+  }
   AMPC_CUDA_CHECK(cudaMemcpyAsync(h->d_x0, h->h_pin, nx * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   const float *d_eps = nullptr;
   if (host_eps) {

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(NTHR) mppi_rollout_fp32_kernel(const AmpcMppiP
     float4 *s4 = reinterpret_cast<float4 *>(s_w);
     for (int i = tid; i < p.wpack_floats / 4; i += NTHR) s4[i] = g4[i];
   }
-  for (int j = warp; j < nx; j += NWARP) s_x[j * BM + lane] = p.x0[j];   // mppi.py:129-130
+  for (int j = warp; j < nx; j += NWARP) s_x[j * BM + lane] = (p.x0_inline && j < 32) ? p.x0_val[j] : p.x0[j];   // mppi.py:129-130
   __syncthreads();
 
   const float *wbase = RES ? s_w : p.wpack;

@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   }
   // mppi.py:129-130: every sample starts from x0.  One load per state per CTA (x0 may live in mapped host memory:
   // ampc_mppi_solve_host reads the observation zero-copy); s_misc is free until the merge at the end.
-  for (int j = tid; j < nx; j += NTHR) s_misc[j] = p.x0[j];
+  for (int j = tid; j < nx; j += NTHR) s_misc[j] = p.x0_inline ? p.x0_val[j] : p.x0[j];
   // K column k of the input layer: k < NXP -> state k (zero beyond nx); NXP <= k < NXP+nu -> control k-NXP
   // (the weight image uses the same permutation).  z = v * scale + bias  (mlp.py:20-24).
   for (int k = tid; k < 64; k += NTHR) {

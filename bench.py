@@ -289,7 +289,10 @@ def gpu_arm(args, wl, rank, world, local_rank):
                                                       float(per_step_ms.max())]},
             "clocks": clk.summary(),
             "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 4 * nx,
-                    "d2h_bytes_per_step": 4 * nu, "api": "autompc_b200.MPPI.run(state, new_obs) with NumPy float64 buffers"},
+                    "d2h_bytes_per_step": 4 * nu, "api": "autompc_b200.MPPI.run(state, new_obs) with NumPy float64 buffers",
+                    "transfer": "host observation -> pinned float32 -> kernel parameters (H2D with the launch); control "
+                                "written by the kernel's last CTA into mapped pinned host memory (D2H), one stream "
+                                "synchronise per step" if world == 1 else "pinned H2D / D2H copies on the stream"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_burst"], "traffic": ncu_traffic(ctl.precision, world),
