@@ -207,19 +207,56 @@ __device__ __forceinline__ void ampc_merge_records(const float *recs, int n_recs
   __syncthreads();
   s = 0.f;
   for (int w = 0; w < nwarp; ++w) s += s_scratch[32 + w];
+  // W[e] = sum_b rec[b][2+e] * rs[b].  Fast path (records in L2, everything 8-byte aligned, scratch large enough):
+  // thread (g, pair) sums every G-th record for two neighbouring entries with MU float2 loads in flight, the G
+  // partial sums meet in shared memory.  The one-thread-per-entry loop below is the general path.
+  const int E2 = HN >> 1;
+  int G = E2 > 0 ? nthr / E2 : 0;
+  if (G > 8) G = 8;
+  if (G > n_recs) G = n_recs;
+  const bool fast = cached && G >= 1 && (HN & 1) == 0 && (rec_stride & 1) == 0 && n_recs + G * HN <= AMPC_MERGE_CACHE;
+  if (fast) {
+    float *s_part = s_rs + n_recs;                   // [G][HN]
+    const int g = tid / E2, pe = tid - g * E2;
+    if (g < G) {
+      constexpr int MU = 16;
+      float2 acc = make_float2(0.f, 0.f);
+      const float *base = recs + 2 + 2 * pe;
+      for (int b0 = g; b0 < n_recs; b0 += G * MU) {
+        float2 v[MU];
+#pragma unroll
+        for (int u = 0; u < MU; ++u) {
+          const int b = b0 + u * G;
+          v[u] = b < n_recs ? __ldcg(reinterpret_cast<const float2 *>(base + (size_t)b * rec_stride)) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < MU; ++u) {
+          const int b = b0 + u * G;
+          const float r = b < n_recs ? s_rs[b] : 0.f;
+          acc.x = fmaf(v[u].x, r, acc.x);
+          acc.y = fmaf(v[u].y, r, acc.y);
+        }
+      }
+      s_part[g * HN + 2 * pe] = acc.x;
+      s_part[g * HN + 2 * pe + 1] = acc.y;
+    }
+    __syncthreads();
+    for (int e = tid; e < HN; e += nthr) {
+      float acc = 0.f;
+      for (int gg = 0; gg < G; ++gg) acc += s_part[gg * HN + e];
+      if (record_out) {
+        record_out[2 + e] = acc;
+      } else {
+        const float v = s_act_shift[e] + acc / s;
+        act_seq[e] = v;
+        if (e < nu) u_out[e] = v * scale[e];
+      }
+    }
+  } else
   for (int e = tid; e < HN; e += nthr) {
     float acc = 0.f;
     if (cached) {
-      constexpr int MU = 16;                           // record loads in flight per thread (they come from L2)
-      int b0 = 0;
-      for (; b0 + MU <= n_recs; b0 += MU) {
-        float v[MU];
-#pragma unroll
-        for (int u = 0; u < MU; ++u) v[u] = __ldcg(recs + (size_t)(b0 + u) * rec_stride + 2 + e);
-#pragma unroll
-        for (int u = 0; u < MU; ++u) acc = fmaf(v[u], s_rs[b0 + u], acc);
-      }
-      for (int b = b0; b < n_recs; ++b)
+      for (int b = 0; b < n_recs; ++b)
         acc = fmaf(__ldcg(recs + (size_t)b * rec_stride + 2 + e), s_rs[b], acc);
     } else {
       for (int b = 0; b < n_recs; ++b) {

@@ -741,24 +741,20 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
     rec[1] = (s_red[8] + s_red[9]) + (s_red[10] + s_red[11]);
   }
   {                                                                       // mppi.py:117 (per-CTA share)
-    constexpr int EU = 8;                                                 // entries per warp iteration: 32 L2 loads in flight per lane
-    float wq[TM / 32];
-#pragma unroll
-    for (int q = 0; q < TM / 32; ++q) wq[q] = s_wgt[lane + 32 * q];
+    // 128 samples of one (step, control) entry are 32 lanes x float4 (the scratch rows are 512-byte aligned);
+    // EU entries = EU 16-byte L2 loads in flight per lane
+    constexpr int EU = 16;
+    const float4 wq = reinterpret_cast<const float4 *>(s_wgt)[lane];
     for (int e0 = warp * EU; e0 < HN; e0 += (NTHR / 32) * EU) {
-      float ld[EU][TM / 32];
+      float4 ld[EU];
 #pragma unroll
       for (int u = 0; u < EU; ++u) {
         const int e = (e0 + u < HN) ? e0 + u : HN - 1;
-        const float *src = a.epsc + (size_t)e * a.Kc + (size_t)blockIdx.x * TM;
-#pragma unroll
-        for (int q = 0; q < TM / 32; ++q) ld[u][q] = __ldcg(src + lane + 32 * q);
+        ld[u] = __ldcg(reinterpret_cast<const float4 *>(a.epsc + (size_t)e * a.Kc + (size_t)blockIdx.x * TM) + lane);
       }
 #pragma unroll
       for (int u = 0; u < EU; ++u) {
-        float v = 0.f;
-#pragma unroll
-        for (int q = 0; q < TM / 32; ++q) v = fmaf(wq[q], ld[u][q], v);
+        float v = fmaf(wq.x, ld[u].x, fmaf(wq.y, ld[u].y, fmaf(wq.z, ld[u].z, wq.w * ld[u].w)));
         v = ampc_warp_sum(v);
         if (lane == 0 && e0 + u < HN) rec[2 + e0 + u] = v;
       }
@@ -775,8 +771,15 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   __syncthreads();
   if (s_last) {
     __threadfence();
+    const uint32_t t_merge = (uint32_t)clock();
     ampc_merge_records(p.partials, (int)gridDim.x, 2 + HN, HN, nu, p.inv_lmda, s_act, c_scale, p.act_seq, p.u_out,
                        p.record_out, s_misc);
+    if constexpr (TRACE) {
+      __syncthreads();
+      if (tid == 0)
+        printf("# last CTA = %d: merge started %u cycles after its kernel entry and took %u cycles\n", (int)blockIdx.x,
+               t_merge - t_entry, (uint32_t)clock() - t_merge);
+    }
     if (p.peer_mail != nullptr) ampc_peer_exchange_merge(p, p.record_out, HN, s_act, c_scale, s_misc);
     if (tid == 0) *p.ticket = 0u;
   }
