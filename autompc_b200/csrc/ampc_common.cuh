@@ -12,6 +12,9 @@
 // ------------------------------------------------------------------ errors ---
 void ampc_set_error(const char *fmt, ...);
 void ampc_count_launch(int n = 1);
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per FUNCTION, not per handle: handles with different shared-memory
+// needs share the kernels, so the limit is only ever raised (process-wide maximum per function and device).
+cudaError_t ampc_raise_smem_limit(const void *func, size_t bytes);
 
 #define AMPC_CUDA_CHECK(expr)                                                              \
   do {                                                                                     \

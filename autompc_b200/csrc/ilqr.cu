@@ -410,7 +410,7 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
   P.hA = w + ohA; P.hB = w + ohB; P.hG = w + ohG; P.JA = w + oJA; P.JB = w + oJB;
   P.info = h->d_int; P.alpha_idx = h->d_int + 3;
   h->smem = ((size_t)n * n * 2 + (size_t)nx * nx * 3 + 2 * nx + (size_t)nx * n + n + (size_t)nu * nx + nu + NT / 32 + LS + 4) * sizeof(double);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(ilqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  if (e == cudaSuccess) e = ampc_raise_smem_limit((const void *)ilqr_kernel, h->smem);
   if (e != cudaSuccess) {
     ampc_set_error("iLQR create: %s", cudaGetErrorString(e));
     cudaFree(h->d_blob); cudaFree(h->d_work); cudaFree(h->d_int);

@@ -237,7 +237,7 @@ extern "C" int ampc_mlp_create(ampc_mlp **out, const ampc_mlp_desc *mlp, int32_t
   if (rc) { delete m; return rc; }
   m->smem_pred = 2 * (size_t)m->net.max_width * sizeof(double);
   m->smem_diff = (3 * (size_t)m->net.max_width + 2 * (size_t)m->net.max_width * (nx + nu)) * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(pred_diff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_diff);
+  cudaError_t e = ampc_raise_smem_limit((const void *)pred_diff_kernel, m->smem_diff);
   if (e != cudaSuccess) {
     ampc_set_error("pred_diff kernel needs %zu B shared memory: %s", m->smem_diff, cudaGetErrorString(e));
     cudaFree(m->d_blob);

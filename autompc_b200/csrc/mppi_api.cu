@@ -1,4 +1,7 @@
 // C ABI for the MPPI solve: handle, weight packing, solve / merge / parity taps.
+#include <map>
+#include <mutex>
+#include <utility>
 #include <stdarg.h>
 #include <string.h>
 
@@ -18,6 +21,20 @@ void ampc_set_error(const char *fmt, ...) {
   va_end(ap);
 }
 void ampc_count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+cudaError_t ampc_raise_smem_limit(const void *func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void *, int>, size_t> limit;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t &cur = limit[std::make_pair(func, dev)];
+  if (bytes <= cur) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
 
 extern "C" const char *ampc_last_error(void) { return g_err; }
 extern "C" const char *ampc_version(void) { return "ampc_b200 0.1 (sm_100a)"; }

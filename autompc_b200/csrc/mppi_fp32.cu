@@ -274,11 +274,9 @@ int ampc_mppi_fp32_configure(const AmpcMppiParams &p, bool *resident_out, size_t
                "fp32 MPPI kernel needs %zu B shared memory (H*nu=%d too large), limit %zu", need,
                p.H * p.nu, cap);
   if (res)
-    AMPC_CUDA_CHECK(cudaFuncSetAttribute(mppi_rollout_fp32_kernel<true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    AMPC_CUDA_CHECK(ampc_raise_smem_limit((const void *)mppi_rollout_fp32_kernel<true>, need));
   else
-    AMPC_CUDA_CHECK(cudaFuncSetAttribute(mppi_rollout_fp32_kernel<false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    AMPC_CUDA_CHECK(ampc_raise_smem_limit((const void *)mppi_rollout_fp32_kernel<false>, need));
   *resident_out = res;
   *smem_out = need;
   return AMPC_OK;

@@ -1028,7 +1028,7 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
   if (e == cudaSuccess) e = cudaMemcpy(pl->d_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_epsc, (size_t)cfg->H * cfg->nu * a.Kc * sizeof(float));
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(tc_kernel_ptr(cg, a.nxp, mlp->act, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
+    e = ampc_raise_smem_limit((const void *)tc_kernel_ptr(cg, a.nxp, mlp->act, false), pl->smem);
   if (e != cudaSuccess) {
     ampc_set_error("tcgen05 MPPI path create: %s", cudaGetErrorString(e));
     ampc_mppi_tc_destroy(pl);
@@ -1044,7 +1044,7 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
     if (v == 2 || v == 4 || v == 6 || v == 8) a.defer_j = v;
   }
   if (getenv("AMPC_TC_TRACE") && tc_trace_available(cg, a.nxp, mlp->act)) {
-    cudaFuncSetAttribute(tc_kernel_ptr(cg, a.nxp, mlp->act, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
+    ampc_raise_smem_limit((const void *)tc_kernel_ptr(cg, a.nxp, mlp->act, true), pl->smem);
     if (cudaMalloc(&pl->d_trace, (NTHR / 32) * TRACE_EV * sizeof(unsigned long long)) == cudaSuccess) {
       cudaMemset(pl->d_trace, 0, (NTHR / 32) * TRACE_EV * sizeof(unsigned long long));
       a.trace = pl->d_trace;

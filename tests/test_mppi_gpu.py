@@ -490,3 +490,20 @@ def test_mppi_sumcost_per_sample_terminal_matches_oracle(precision):
     np.testing.assert_allclose(costs + ctl._term_const, costs_o, rtol=TOL[precision]["cost_rtol"] * 10,
                                atol=TOL[precision]["cost_rtol"] * np.abs(costs_o).max())
     ctl.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_handles_with_different_shared_memory_needs_coexist(precision):
+    """The dynamic shared-memory limit is a per-kernel attribute: a controller created earlier with the LARGER need
+    (longer horizon) must still launch after a smaller one was created (regression: invalid-argument launch error
+    when evaluate_candidates mixed horizons)."""
+    p = synthetic_mlp(4, 1, [64, 64], seed=2)
+    cost = QuadCostParams(np.eye(4), 0.1 * np.eye(1), np.eye(4))
+    big = _engine(p, cost, [-1.0], [1.0], horizon=60, num_path=256, seed=1, precision=precision)
+    small = _engine(p, cost, [-1.0], [1.0], horizon=5, num_path=256, seed=1, precision=precision)
+    x0 = np.array([0.1, 0.2, -0.1, 0.0])
+    u_small = small.solve(x0)
+    u_big = big.solve(x0)                     # failed with cudaErrorInvalidValue before the limit became monotone
+    assert np.all(np.isfinite(u_small)) and np.all(np.isfinite(u_big))
+    big.close()
+    small.close()
