@@ -42,7 +42,10 @@ if rank == 0:
     for ex in ("nvlink", "nccl"):
         d = np.abs(res[ex][1] - uf).max(axis=1)
         assert d[0] < 1e-5 and d.max() < 5e-2, (ex, d)
-    assert np.abs(res["nvlink"][1] - res["nccl"][1]).max() < 1e-5
+    # the two exchanges merge the same records with different thread groupings: first solve equal to fp32 rounding,
+    # later (warm-started) solves within the bf16 tolerance like the comparison with the single GPU above
+    dx = np.abs(res["nvlink"][1] - res["nccl"][1]).max(axis=1)
+    assert dx[0] < 1e-5 and dx.max() < 5e-2, dx
     print("multi_gpu_check ok", flush=True)
 dist.barrier()
 dist.destroy_process_group()
