@@ -298,22 +298,25 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   float *s_red = s_cc + TM;                            // 32
   float *s_misc = s_red + 32;                          // 64 + AMPC_MERGE_CACHE
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_misc + 64 + AMPC_MERGE_CACHE);   // [0..1]=bar_d[h], [2..3]=bar_a[kp]
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2 * MAXG);
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2 * MAXG + 1);   // s_bar[2*MAXG] = bar_w (weight image landed)
   __shared__ int s_last;
 
-  {
-    const uint4 *src = reinterpret_cast<const uint4 *>(a.wimg + (size_t)cta_rank * a.w_bytes);
-    uint4 *dst = reinterpret_cast<uint4 *>(s_w);
-    const int nv = (int)(a.w_bytes >> 4);
-    constexpr int WU = 8;                               // 16-byte loads in flight per thread
-    for (int i0 = tid; i0 < nv; i0 += NTHR * WU) {
-      uint4 v[WU];
-#pragma unroll
-      for (int u = 0; u < WU; ++u)
-        if (i0 + u * NTHR < nv) v[u] = __ldg(src + i0 + u * NTHR);
-#pragma unroll
-      for (int u = 0; u < WU; ++u)
-        if (i0 + u * NTHR < nv) dst[i0 + u * NTHR] = v[u];
+  // Weight image (this CTA's half): TMA bulk copies global -> shared, completion counted in bytes on bar_w.  One
+  // thread issues them before anything else so that they overlap the rest of the setup; it waits for them just
+  // before the setup barrier.  (The staged LDG/STS loop this replaces was most of the 7.8 k-cycle setup.)
+  const uint32_t bar_w = smem_u32(&s_bar[2 * MAXG]);
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    fence_mbar_init();
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(a.w_bytes) : "memory");
+    const uint8_t *src = a.wimg + (size_t)cta_rank * a.w_bytes;
+    constexpr uint32_t CHUNK = 32768;
+    for (uint32_t off = 0; off < a.w_bytes; off += CHUNK) {
+      const uint32_t n = (a.w_bytes - off < CHUNK) ? a.w_bytes - off : CHUNK;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(s_w + off)),
+                   "l"(src + off), "r"(n), "r"(bar_w)
+                   : "memory");
     }
   }
   for (int i = tid; i < cl.total; i += NTHR) s_const[i] = p.consts[i];
@@ -359,7 +362,8 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
     fence_mbar_init();
   }
   if (warp == MMA_WARP) tmem_alloc<CG>(smem_u32(s_tmem));
-  fence_proxy_async_smem();                            // weight image (generic-proxy stores) -> tensor-core reads
+  if (tid == 0) mbar_wait(bar_w, 0);                   // weight image landed (async proxy -> async proxy: no fence needed)
+  fence_proxy_async_smem();
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -811,7 +815,7 @@ size_t tc_smem_bytes(const TcArgs &a, int nx, int nu, int H) {
   const AmpcConstLayout cl(nx, nu);
   const size_t floats = (size_t)cl.total + ((H * nu + 3) & ~3) + (size_t)nx * TM +
                         (size_t)2 * nu * TM + 2 * 64 + 2 * 2 * 32 + 4 * 32 + 2 * TM + 32 + 64 + AMPC_MERGE_CACHE;
-  return 1024 + a.w_bytes + floats * sizeof(float) + 2 * MAXG * sizeof(uint64_t) + 16 +
+  return 1024 + a.w_bytes + floats * sizeof(float) + (2 * MAXG + 1) * sizeof(uint64_t) + 16 +
          (getenv("AMPC_TC_TRACE") ? (NTHR / 32) * TRACE_EV * sizeof(uint32_t) + 16 : 0);
 }
 
