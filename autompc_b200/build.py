@@ -9,6 +9,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libampc_b200.so")
 SOURCES = ["mppi_api.cu", "mppi_fp32.cu", "mppi_tc.cu", "mlp_ops.cu", "ilqr.cu"]
+# the tcgen05 kernel template is instantiated once per (cta_group, NXP, ReLU, trace) combination, each as its own
+# compilation of mppi_tc_inst.cu, so that the matrix builds in parallel
+TC_INSTANCES = [(cg, nxp, relu, 0) for cg in (1, 2) for relu in (0, 1) for nxp in (4, 8, 16, 24, 32)] + [(2, 24, 1, 1)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -30,26 +33,42 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a and link the shared library."""
+    """Compile every CUDA source for sm_100a (up to os.cpu_count() nvcc processes at a time) and link the library."""
     if not force and not needs_build():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    objs = []
-    procs = []
-    for src in SOURCES:
-        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-            "-c", os.path.join(CSRC, src), "-o", obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
-    for src, pr in procs:
+    for f in os.listdir(LIB_DIR):                        # stale objects of an older source layout
+        if f.endswith(".o"):
+            os.remove(os.path.join(LIB_DIR, f))
+    jobs = [(src, os.path.join(LIB_DIR, src.replace(".cu", ".o")), []) for src in SOURCES]
+    for cg, nxp, relu, tr in TC_INSTANCES:
+        obj = os.path.join(LIB_DIR, "mppi_tc_inst_cg%d_nxp%d_relu%d_trace%d.o" % (cg, nxp, relu, tr))
+        jobs.append(("mppi_tc_inst.cu", obj, ["-DAMPC_TC_INST_CG=%d" % cg, "-DAMPC_TC_INST_NXP=%d" % nxp,
+                                              "-DAMPC_TC_INST_RELU=%d" % relu, "-DAMPC_TC_INST_TRACE=%d" % tr]))
+    max_par = max(1, min(len(jobs), int(os.environ.get("AMPC_BUILD_JOBS", os.cpu_count() or 4))))
+    pending, running, objs = list(jobs), [], []
+
+    def reap(src, pr):
         out, _ = pr.communicate()
         if verbose or pr.returncode:
             sys.stderr.write(out)
         if pr.returncode:
+            for _, other in running:
+                other.kill()
             raise RuntimeError("nvcc failed on %s" % src)
+
+    while pending or running:
+        while pending and len(running) < max_par:
+            src, obj, defs = pending.pop(0)
+            cmd = [_nvcc()] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + [
+                "-c", os.path.join(CSRC, src), "-o", obj]
+            running.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+            objs.append(obj)
+        reap(*running.pop(0))
     cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
+    for obj in objs:                                     # only the .so travels with the repo snapshot
+        os.remove(obj)
     return LIB
 
 
