@@ -65,9 +65,9 @@ def measured_peaks():
 
 def ncu_traffic(precision, world):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the rollout kernel, from the committed
-    `ncu --set full` capture of this same command at N=1 (profiles/r01_mppi_tc_v11_ncu_full.md: 492 288 B read,
-    0 B written -- the clipped-noise scratch stays in L2).  None when no capture exists for the configuration."""
-    return 492288 if (precision == "bf16" and world == 1) else None
+    `ncu --set full` capture of this same command at N=1 (profiles/r01_mppi_tc_v11_ncu_full.md: 503 296 B read,
+    1 792 B written -- the clipped-noise scratch stays in L2).  None when no capture exists for the configuration."""
+    return 503296 + 1792 if (precision == "bf16" and world == 1) else None
 
 
 # --------------------------------------------------------------------------- CPU arm ---
