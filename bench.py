@@ -92,6 +92,12 @@ def cpu_port_rate(wl, budget_s, min_solves=2):
             o.solve(wl["x0"])
         return (time.perf_counter() - t0) / n
 
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 for every rank)
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
     probe_k = min(K, 512)
     t_probe = run(probe_k, 1)
     per_sample = t_probe / probe_k
