@@ -125,6 +125,7 @@ class MPPI(Controller):
             raise ValueError("num_path=%d cannot be sharded over %d ranks" % (self.num_path, self.world))
         # --- engine handle
         self._mlp_holder = _abi.MlpDescHolder(self.weights)
+        self._host_io = None
         self._cost_holder, self._stage_const, self._term_const = _quad_cost_of(task, nx, nu)
         lib = _abi.lib()
         self._h = None
@@ -225,13 +226,22 @@ class MPPI(Controller):
             eps = self.sample_numpy_noise()
         if self.world > 1:
             u = self._solve_sharded(x0, eps)
+        elif eps is None:
+            # hot path of run(): preallocated buffers and cached ctypes pointers (``a.ctypes.data_as`` builds a new
+            # interface object per call: several microseconds next to a 240 us solve)
+            io = self._host_io
+            if io is None:
+                xb, ub = np.empty(self.dim_state), np.empty(self.dim_ctrl)
+                io = self._host_io = (xb, ub, _abi.dptr(xb), _abi.dptr(ub), _abi.lib().ampc_mppi_solve_host)
+            io[0][:] = x0
+            rc = io[4](self._h, io[2], None, self.seed, self.cur_step, io[3])
+            if rc:
+                _abi.check(rc)
+            u = io[1].copy()                    # callee returns fresh arrays (controller.py:61-121)
         else:
             u = np.empty(self.dim_ctrl)
-            e_ptr = None
-            if eps is not None:
-                eps = _abi.f64(eps, (self.H, self.K_local, self.dim_ctrl))
-                e_ptr = _abi.dptr(eps)
-            _abi.check(_abi.lib().ampc_mppi_solve_host(self._h, _abi.dptr(x0), e_ptr, self.seed, self.cur_step,
+            eps = _abi.f64(eps, (self.H, self.K_local, self.dim_ctrl))
+            _abi.check(_abi.lib().ampc_mppi_solve_host(self._h, _abi.dptr(x0), _abi.dptr(eps), self.seed, self.cur_step,
                                                        _abi.dptr(u)))
         self.cur_step += 1
         return u
