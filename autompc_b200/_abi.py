@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libampc_b200.so")
 
 AMPC_OK, AMPC_ERR_INVALID, AMPC_ERR_UNSUPPORTED, AMPC_ERR_CUDA, AMPC_ERR_NOMEM = 0, -1, -2, -3, -4
 ACT_CODES = {"relu": 0, "tanh": 1, "sigmoid": 2, "selu": 3}
-PREC_CODES = {"fp32": 0, "bf16": 1}
+PREC_CODES = {"fp32": 0, "bf16": 1, "fp16": 2}
 MAX_LAYERS = 5
 
 _dp = C.POINTER(C.c_double)
@@ -60,6 +60,7 @@ EXPORTS = {
     "ampc_mppi_connect_peers_ipc": [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p],
     "ampc_mppi_connect_peers_local": [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)],
     "ampc_mppi_solve_fused": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p],
+    "ampc_mppi_solve_fused_host": [C.c_void_p, _dp, _dp, C.c_uint64, C.c_uint64, _dp],
     "ampc_mppi_closed_loop_start": [C.c_void_p, C.c_void_p, _dp, C.c_int32, C.c_uint64, C.c_uint64],
     "ampc_mppi_closed_loop_finish": [C.c_void_p, C.c_int32, _dp, _dp, _dp],
     "ampc_mppi_debug_trace": [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32],

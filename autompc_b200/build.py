@@ -11,7 +11,8 @@ LIB = os.path.join(LIB_DIR, "libampc_b200.so")
 SOURCES = ["mppi_api.cu", "mppi_fp32.cu", "mppi_tc.cu", "mlp_ops.cu", "ilqr.cu"]
 # the tcgen05 kernel template is instantiated once per (cta_group, NXP, ReLU, trace) combination, each as its own
 # compilation of mppi_tc_inst.cu, so that the matrix builds in parallel
-TC_INSTANCES = [(cg, nxp, relu, 0) for cg in (1, 2) for relu in (0, 1) for nxp in (4, 8, 16, 24, 32)] + [(2, 24, 1, 1)]
+TC_INSTANCES = [(cg, nxp, relu, f16, 0) for f16 in (0, 1) for cg in (1, 2) for relu in (0, 1)
+                for nxp in (4, 8, 16, 24, 32)] + [(2, 24, 1, 0, 1)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -41,10 +42,11 @@ def build(force=False, verbose=False):
         if f.endswith(".o"):
             os.remove(os.path.join(LIB_DIR, f))
     jobs = [(src, os.path.join(LIB_DIR, src.replace(".cu", ".o")), []) for src in SOURCES]
-    for cg, nxp, relu, tr in TC_INSTANCES:
-        obj = os.path.join(LIB_DIR, "mppi_tc_inst_cg%d_nxp%d_relu%d_trace%d.o" % (cg, nxp, relu, tr))
+    for cg, nxp, relu, f16, tr in TC_INSTANCES:
+        obj = os.path.join(LIB_DIR, "mppi_tc_inst_cg%d_nxp%d_relu%d_f16%d_trace%d.o" % (cg, nxp, relu, f16, tr))
         jobs.append(("mppi_tc_inst.cu", obj, ["-DAMPC_TC_INST_CG=%d" % cg, "-DAMPC_TC_INST_NXP=%d" % nxp,
-                                              "-DAMPC_TC_INST_RELU=%d" % relu, "-DAMPC_TC_INST_TRACE=%d" % tr]))
+                                              "-DAMPC_TC_INST_RELU=%d" % relu, "-DAMPC_TC_INST_F16=%d" % f16,
+                                              "-DAMPC_TC_INST_TRACE=%d" % tr]))
     max_par = max(1, min(len(jobs), int(os.environ.get("AMPC_BUILD_JOBS", os.cpu_count() or 4))))
     pending, running, objs = list(jobs), [], []
 

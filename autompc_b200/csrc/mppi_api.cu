@@ -188,8 +188,10 @@ void free_handle(ampc_mppi *h) {
   delete h;
 }
 
+// fused = true: the multi-GPU exchange runs in the kernel's tail (ampc_mppi_connect_peers_* done before)
 int launch_rollout(ampc_mppi *h, const float *dev_x0, const float *dev_eps, uint64_t seed, uint64_t counter,
-                   float *dev_u, float *dev_record, cudaStream_t stream, const float *inline_x0 = nullptr) {
+                   float *dev_u, float *dev_record, cudaStream_t stream, const float *inline_x0 = nullptr,
+                   bool fused = false) {
   AmpcMppiParams p = h->p;
   p.x0_inline = 0;
   if (inline_x0) {
@@ -203,8 +205,61 @@ int launch_rollout(ampc_mppi *h, const float *dev_x0, const float *dev_eps, uint
   p.u_out = dev_u;
   p.record_out = dev_record;
   p.peer_mail = nullptr;
+  if (fused) {
+    p.record_out = h->d_rec;
+    p.peer_mail = h->d_peer;
+    p.world = h->world;
+    p.rank = h->rank;
+    p.seq = ++h->seq;
+  }
   if (h->tc) return ampc_mppi_tc_launch(h->tc, p, stream);
   return ampc_mppi_fp32_launch(p, h->resident, h->smem, stream);
+}
+
+// external noise (parity mode): float64 host (H,K,nu) -> pinned float32 staging -> device, on the handle's stream
+int stage_eps(ampc_mppi *h, const double *host_eps, const float **d_eps_out) {
+  const size_t n = (size_t)h->cfg.H * h->cfg.K * h->cfg.nu;
+  if (h->eps_elems < n) {
+    if (h->h_eps) cudaFreeHost(h->h_eps);
+    cudaFree(h->d_eps);
+    h->h_eps = nullptr; h->d_eps = nullptr; h->eps_elems = 0;
+    AMPC_CUDA_CHECK(cudaMallocHost(&h->h_eps, n * sizeof(float)));
+    AMPC_CUDA_CHECK(cudaMalloc(&h->d_eps, n * sizeof(float)));
+    h->eps_elems = n;
+  }
+  for (size_t i = 0; i < n; ++i) h->h_eps[i] = (float)host_eps[i];
+  AMPC_CUDA_CHECK(cudaMemcpyAsync(h->d_eps, h->h_eps, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  *d_eps_out = h->d_eps;
+  return AMPC_OK;
+}
+
+// One solve with HOST buffers on the handle's stream (fused = with the peer exchange in the kernel's tail).
+int solve_host_impl(ampc_mppi *h, const double *host_x0, const double *host_eps, uint64_t seed, uint64_t counter,
+                    double *host_u, bool fused) {
+  const int nx = h->cfg.nx, nu = h->cfg.nu;
+  for (int j = 0; j < nx; ++j) h->h_pin[j] = (float)host_x0[j];
+  const float *d_eps = nullptr;
+  if (host_eps) {
+    int rc = stage_eps(h, host_eps, &d_eps);
+    if (rc) return rc;
+  }
+  if (nx <= 32 && !getenv("AMPC_NO_INLINE_IO")) {
+    // The only host traffic besides (optional) external noise is the observation in (nx floats) and the control out
+    // (nu floats).  The observation rides in the kernel parameters and the last CTA writes the control straight into
+    // the mapped pinned buffer: one launch + one synchronise instead of copy -> launch -> copy on the stream.
+    int rc = launch_rollout(h, h->d_x0, d_eps, seed, counter, h->d_pin + nx, nullptr, h->stream, h->h_pin, fused);
+    if (rc) return rc;
+    AMPC_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    for (int j = 0; j < nu; ++j) host_u[j] = h->h_pin[nx + j];
+    return AMPC_OK;
+  }
+  AMPC_CUDA_CHECK(cudaMemcpyAsync(h->d_x0, h->h_pin, nx * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  int rc = launch_rollout(h, h->d_x0, d_eps, seed, counter, h->d_u, nullptr, h->stream, nullptr, fused);
+  if (rc) return rc;
+  AMPC_CUDA_CHECK(cudaMemcpyAsync(h->h_pin + nx, h->d_u, nu * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  AMPC_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  for (int j = 0; j < nu; ++j) host_u[j] = h->h_pin[nx + j];
+  return AMPC_OK;
 }
 
 }  // namespace
@@ -307,10 +362,11 @@ extern "C" int ampc_mppi_create(ampc_mppi **out, const ampc_mppi_cfg *cfg, const
   p.consts = h->d_consts; p.act_seq = h->d_act; p.costs = h->d_costs; p.term_out = h->d_term;
   p.ticket = h->d_ticket;
 
-  if (cfg->precision == AMPC_PREC_BF16) {
+  if (cfg->precision == AMPC_PREC_BF16 || cfg->precision == AMPC_PREC_FP16) {
     const char *why = "";
     if (!ampc_mppi_tc_supported(cfg, mlp, &why)) {
-      ampc_set_error("precision=bf16 (tcgen05) does not support this problem: %s", why);
+      ampc_set_error("precision=%s (tcgen05) does not support this problem: %s",
+                     cfg->precision == AMPC_PREC_FP16 ? "fp16" : "bf16", why);
       free_handle(h);
       return AMPC_ERR_UNSUPPORTED;
     }
@@ -389,42 +445,7 @@ extern "C" int ampc_mppi_solve_host(ampc_mppi *h, const double *host_x0, const d
                                     uint64_t counter, double *host_u) {
   AMPC_REQUIRE(h && host_x0 && host_u, AMPC_ERR_INVALID, "null argument");
   DeviceGuard g(h->device);
-  const int nx = h->cfg.nx, nu = h->cfg.nu;
-  for (int j = 0; j < nx; ++j) h->h_pin[j] = (float)host_x0[j];
-  if (!host_eps && nx <= 32 && !getenv("AMPC_NO_INLINE_IO")) {
-    // In-kernel noise: the only host traffic is the observation in (nx floats) and the control out (nu floats).
-    // The observation rides in the kernel parameters and the last CTA writes the control straight into the mapped
-    // pinned buffer: one launch + one synchronise instead of copy -> launch -> copy on the stream.
-    int rc = launch_rollout(h, h->d_x0, nullptr, seed, counter, h->d_pin + nx, nullptr, h->stream, h->h_pin);
-    if (rc) return rc;
-    AMPC_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    for (int j = 0; j < nu; ++j) host_u[j] = h->h_pin[nx + j];
-    return AMPC_OK;
-  }
-  AMPC_CUDA_CHECK(cudaMemcpyAsync(h->d_x0, h->h_pin, nx * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  const float *d_eps = nullptr;
-  if (host_eps) {
-    const size_t n = (size_t)h->cfg.H * h->cfg.K * nu;
-    if (h->eps_elems < n) {
-      if (h->h_eps) cudaFreeHost(h->h_eps);
-  for (void *q : h->ipc_opened) cudaIpcCloseMemHandle(q);
-  cudaFree(h->d_mail); cudaFree(h->d_rec); cudaFree(h->d_peer); cudaFree(h->d_cl);
-      cudaFree(h->d_eps);
-      h->h_eps = nullptr; h->d_eps = nullptr; h->eps_elems = 0;
-      AMPC_CUDA_CHECK(cudaMallocHost(&h->h_eps, n * sizeof(float)));
-      AMPC_CUDA_CHECK(cudaMalloc(&h->d_eps, n * sizeof(float)));
-      h->eps_elems = n;
-    }
-    for (size_t i = 0; i < n; ++i) h->h_eps[i] = (float)host_eps[i];
-    AMPC_CUDA_CHECK(cudaMemcpyAsync(h->d_eps, h->h_eps, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    d_eps = h->d_eps;
-  }
-  int rc = launch_rollout(h, h->d_x0, d_eps, seed, counter, h->d_u, nullptr, h->stream);
-  if (rc) return rc;
-  AMPC_CUDA_CHECK(cudaMemcpyAsync(h->h_pin + nx, h->d_u, nu * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-  AMPC_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-  for (int j = 0; j < nu; ++j) host_u[j] = h->h_pin[nx + j];
-  return AMPC_OK;
+  return solve_host_impl(h, host_x0, host_eps, seed, counter, host_u, false);
 }
 
 extern "C" int ampc_mppi_get_costs(ampc_mppi *h, double *host_costs, double *term_const) {
@@ -568,14 +589,15 @@ extern "C" int ampc_mppi_solve_fused(ampc_mppi *h, const float *dev_x0, const fl
   AMPC_REQUIRE(h && dev_x0 && dev_u, AMPC_ERR_INVALID, "null argument");
   AMPC_REQUIRE(h->d_peer && h->world >= 1, AMPC_ERR_INVALID, "ampc_mppi_connect_peers_* has not been called");
   DeviceGuard g(h->device);
-  AmpcMppiParams p = h->p;
-  p.x0 = dev_x0; p.eps = dev_eps; p.seed = seed; p.ctr = counter; p.u_out = dev_u;
-  p.record_out = h->d_rec;
-  p.peer_mail = h->d_peer;
-  p.world = h->world; p.rank = h->rank;
-  p.seq = ++h->seq;
-  if (h->tc) return ampc_mppi_tc_launch(h->tc, p, (cudaStream_t)stream);
-  return ampc_mppi_fp32_launch(p, h->resident, h->smem, (cudaStream_t)stream);
+  return launch_rollout(h, dev_x0, dev_eps, seed, counter, dev_u, nullptr, (cudaStream_t)stream, nullptr, true);
+}
+
+extern "C" int ampc_mppi_solve_fused_host(ampc_mppi *h, const double *host_x0, const double *host_eps, uint64_t seed,
+                                          uint64_t counter, double *host_u) {
+  AMPC_REQUIRE(h && host_x0 && host_u, AMPC_ERR_INVALID, "null argument");
+  AMPC_REQUIRE(h->d_peer && h->world >= 1, AMPC_ERR_INVALID, "ampc_mppi_connect_peers_* has not been called");
+  DeviceGuard g(h->device);
+  return solve_host_impl(h, host_x0, host_eps, seed, counter, host_u, true);
 }
 
 // ------------------------------------------------------------ device-resident closed loop ---

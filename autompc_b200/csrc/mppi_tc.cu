@@ -1,4 +1,4 @@
-// Host side of the tcgen05 MPPI path: shape planning, bf16 weight images, launch.  The kernel lives in
+// Host side of the tcgen05 MPPI path: shape planning, 16-bit (bf16 or IEEE half) weight images, launch.  The kernel lives in
 // mppi_tc_kernel.cuh and is instantiated in mppi_tc_inst_*.cu.
 #include <algorithm>
 #include <vector>
@@ -17,6 +17,51 @@ uint16_t f32_to_bf16(float f) {
   return (uint16_t)(u >> 16);
 }
 
+// IEEE half, round to nearest even, saturating at +-65504 (the kernel's conversions are .satfinite too)
+uint16_t f32_to_f16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint16_t sign = (uint16_t)((u >> 16) & 0x8000u);
+  const uint32_t mag = u & 0x7FFFFFFFu;
+  if (mag > 0x7F800000u) return (uint16_t)(sign | 0x7E00u);           // NaN
+  if (mag >= 0x477FF000u) return (uint16_t)(sign | 0x7BFFu);          // >= 65520 rounds past the largest finite half
+  if (mag < 0x33000001u) return sign;                                 // <= 2^-25: rounds to zero
+  int e = (int)(mag >> 23) - 127;
+  uint32_t m = (mag & 0x7FFFFFu) | 0x800000u;                         // 24-bit significand
+  int shift = (e < -14) ? (13 + (-14 - e)) : 13;                      // subnormal halves lose more bits
+  uint32_t h = m >> shift;
+  const uint32_t rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1);
+  if (rem > half || (rem == half && (h & 1u))) ++h;
+  if (e < -14) return (uint16_t)(sign | h);                           // subnormal (a carry into 0x400 is the smallest normal)
+  return (uint16_t)(sign | (uint16_t)(((uint32_t)(e + 15) << 10) + (h - 0x400u)));   // carry propagates into the exponent
+}
+float f16_to_f32(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  int e = (h >> 10) & 31;
+  uint32_t m = h & 0x3FFu;
+  uint32_t u;
+  if (e == 0) {
+    if (m == 0) { u = sign; }
+    else {
+      e = 1;
+      while (!(m & 0x400u)) { m <<= 1; --e; }
+      u = sign | ((uint32_t)(e + 112) << 23) | ((m & 0x3FFu) << 13);
+    }
+  } else if (e == 31) u = sign | 0x7F800000u | (m << 13);
+  else u = sign | ((uint32_t)(e + 112) << 23) | (m << 13);
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+uint16_t f32_to_16(float f, bool f16) { return f16 ? f32_to_f16(f) : f32_to_bf16(f); }
+float f16or_bf16_to_f32(uint16_t h, bool f16) {
+  if (f16) return f16_to_f32(h);
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
 size_t tc_smem_bytes(const TcArgs &a, int nx, int nu, int H) {
   const AmpcConstLayout cl(nx, nu);
   const size_t floats = (size_t)cl.total + ((H * nu + 3) & ~3) + (size_t)nx * TM +
@@ -33,7 +78,7 @@ int chunk_width(int npad, bool last) {
   return npad / 2;                    // hidden GEMMs of width >= 128 are issued as two N-halves
 }
 
-void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg) {
+void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg, bool f16) {
   memset(&a, 0, sizeof(a));
   a.n_layers = mlp->n_layers;
   {
@@ -57,14 +102,14 @@ void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg) {
     off += (uint32_t)kblk * rows * 128;
     a.b_off[l] = boff;
     boff += a.npad[l];
-    // kind::f16: c=f32 (bit 4), a=bf16 (bit 7), b=bf16 (bit 10), both K-major, N>>3 at 17, M>>4 at 24
+    // kind::f16: c=f32 (bit 4), a/b format at bits 7 / 10 (0 = f16, 1 = bf16), both K-major, N>>3 at 17, M>>4 at 24
     a.cw[l] = chunk_width(a.npad[l], l == mlp->n_layers - 1);
     a.nch[l] = a.npad[l] / a.cw[l];
     a.nh[l] = a.nch[l];
     a.hwid[l] = a.cw[l];
     a.nkp[l] = (l == 0) ? 1 : a.nh[l - 1];
     a.awid[l] = (l == 0) ? 64 : a.hwid[l - 1];
-    a.idesc[l] = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.cw[l] >> 3) << 17) |
+    a.idesc[l] = (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(a.cw[l] >> 3) << 17) |
                  ((uint32_t)((TM * cg) >> 4) << 24);
   }
   a.w_bytes = off;
@@ -75,12 +120,14 @@ void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg) {
 
 // the timeline build (AMPC_TC_TRACE=1) exists for the headline shape only: CTA pairs, NXP = 24, ReLU
 static bool tc_trace_available(int cg, int nxp, int act) { return cg == 2 && nxp == 24 && act == AMPC_ACT_RELU; }
-static TcKernel tc_kernel_ptr(int cg, int nxp, int act, bool traced) {
-  if (traced && tc_trace_available(cg, nxp, act)) return ampc_tc_kernel_cg2_nxp24_relu1_trace1();
+static TcKernel tc_kernel_ptr(int cg, int nxp, int act, bool f16, bool traced) {
+  if (traced && !f16 && tc_trace_available(cg, nxp, act)) return ampc_tc_kernel_cg2_nxp24_relu1_f160_trace1();
   const bool relu = act == AMPC_ACT_RELU;
-#define AMPC_TC_PICK(N)                                                                                           \
-  return cg == 1 ? (relu ? ampc_tc_kernel_cg1_nxp##N##_relu1_trace0() : ampc_tc_kernel_cg1_nxp##N##_relu0_trace0()) \
-                 : (relu ? ampc_tc_kernel_cg2_nxp##N##_relu1_trace0() : ampc_tc_kernel_cg2_nxp##N##_relu0_trace0())
+#define AMPC_TC_PICK_F(N, F)                                                                                                  \
+  return cg == 1 ? (relu ? ampc_tc_kernel_cg1_nxp##N##_relu1_f16##F##_trace0() : ampc_tc_kernel_cg1_nxp##N##_relu0_f16##F##_trace0()) \
+                 : (relu ? ampc_tc_kernel_cg2_nxp##N##_relu1_f16##F##_trace0() : ampc_tc_kernel_cg2_nxp##N##_relu0_f16##F##_trace0())
+#define AMPC_TC_PICK(N) \
+  if (f16) { AMPC_TC_PICK_F(N, 1); } else { AMPC_TC_PICK_F(N, 0); }
   switch (nxp) {
     case 4: AMPC_TC_PICK(4);
     case 8: AMPC_TC_PICK(8);
@@ -89,11 +136,13 @@ static TcKernel tc_kernel_ptr(int cg, int nxp, int act, bool traced) {
     default: AMPC_TC_PICK(32);
   }
 #undef AMPC_TC_PICK
+#undef AMPC_TC_PICK_F
 }
 
 struct AmpcTcPlan {
   TcArgs args;
   int cg = 1;
+  bool f16 = false;
   int act = AMPC_ACT_RELU;
   int grid = 0;
   size_t smem = 0;
@@ -108,6 +157,25 @@ static bool tc_shape_ok(const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp, cons
   if (cfg->nu > 32) { *why = "nu > 32"; return false; }
   for (int l = 1; l < mlp->n_layers; ++l)
     if (mlp->dims[l] > 256) { *why = "hidden width > 256"; return false; }
+  {
+    // the input layer's A operand has 4 K-steps = 64 columns: padded state + controls + the two constant-one columns
+    const int nxp = cfg->nx <= 4 ? 4 : (cfg->nx <= 8 ? 8 : (cfg->nx <= 16 ? 16 : (cfg->nx <= 24 ? 24 : 32)));
+    if (nxp + cfg->nu + 2 > 64) { *why = "padded state + controls + 2 bias columns exceed the 64-column input block"; return false; }
+  }
+  if (cfg->precision == AMPC_PREC_FP16) {
+    // IEEE half operands: every weight (output rows as scaled into z space) and bias must be finite in half
+    const int L = mlp->n_layers, nx = mlp->dims[L];
+    for (int l = 0; l < L; ++l) {
+      const int Kl = mlp->dims[l], Nl = mlp->dims[l + 1];
+      for (int n = 0; n < Nl; ++n) {
+        const double k1 = (l == L - 1) ? mlp->dy_std[n] / mlp->xu_std[n] : 1.0;
+        double mx = fabs((l == L - 1) ? (mlp->b[l][n] * mlp->dy_std[n] + mlp->dy_mean[n]) / mlp->xu_std[n] : mlp->b[l][n]);
+        for (int k = 0; k < Kl; ++k) mx = fmax(mx, fabs(mlp->W[l][(size_t)n * Kl + k] * k1));
+        if (!(mx < 6.0e4)) { *why = "a weight or bias exceeds the IEEE half range (precision=fp16)"; return false; }
+      }
+    }
+    (void)nx;
+  }
   return true;
 }
 
@@ -115,7 +183,7 @@ static bool tc_shape_ok(const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp, cons
 static int tc_pick_cg(const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp, size_t cap, TcArgs *out, size_t *smem_out) {
   for (int cg = 1; cg <= 2; ++cg) {
     TcArgs a;
-    fill_args(a, mlp, cg);
+    fill_args(a, mlp, cg, cfg->precision == AMPC_PREC_FP16);
     const size_t need = tc_smem_bytes(a, cfg->nx, cfg->nu, cfg->H);
     if (need <= cap) {
       *out = a;
@@ -137,7 +205,7 @@ int ampc_mppi_tc_supported(const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp, c
   TcArgs a;
   size_t smem = 0;
   if (!tc_pick_cg(cfg, mlp, (size_t)max_optin, &a, &smem)) {
-    *why = "bf16 weight image does not fit in the shared memory of a CTA pair";
+    *why = "16-bit weight image does not fit in the shared memory of a CTA pair";
     return 0;
   }
   return 1;
@@ -162,7 +230,7 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
   const char *force = getenv("AMPC_TC_FORCE_CG");
   if (force && (force[0] == '1' || force[0] == '2')) {
     const int f = force[0] - '0';
-    fill_args(pl->args, mlp, f);
+    fill_args(pl->args, mlp, f, cfg->precision == AMPC_PREC_FP16);
     pl->smem = tc_smem_bytes(pl->args, cfg->nx, cfg->nu, cfg->H);
     cg = (pl->smem <= (size_t)max_optin) ? f : 0;
   }
@@ -172,6 +240,8 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
     return AMPC_ERR_UNSUPPORTED;
   }
   pl->cg = cg;
+  pl->f16 = cfg->precision == AMPC_PREC_FP16;
+  const bool f16 = pl->f16;
   pl->act = mlp->act;
   TcArgs &a = pl->args;
   const int tiles = (cfg->K + TM - 1) / TM;
@@ -212,12 +282,10 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
               if (ng < Nl && (bsel == 0 || bsel == 1)) {
                 const float b = outl ? (float)((mlp->b[l][ng] * mlp->dy_std[ng] + mlp->dy_mean[ng]) / mlp->xu_std[ng])
                                      : (float)mlp->b[l][ng];
-                uint32_t hb = (uint32_t)f32_to_bf16(b) << 16;
-                float bhi;
-                memcpy(&bhi, &hb, 4);
+                const float bhi = f16or_bf16_to_f32(f32_to_16(b, f16), f16);
                 v = (bsel == 0) ? bhi : (b - bhi);
               }
-              img[byte / 2 + e] = f32_to_bf16(v);
+              img[byte / 2 + e] = f32_to_16(v, f16);
             }
           }
     for (int j = 0; j < Nl; ++j) bias[a.b_off[l] + j] = (float)mlp->b[l][j];
@@ -228,7 +296,7 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
   if (e == cudaSuccess) e = cudaMemcpy(pl->d_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_epsc, (size_t)cfg->H * cfg->nu * a.Kc * sizeof(float));
   if (e == cudaSuccess)
-    e = ampc_raise_smem_limit((const void *)tc_kernel_ptr(cg, a.nxp, mlp->act, false), pl->smem);
+    e = ampc_raise_smem_limit((const void *)tc_kernel_ptr(cg, a.nxp, mlp->act, f16, false), pl->smem);
   if (e != cudaSuccess) {
     ampc_set_error("tcgen05 MPPI path create: %s", cudaGetErrorString(e));
     ampc_mppi_tc_destroy(pl);
@@ -243,8 +311,8 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
     const int v = atoi(dj);
     if (v == 2 || v == 4 || v == 6 || v == 8) a.defer_j = v;
   }
-  if (getenv("AMPC_TC_TRACE") && tc_trace_available(cg, a.nxp, mlp->act)) {
-    ampc_raise_smem_limit((const void *)tc_kernel_ptr(cg, a.nxp, mlp->act, true), pl->smem);
+  if (getenv("AMPC_TC_TRACE") && !f16 && tc_trace_available(cg, a.nxp, mlp->act)) {
+    ampc_raise_smem_limit((const void *)tc_kernel_ptr(cg, a.nxp, mlp->act, f16, true), pl->smem);
     if (cudaMalloc(&pl->d_trace, (NTHR / 32) * TRACE_EV * sizeof(unsigned long long)) == cudaSuccess) {
       cudaMemset(pl->d_trace, 0, (NTHR / 32) * TRACE_EV * sizeof(unsigned long long));
       a.trace = pl->d_trace;
@@ -270,7 +338,7 @@ int ampc_mppi_tc_launch(AmpcTcPlan *plan, const AmpcMppiParams &p, cudaStream_t 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_kernel_ptr(plan->cg, plan->args.nxp, plan->act, plan->args.trace != nullptr), p, plan->args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_kernel_ptr(plan->cg, plan->args.nxp, plan->act, plan->f16, plan->args.trace != nullptr), p, plan->args);
   ampc_count_launch();
   AMPC_CUDA_CHECK(e);
   return AMPC_OK;

@@ -212,15 +212,21 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-// {lo, hi} -> packed bf16x2 (element with the even K index in the low half)
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+// {lo, hi} -> packed 16-bit pair (element with the even K index in the low half).  F16 = false: bf16 (8-bit
+// mantissa, fp32 range); F16 = true: IEEE half (11-bit mantissa -- the operand precision of kind::tf32 -- at the
+// full kind::f16 rate; finite range 65504, so the conversions saturate instead of producing inf).
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_16(float lo, float hi) {
   uint32_t d;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  if constexpr (F16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
-__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_16_relu(float lo, float hi) {
   uint32_t d;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  if constexpr (F16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
 // d^T M d for this thread's sample; v laid out [i][TM]
@@ -245,15 +251,15 @@ __device__ __forceinline__ float quad_full(const float *M, const float *v, const
 
 // activation + bf16 pack of NV consecutive accumulator columns (the bias is already in the accumulator:
 // it enters every hidden GEMM through a constant-one K-step, split in two bf16 terms)
-template <int NV, bool RELU>
+template <int NV, bool RELU, bool F16>
 __device__ __forceinline__ void epi_pack(const uint32_t (&r)[NV], int act, uint32_t (&pk)[NV / 2]) {
   if constexpr (RELU) {
 #pragma unroll
-    for (int q = 0; q < NV / 2; ++q) pk[q] = pack_bf16_relu(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]));
+    for (int q = 0; q < NV / 2; ++q) pk[q] = pack_16_relu<F16>(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]));
   } else {
 #pragma unroll
     for (int q = 0; q < NV / 2; ++q)
-      pk[q] = pack_bf16(ampc_act<float>(act, __uint_as_float(r[2 * q])), ampc_act<float>(act, __uint_as_float(r[2 * q + 1])));
+      pk[q] = pack_16<F16>(ampc_act<float>(act, __uint_as_float(r[2 * q])), ampc_act<float>(act, __uint_as_float(r[2 * q + 1])));
   }
 }
 
@@ -275,7 +281,7 @@ __device__ __forceinline__ void issue_pair(uint32_t dh, uint32_t a_pair, uint32_
 // instantiation with a runtime switch.  Keeping their code out of the ReLU kernel matters: inlined, it put 43 KB
 // of cold instructions between the LDTM, the packs and the STTM of every epilogue (instruction-cache misses on
 // the critical path).
-template <int CG, int NXP, bool RELU, bool TRACE>
+template <int CG, int NXP, bool RELU, bool F16, bool TRACE>
 __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppiParams p, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -578,14 +584,14 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
       asm volatile("bar.sync %0, %1;" ::"r"(BAR_FULL + b), "n"(NEPI / 2 + NCTL) : "memory");   // controls of `step` are ready
       if constexpr (NXP % 16 != 0) {
 #pragma unroll
-        for (int q = 0; q < NMIX; ++q) cpk[q] = pack_bf16(zctl(su, NXP + 2 * q), zctl(su, NXP + 2 * q + 1));
+        for (int q = 0; q < NMIX; ++q) cpk[q] = pack_16<F16>(zctl(su, NXP + 2 * q), zctl(su, NXP + 2 * q + 1));
       }
 #pragma unroll
       for (int g = (NXP + 15) / 16; g < 4; ++g) {
         if (g * 16 < kpad0) {
           uint32_t pk[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) pk[q] = pack_bf16(zctl(su, g * 16 + 2 * q), zctl(su, g * 16 + 2 * q + 1));
+          for (int q = 0; q < 8; ++q) pk[q] = pack_16<F16>(zctl(su, g * 16 + 2 * q), zctl(su, g * 16 + 2 * q + 1));
           tmem_st8(lane_base + buf * TMEM_BUF + (uint32_t)((g >> 1) * 32 + (g & 1) * 8), pk);
         }
       }
@@ -598,7 +604,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int k = g * 16 + q * 2;                 // NXP is even: a pair is all state or all control
-          if (k < NXP) pk[q] = pack_bf16(z[k < NXP ? k : 0], z[k + 1 < NXP ? k + 1 : 0]);
+          if (k < NXP) pk[q] = pack_16<F16>(z[k < NXP ? k : 0], z[k + 1 < NXP ? k + 1 : 0]);
           else pk[q] = cpk[(k - NXP) / 2 < NMIX ? (k - NXP) / 2 : 0];
         }
         tmem_st8(lane_base + buf * TMEM_BUF + (uint32_t)((g >> 1) * 32 + (g & 1) * 8), pk);
@@ -638,21 +644,21 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
             tmem_ld32(c0, ra);
             tmem_ld32(c0 + 32, rb);
             tc_wait_ld();
-            epi_pack<32, RELU>(ra, p.act, pk);
+            epi_pack<32, RELU, F16>(ra, p.act, pk);
             tmem_st16(c0, pk);
-            epi_pack<32, RELU>(rb, p.act, pk);
+            epi_pack<32, RELU, F16>(rb, p.act, pk);
             tmem_st16(c0 + 16, pk);
           } else {                                      // hwid == 64: 32 columns
             const uint32_t c0 = dbuf + (uint32_t)(h * 64 + hf * 32);
             tmem_ld32(c0, ra);
             tc_wait_ld();
-            epi_pack<32, RELU>(ra, p.act, pk);
+            epi_pack<32, RELU, F16>(ra, p.act, pk);
             tmem_st16(c0, pk);
           }
           if (h == 0 && hf == 0 && a.ones[l]) {         // constant-one K-step of the next GEMM (its bias), in free columns
             uint32_t one[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) one[q] = q == 0 ? 0x3F803F80u : 0u;
+            for (int q = 0; q < 8; ++q) one[q] = q == 0 ? (F16 ? 0x3C003C00u : 0x3F803F80u) : 0u;
             tmem_st8(dbuf + (uint32_t)(hwid >> 2), one);
           }
           signal_a(h);
@@ -811,11 +817,12 @@ typedef void (*TcKernel)(const AmpcMppiParams, const TcArgs);
 }  // namespace ampc_tc
 
 // one getter per instantiation (mppi_tc_inst.cu compiled once per combination)
-#define AMPC_TC_DECL(cg, nxp, relu, tr) ampc_tc::TcKernel ampc_tc_kernel_cg##cg##_nxp##nxp##_relu##relu##_trace##tr();
-#define AMPC_TC_DECL_NXP(cg, relu) \
-  AMPC_TC_DECL(cg, 4, relu, 0) AMPC_TC_DECL(cg, 8, relu, 0) AMPC_TC_DECL(cg, 16, relu, 0) AMPC_TC_DECL(cg, 24, relu, 0) \
-  AMPC_TC_DECL(cg, 32, relu, 0)
-AMPC_TC_DECL_NXP(1, 0) AMPC_TC_DECL_NXP(1, 1) AMPC_TC_DECL_NXP(2, 0) AMPC_TC_DECL_NXP(2, 1)
-AMPC_TC_DECL(2, 24, 1, 1)   // the timeline build: headline shape only
+#define AMPC_TC_DECL(cg, nxp, relu, f16, tr) ampc_tc::TcKernel ampc_tc_kernel_cg##cg##_nxp##nxp##_relu##relu##_f16##f16##_trace##tr();
+#define AMPC_TC_DECL_NXP(cg, relu, f16) \
+  AMPC_TC_DECL(cg, 4, relu, f16, 0) AMPC_TC_DECL(cg, 8, relu, f16, 0) AMPC_TC_DECL(cg, 16, relu, f16, 0) \
+  AMPC_TC_DECL(cg, 24, relu, f16, 0) AMPC_TC_DECL(cg, 32, relu, f16, 0)
+AMPC_TC_DECL_NXP(1, 0, 0) AMPC_TC_DECL_NXP(1, 1, 0) AMPC_TC_DECL_NXP(2, 0, 0) AMPC_TC_DECL_NXP(2, 1, 0)
+AMPC_TC_DECL_NXP(1, 0, 1) AMPC_TC_DECL_NXP(1, 1, 1) AMPC_TC_DECL_NXP(2, 0, 1) AMPC_TC_DECL_NXP(2, 1, 1)
+AMPC_TC_DECL(2, 24, 1, 0, 1)   // the timeline build: headline shape only
 #undef AMPC_TC_DECL_NXP
 #undef AMPC_TC_DECL

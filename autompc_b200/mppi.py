@@ -13,8 +13,14 @@ Engine-only keyword arguments (all optional):
                ``(seed, cur_step, sample, step)``) or ``"numpy"`` (parity mode:
                the noise is drawn on the host from the global NumPy stream in
                exactly the reference's order, ``mppi.py:126``, and uploaded).
-``precision``  ``"fp32"`` | ``"bf16"`` | ``"auto"`` (bf16 tcgen05 kernel when the
-               MLP shape allows it, else fp32).
+``precision``  ``"fp32"`` (CUDA-core FMA) | ``"fp16"`` | ``"bf16"`` (tcgen05 tensor-core kernel
+               with IEEE-half / bfloat16 operands, fp32 accumulation, state, cost and
+               softmax) | ``"auto"`` (default: fp16 when the shape and the weight range
+               allow it, else bf16, else fp32).  The reference computes in float64
+               (``autompc/sysid/mlp.py:165``); measured deviation of the updated,
+               normalised action sequence from it at the C3 configuration: fp32 ~1e-4,
+               fp16 ~1e-3 (11-bit significands = the operand precision of tf32),
+               bf16 ~1e-2.  Ask for ``"fp32"`` when parity matters more than speed.
 ``terminal``   ``"reference"`` (default: last sample's terminal cost added to
                all samples, ``mppi.py:79-82``) or ``"per_sample"``.
 ``device``     CUDA ordinal.
@@ -129,9 +135,9 @@ class MPPI(Controller):
         self._cost_holder, self._stage_const, self._term_const = _quad_cost_of(task, nx, nu)
         lib = _abi.lib()
         self._h = None
-        order = {"auto": ["bf16", "fp32"], "fp32": ["fp32"], "bf16": ["bf16"]}.get(precision)
+        order = {"auto": ["fp16", "bf16", "fp32"], "fp32": ["fp32"], "bf16": ["bf16"], "fp16": ["fp16"]}.get(precision)
         if order is None:
-            raise ValueError("precision must be 'auto', 'fp32' or 'bf16'")
+            raise ValueError("precision must be 'auto', 'fp32', 'fp16' or 'bf16'")
         err = None
         for prec in order:
             cfg = _abi.MppiCfg(self.K_local, self.H, nx, nu, self.sigma, self.lmda,
@@ -179,7 +185,22 @@ class MPPI(Controller):
         self.cur_step = 0
         self.niter = 1                                                     # mppi.py:105
         act = np.random.normal(scale=np.sqrt(self.sigma), size=(self.H, self.dim_ctrl))
-        self._set_act(act)
+        # sharded controller: every rank must roll out around the SAME nominal sequence; rank 0's draw is the one
+        self._set_act(self._from_rank0(act))
+
+    def _from_rank0(self, a):
+        """Broadcast of a host float64 array from rank 0 of the group (identity when unsharded).  The ranks'
+        process-global NumPy streams are not assumed to be in step."""
+        if self.world == 1:
+            return a
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+        on_gpu = dist.get_backend(self.group) == "nccl"
+        if on_gpu:
+            t = t.to(torch.device("cuda", self.device))
+        dist.broadcast(t, src=dist.get_global_rank(self.group, 0), group=self.group)
+        return t.cpu().numpy()
 
     # ------------------------------------------------------------------ engine access ---
     def _set_act(self, act):
@@ -215,7 +236,7 @@ class MPPI(Controller):
     def sample_numpy_noise(self):
         """mppi.py:126: K*H*nu draws in C order over (K,H,nu), transposed to (H,K,nu)."""
         eps = np.random.normal(scale=np.sqrt(self.sigma), size=(self.num_path, self.H, self.dim_ctrl))
-        eps = eps.transpose((1, 0, 2))
+        eps = self._from_rank0(eps).transpose((1, 0, 2))     # sharded: rank 0's stream is the one (see _from_rank0)
         return np.ascontiguousarray(eps[:, self.k_offset:self.k_offset + self.K_local, :])
 
     # ------------------------------------------------------------------ solve ---
@@ -283,6 +304,22 @@ class MPPI(Controller):
         self.cur_step += 1
 
     def _solve_sharded(self, x0, eps):
+        if self.exchange == "nvlink":
+            # one launch, no torch on the path: observation in the kernel parameters, merged control in mapped pinned
+            # host memory (same as the unsharded hot path)
+            io = self._host_io
+            if io is None:
+                xb, ub = np.empty(self.dim_state), np.empty(self.dim_ctrl)
+                io = self._host_io = (xb, ub, _abi.dptr(xb), _abi.dptr(ub), _abi.lib().ampc_mppi_solve_fused_host)
+            io[0][:] = x0
+            e = None
+            if eps is not None:
+                eps = _abi.f64(eps, (self.H, self.K_local, self.dim_ctrl))
+                e = _abi.dptr(eps)
+            rc = io[4](self._h, io[2], e, self.seed, self.cur_step, io[3])
+            if rc:
+                _abi.check(rc)
+            return io[1].copy()
         import torch
         dev = torch.device("cuda", self.device)
         b = self._shard_bufs()

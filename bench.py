@@ -67,7 +67,7 @@ def ncu_traffic(precision, world):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the rollout kernel, from the committed
     `ncu --set full` capture of this same command at N=1 (profiles/r01_mppi_tc_v11_ncu_full.md: 503 296 B read,
     1 792 B written -- the clipped-noise scratch stays in L2).  None when no capture exists for the configuration."""
-    return 503296 + 1792 if (precision == "bf16" and world == 1) else None
+    return 503296 + 1792 if (precision in ("bf16", "fp16") and world == 1) else None
 
 
 # --------------------------------------------------------------------------- CPU arm ---
@@ -282,7 +282,7 @@ def gpu_arm(args, wl, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16" if ctl.precision == "bf16" else "f32", "data": "synthetic",
+            "dtype": {"bf16": "bf16", "fp16": "fp16"}.get(ctl.precision, "f32"), "data": "synthetic",
             "config": {"workload": wl["label"], "noise": "in-kernel Philox4x32-10", "precision": ctl.precision,
                        "parallelism": ("samples sharded over %d GPU(s), %d-float softmax record exchanged by %s"
                                        % (world, 2 + wl["H"] * nu,
@@ -323,7 +323,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c2"])
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp16", "bf16"])
     ap.add_argument("--exchange", default="nvlink", choices=["nvlink", "nccl"],
                     help="N>1: how the ranks' softmax records meet (fused NVLink peer stores, or NCCL all-gather)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

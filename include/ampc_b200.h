@@ -42,7 +42,13 @@ enum { AMPC_ACT_RELU = 0, AMPC_ACT_TANH = 1, AMPC_ACT_SIGMOID = 2, AMPC_ACT_SELU
 /* arithmetic of the MPPI rollout kernel */
 enum {
   AMPC_PREC_FP32 = 0, /* CUDA-core fp32 FMA, any layer sizes <= 256                       */
-  AMPC_PREC_BF16 = 1  /* tcgen05 (UMMA) bf16 x bf16 -> fp32 in TMEM; state/cost stay fp32  */
+  AMPC_PREC_BF16 = 1, /* tcgen05 (UMMA) bf16 x bf16 -> fp32 in TMEM; state/cost stay fp32  */
+  AMPC_PREC_FP16 = 2  /* tcgen05 (UMMA) IEEE half x half -> fp32: 11-bit significands, i.e. the
+                         operand precision of kind::tf32, at the full kind::f16 rate and half the
+                         shared-memory footprint of tf32 (a tf32 image of the 3x256 network does not
+                         fit a CTA pair).  Operands saturate at +-65504; create() refuses weights
+                         outside that range (AMPC_ERR_UNSUPPORTED).  The reference network is
+                         float64 (autompc/sysid/mlp.py:165); this is the fp32-class tensor-core mode */
 };
 
 #define AMPC_MAX_LAYERS 5 /* <= 4 hidden + output, autompc/sysid/mlp.py:110-111 */
@@ -146,6 +152,11 @@ int ampc_mppi_connect_peers_ipc(ampc_mppi *h, int32_t world, int32_t rank, const
 int ampc_mppi_connect_peers_local(ampc_mppi *h, int32_t world, int32_t rank, ampc_mppi *const *handles);
 int ampc_mppi_solve_fused(ampc_mppi *h, const float *dev_x0, const float *dev_eps, uint64_t seed,
                           uint64_t counter, float *dev_u, void *stream);
+/* solve_fused with HOST buffers (what MPPI.run holds, mppi.py:154-168): like solve_host the observation rides in
+ * the kernel parameters and the merged control lands in mapped pinned host memory; synchronous.  host_eps: NULL or
+ * this shard's (H,K,nu) float64 slice of the unclipped noise.                                              */
+int ampc_mppi_solve_fused_host(ampc_mppi *h, const double *host_x0, const double *host_eps, uint64_t seed,
+                               uint64_t counter, double *host_u);
 
 /* Debug tap, no reference counterpart: when the handle was created with AMPC_TC_TRACE=1 in the environment,
  * copies the tcgen05 kernel's timeline of CTA 0 ([warp][64] words = clock64 << 8 | tag) to host.       */

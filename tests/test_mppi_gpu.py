@@ -507,3 +507,172 @@ def test_handles_with_different_shared_memory_needs_coexist(precision):
     assert np.all(np.isfinite(u_small)) and np.all(np.isfinite(u_big))
     big.close()
     small.close()
+
+
+# ----------------------------------------------------------------------------- round-2 regressions / parity holes ---
+def test_external_eps_after_peer_connect_and_closed_loop():
+    """Regression (round-1 review): the external-eps staging branch of ampc_mppi_solve_host freed the peer mailboxes and
+    the closed-loop buffers.  Sequence on ONE handle pair: connect peers -> fused solve -> external-eps solve (grows the
+    staging buffers) -> fused solve again -> destroy; and closed loop -> external eps -> closed loop on another."""
+    import ctypes as C
+    import torch
+    from autompc_b200 import MPPI, B200MLP, _abi, simulate
+    from tests.gpu_helpers import problem_of
+    p = synthetic_mlp(17, 6, [64, 64], seed=2)
+    cost = QuadCostParams(np.eye(17), 0.01 * np.eye(6), 10 * np.eye(17))
+    K, H = 512, 8
+    np.random.seed(0)
+    full = _engine(p, cost, -np.ones(6), np.ones(6), horizon=H, num_path=K, seed=5, precision="fp32")
+    act0 = np.ascontiguousarray(full.act_sequence)
+    x0 = np.random.default_rng(1).normal(size=17)
+    lib = _abi.lib()
+    dev = torch.device("cuda", 0)
+    x0_d = torch.tensor(x0, dtype=torch.float32, device=dev)
+    hs = (C.c_void_p * 2)()
+    for r, (off, n) in enumerate([(0, 256), (256, 256)]):
+        cfg = _abi.MppiCfg(n, H, 17, 6, 1.0, 1.0, 0, _abi.PREC_CODES["fp32"], off, K, 0)
+        h = C.c_void_p()
+        _abi.check(lib.ampc_mppi_create(C.byref(h), C.byref(cfg), C.byref(full._mlp_holder.desc),
+                                        C.byref(full._cost_holder.desc)))
+        _abi.check(lib.ampc_mppi_set_act_seq(h, _abi.dptr(act0)))
+        hs[r] = h
+    for r in range(2):
+        _abi.check(lib.ampc_mppi_connect_peers_local(hs[r], 2, r, hs))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    us = [torch.zeros(6, dtype=torch.float32, device=dev) for _ in range(2)]
+
+    def fused(step):
+        for r in range(2):
+            _abi.check(lib.ampc_mppi_solve_fused(hs[r], x0_d.data_ptr(), None, 5, step, us[r].data_ptr(),
+                                                 streams[r].cuda_stream))
+        torch.cuda.synchronize()
+        return [u.cpu().numpy() for u in us]
+
+    u_ref = full.solve(x0)
+    for u in fused(0):
+        np.testing.assert_allclose(u, u_ref, rtol=0, atol=SHARD_ATOL)
+    # external noise on the connected handles (this is the branch that used to free d_mail / d_rec / d_peer)
+    eps = np.random.default_rng(2).normal(size=(H, 256, 6))
+    for r in range(2):
+        u = np.empty(6)
+        _abi.check(lib.ampc_mppi_solve_host(hs[r], _abi.dptr(x0), _abi.dptr(eps), 5, 1, _abi.dptr(u)))
+        assert np.all(np.isfinite(u))
+    for r in range(2):                                     # the host solves updated each shard on its own: re-align
+        _abi.check(lib.ampc_mppi_set_act_seq(hs[r], _abi.dptr(act0)))
+    full.act_sequence = act0
+    u_ref = full.solve(x0)                                 # cur_step 1 on `full`; fused() must use the same counter
+    for u in fused(1):
+        np.testing.assert_allclose(u, u_ref, rtol=0, atol=SHARD_ATOL)
+    for r in range(2):
+        _abi.check(lib.ampc_mppi_destroy(hs[r]))          # double free / double close showed up here
+    full.close()
+    # closed loop -> external eps -> closed loop
+    system, task, model = problem_of(p, cost, -np.ones(6), np.ones(6))
+    np.random.seed(3)
+    ctl = MPPI(system, task, model, horizon=H, num_path=256, seed=9, precision="fp32")
+    a = simulate(ctl, x0, sim_model=model, max_steps=6)
+    ctl.solve(x0, eps=np.random.default_rng(4).normal(size=(H, 256, 6)))
+    np.random.seed(3)
+    ctl.reset()                                           # same draw as the constructor's, cur_step back to 0
+    b = simulate(ctl, x0, sim_model=model, max_steps=6)   # T <= cl_T: reuses d_cl (was freed memory before the fix)
+    np.testing.assert_array_equal(a.obs, b.obs)
+    np.testing.assert_array_equal(a.ctrls, b.ctrls)
+    torch.cuda.synchronize()
+    ctl.close()
+
+
+# tensor-core modes: tolerances are the deviations measured by scripts/measure_precision.py (profiles/r02_precision.jsonl)
+# with head-room.  fp16 = IEEE-half operands (11-bit significands, what kind::tf32 keeps), fp32 accumulate.
+TOL["fp16"] = dict(cost_rtol=3e-4, act_atol=5e-3)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_mppi_c3_full_size_matches_oracle(precision):
+    """BASELINE config C3 at its OWN size (K=16384, H=50, MLP 23-256-256-256-17) on the tensor-core kernel against the
+    float64 oracle on the same uploaded noise (mppi.py:120-152): costs, arg-min sample, action sequence, control."""
+    from autompc_b200.problems import halfcheetah_dim_problem
+    from autompc_b200 import MPPI, B200MLP
+    from oracle.mppi_oracle import MLPParams
+    system, task, w, x0 = halfcheetah_dim_problem()
+    Q, R, F = task.get_cost().get_cost_matrices()
+    p = MLPParams(w.W, w.b, w.act, w.xu_mean, w.xu_std, w.dy_mean, w.dy_std, w.nx, w.nu)
+    cost = QuadCostParams(Q, R, F, task.get_cost().get_goal())
+    b = task.get_ctrl_bounds()
+    np.random.seed(0)
+    ctl = MPPI(system, task, B200MLP(system, w), horizon=50, num_path=16384, noise="numpy", precision=precision)
+    np.random.seed(0)
+    o = MPPIOracle(p, cost, b[:, 0], b[:, 1], horizon=50, num_path=16384)
+    eps = o.sample_eps()
+    _check_solve(ctl, o, x0, eps, TOL[precision], check_argmin=False)
+    costs, _ = ctl.last_costs()
+    ref = o.last_costs - o.term_const
+    srt = np.sort(ref)
+    if srt[1] - srt[0] > 4 * TOL[precision]["cost_rtol"] * abs(srt[0]):
+        assert int(np.argmin(costs)) == int(np.argmin(ref))
+    ctl.close()
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_mppi_fp16_tensor_core_matches_oracle(case, monkeypatch):
+    """IEEE-half operands on the same tcgen05 kernel: fp32-class tolerance (SURVEY 7.3 planned tf32 at 5e-3)."""
+    nx, nu, hidden, act, K, H, sigma, lmda, force_cg = case[:9]
+    dense = len(case) > 9 and case[9]
+    if force_cg:
+        monkeypatch.setenv("AMPC_TC_FORCE_CG", force_cg)
+    else:
+        monkeypatch.delenv("AMPC_TC_FORCE_CG", raising=False)
+    rng = np.random.default_rng(5)
+    p = synthetic_mlp(nx, nu, hidden, act=act, seed=3)
+    if dense:
+        A, B, C = rng.normal(size=(nx, nx)), rng.normal(size=(nu, nu)), rng.normal(size=(nx, nx))
+        cost = QuadCostParams(A @ A.T / nx, 0.01 * (B @ B.T) / nu, C @ C.T / nx, goal=0.1 * rng.normal(size=nx))
+    else:
+        cost = QuadCostParams(np.eye(nx), 0.01 * np.eye(nu), 10 * np.eye(nx), goal=0.05 * rng.normal(size=nx))
+    umax = rng.uniform(0.5, 2.0, size=nu)
+    umin = -umax * rng.uniform(0.5, 1.0, size=nu)
+    np.random.seed(1)
+    ctl = _engine(p, cost, umin, umax, horizon=H, num_path=K, sigma=sigma, lmda=lmda, noise="numpy",
+                  precision="fp16")
+    assert ctl.precision == "fp16"
+    np.random.seed(1)
+    o = MPPIOracle(p, cost, umin, umax, horizon=H, num_path=K, sigma=sigma, lmda=lmda)
+    x0 = rng.normal(size=nx)
+    for _ in range(3):
+        eps = o.sample_eps()
+        u, _ = _check_solve(ctl, o, x0, eps, TOL["fp16"], check_argmin=False)
+        costs, _t = ctl.last_costs()
+        ref = o.last_costs - o.term_const
+        srt = np.sort(ref)
+        if K > 1 and srt[1] - srt[0] > 4 * TOL["fp16"]["cost_rtol"] * abs(srt[0]):
+            assert int(np.argmin(costs)) == int(np.argmin(ref))
+        x0 = mlp_pred_batch(p, x0[None], u[None])[0]
+    ctl.close()
+
+
+def test_fp16_refuses_out_of_range_weights_and_auto_falls_back():
+    """precision='fp16' needs weights inside the half range; 'auto' then takes bf16 (same kernel, bf16 operands)."""
+    p = synthetic_mlp(4, 1, [32], seed=1)
+    p.weights[0][0, 0] = 1.0e5
+    cost = QuadCostParams(np.eye(4), np.eye(1), np.eye(4))
+    with pytest.raises(ValueError, match="half range"):
+        _engine(p, cost, [-1.0], [1.0], horizon=5, num_path=64, precision="fp16")
+    ctl = _engine(p, cost, [-1.0], [1.0], horizon=5, num_path=64, precision="auto")
+    assert ctl.precision == "bf16"
+    ctl.close()
+
+
+def test_tc_refuses_input_block_overflow():
+    """nx padded to 32 plus nu >= 31 does not fit the 64-column input block: the tensor-core path must refuse it
+    (round-1 advisor finding: it silently dropped the last control / bias columns) and 'auto' must take fp32."""
+    p = synthetic_mlp(30, 31, [64], seed=1)
+    cost = QuadCostParams(np.eye(30), np.eye(31), np.eye(30))
+    for prec in ("bf16", "fp16"):
+        with pytest.raises(ValueError, match="input block"):
+            _engine(p, cost, -np.ones(31), np.ones(31), horizon=4, num_path=64, precision=prec)
+    np.random.seed(0)
+    ctl = _engine(p, cost, -np.ones(31), np.ones(31), horizon=4, num_path=64, precision="auto", noise="numpy")
+    assert ctl.precision == "fp32"
+    np.random.seed(0)
+    o = MPPIOracle(p, cost, -np.ones(31), np.ones(31), horizon=4, num_path=64)
+    _check_solve(ctl, o, np.zeros(30), o.sample_eps(), TOL["fp32"], check_argmin=False)
+    ctl.close()
