@@ -10,8 +10,12 @@ products with fp32 state/cost ("bf16").  The softmax amplifies ABSOLUTE cost err
 by 1/lmda, so the tolerance on the updated action sequence is per (precision, lmda,
 cost scale); the numbers below are for the listed cases:
    fp32 : costs rtol 2e-5, action sequence atol 2e-3 (normalised controls, |.| <= 1)
-   bf16 : costs rtol 2e-3, action sequence atol 5e-2
+   fp16 : costs rtol 1e-4, action sequence atol 2e-3   (IEEE-half operands = tf32's 11-bit significands)
+   bf16 : costs rtol 1e-3, action sequence atol 2e-2
    exact: argmin(costs) (trajectory index), the shift indexing, the RNG draw order.
+Measured on a B200 (scripts/measure_precision.py -> profiles/r02_precision.jsonl), worst case over the synthetic
+cases below / at C3 full size: fp32 7e-5 / 1.3e-5, fp16 8.6e-4 / 2.1e-4, bf16 7.4e-3 / 2.1e-3 on the action
+sequence; 5e-7, 3.1e-5, 2.6e-4 relative on the costs.
 """
 import os
 
@@ -24,7 +28,8 @@ from tests.helpers import GOLDEN, load_cartpole, synthetic_mlp
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": dict(cost_rtol=2e-5, act_atol=2e-3), "bf16": dict(cost_rtol=2e-3, act_atol=5e-2)}
+TOL = {"fp32": dict(cost_rtol=2e-5, act_atol=2e-3), "fp16": dict(cost_rtol=1e-4, act_atol=2e-3),
+       "bf16": dict(cost_rtol=1e-3, act_atol=2e-2)}
 
 # sharded vs unsharded solves run the same per-sample arithmetic (Philox is keyed by the global sample index);
 # they differ only in the fp32 summation order of the softmax merge: a few ulp of O(1) controls
@@ -345,14 +350,15 @@ def test_mppi_full_size_c3_properties():
     properties: (i) the update is a convex combination of the clipped noise => every entry of
     act_sequence - shift(act_sequence) lies inside the clip box; (ii) costs of the first 256 samples
     equal a K=256 solve on the same global sample indices (samples are independent);
-    (iii) identical seeds => identical result; (iv) auto precision picks the tensor-core path."""
+    (iii) identical seeds => identical result; (iv) auto precision picks the tensor-core path.
+    (The oracle comparison at this size is test_mppi_c3_full_size_matches_oracle.)"""
     from autompc_b200.problems import halfcheetah_dim_problem
     from autompc_b200 import MPPI, B200MLP
     system, task, w, x0 = halfcheetah_dim_problem()
     model = B200MLP(system, w)
     np.random.seed(0)
     big = MPPI(system, task, model, horizon=50, num_path=16384, seed=3)
-    assert big.precision == "bf16"
+    assert big.precision == "fp16"                 # 'auto': tensor-core kernel, IEEE-half operands
     act0 = big.act_sequence
     u1 = big.solve(x0)
     costs_big, _ = big.last_costs()
@@ -581,11 +587,6 @@ def test_external_eps_after_peer_connect_and_closed_loop():
     ctl.close()
 
 
-# tensor-core modes: tolerances are the deviations measured by scripts/measure_precision.py (profiles/r02_precision.jsonl)
-# with head-room.  fp16 = IEEE-half operands (11-bit significands, what kind::tf32 keeps), fp32 accumulate.
-TOL["fp16"] = dict(cost_rtol=3e-4, act_atol=5e-3)
-
-
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
 def test_mppi_c3_full_size_matches_oracle(precision):
     """BASELINE config C3 at its OWN size (K=16384, H=50, MLP 23-256-256-256-17) on the tensor-core kernel against the
@@ -675,4 +676,45 @@ def test_tc_refuses_input_block_overflow():
     np.random.seed(0)
     o = MPPIOracle(p, cost, -np.ones(31), np.ones(31), horizon=4, num_path=64)
     _check_solve(ctl, o, np.zeros(30), o.sample_eps(), TOL["fp32"], check_argmin=False)
+    ctl.close()
+
+
+# Unmodified-reference fixtures on the TENSOR-CORE kernel (round-1 review: they only ran on the fp32 kernel).
+# The fixtures use the trained cartpole MLP, whose dynamics near the upright are unstable, with F = diag(2,3000,.15,.3):
+# operand rounding is amplified along the H-step rollouts and then by F, so the stated tolerance is per fixture
+# (measured deviations: profiles/r02_precision.jsonl).  K512_H30 in bf16 is not comparable at all (the arg-min sample
+# flips: cost differences of 2.5 % of the cost scale at lmda = 1) and is excluded with this note; C2's own
+# configuration (K4096_H30) passes in both modes.
+FIXTURE_TC_TOL = {
+    ("mppi_cartpole_K256_H20", "fp16"): dict(act=1e-3, cost_diff=1e-3),
+    ("mppi_cartpole_K256_H20", "bf16"): dict(act=5e-3, cost_diff=6e-3),
+    ("mppi_cartpole_K100_H5", "fp16"): dict(act=5e-3, cost_diff=1e-3),
+    ("mppi_cartpole_K100_H5", "bf16"): dict(act=5e-2, cost_diff=1.5e-2),
+    ("mppi_cartpole_K512_H30", "fp16"): dict(act=5e-2, cost_diff=4e-3),
+    ("mppi_cartpole_K4096_H30", "fp16"): dict(act=1e-3, cost_diff=2e-3),
+    ("mppi_cartpole_K4096_H30", "bf16"): dict(act=1e-3, cost_diff=8e-3),
+}
+
+
+@pytest.mark.parametrize("name,precision", sorted(FIXTURE_TC_TOL))
+def test_tensor_core_kernel_matches_unmodified_reference_fixture(name, precision):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    mlp, cost, umin, umax, _, _ = load_cartpole()
+    tol = FIXTURE_TC_TOL[(name, precision)]
+    np.random.seed(int(z["seed"]))
+    ctl = _engine(mlp, cost, umin, umax, horizon=int(z["H"]), num_path=int(z["K"]), sigma=float(z["sigma"]),
+                  lmda=float(z["lmda"]), noise="numpy", precision=precision)
+    assert ctl.precision == precision
+    np.testing.assert_allclose(ctl.act_sequence, z["act0"], rtol=0, atol=1e-7)
+    constate = np.zeros(5)
+    for s_ in range(int(z["n_steps"])):
+        if s_ > 0:
+            ctl.act_sequence = z["act_%d" % (s_ - 1)]      # every step compared from the reference's warm start
+        u, constate = ctl.run(constate, z["x0_%d" % s_])
+        costs, term = ctl.last_costs()
+        ref = z["costs_%d" % s_]
+        np.testing.assert_allclose(costs - costs.min(), ref - ref.min(), rtol=0, atol=tol["cost_diff"] * np.abs(ref).max())
+        assert int(np.argmin(costs)) == int(z["argmin_%d" % s_])
+        np.testing.assert_allclose(ctl.act_sequence, z["act_%d" % s_], rtol=0, atol=tol["act"])
+        np.testing.assert_allclose(u, z["u_%d" % s_], rtol=0, atol=tol["act"] * 20.0)
     ctl.close()
