@@ -52,6 +52,8 @@ EXPORTS = {
     "ampc_mppi_solve_host": [C.c_void_p, _dp, _dp, C.c_uint64, C.c_uint64, _dp],
     "ampc_mppi_solve": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p],
     "ampc_mppi_get_costs": [C.c_void_p, _dp, _dp],
+    "ampc_mppi_set_box_costs": [C.c_void_p, C.c_int32, _dp, _dp, _dp],
+    "ampc_mppi_set_eval_cost": [C.c_void_p, C.POINTER(QuadCost), C.c_int32, _dp, _dp, _dp],
     "ampc_mppi_get_noise": [C.c_void_p, C.c_uint64, C.c_uint64, _fp],
     "ampc_mppi_record_floats": [C.c_void_p],
     "ampc_mppi_rollout_partial": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p],

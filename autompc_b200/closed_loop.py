@@ -42,6 +42,26 @@ def _check(controller, term_cond, dynamics, sim_model):
         raise ValueError("the closed loop needs noise='philox' and an unsharded controller")
 
 
+def _set_eval_cost(controller, cost):
+    """The trajectory cost the closed loop accumulates: the controller's own by default; ``cost`` (any cost object
+    ``cost_spec_of`` reads: QuadCost / ThresholdCost / BoxThresholdCost / SumCost of them) when the candidate is
+    scored with the TASK's cost rather than the one it optimises (tuning/pipeline_tuner.py:230-231)."""
+    if cost is None:
+        if getattr(controller, "_eval_cost", None) is not None:      # back to the controller's own cost
+            spec = controller._cost
+            _abi.check(_abi.lib().ampc_mppi_set_eval_cost(
+                controller._h, C.byref(spec.holder.desc), spec.n_box, _abi.dptr(spec.box_lo), _abi.dptr(spec.box_hi),
+                _abi.dptr(spec.box_w)))
+            controller._eval_cost = None
+        return
+    from .mppi import cost_spec_of
+    spec = cost_spec_of(cost, controller.task.get_ctrl_bounds(), controller.dim_state, controller.dim_ctrl)
+    _abi.check(_abi.lib().ampc_mppi_set_eval_cost(
+        controller._h, C.byref(spec.holder.desc) if spec.quad else None, spec.n_box, _abi.dptr(spec.box_lo),
+        _abi.dptr(spec.box_hi), _abi.dptr(spec.box_w)))
+    controller._eval_cost = spec
+
+
 def _start(controller, sim, init_obs, T):
     x0 = _abi.f64(init_obs, (controller.dim_state,))
     _abi.check(_abi.lib().ampc_mppi_closed_loop_start(controller._h, sim._h, _abi.dptr(x0), T, controller.seed,
@@ -55,23 +75,29 @@ def _finish(controller, T):
     _abi.check(_abi.lib().ampc_mppi_closed_loop_finish(controller._h, T, _abi.dptr(obs), _abi.dptr(ctrls[:T]),
                                                        C.byref(cost)))
     # constants of a folded SumCost: Cost.__call__ (cost.py:27-41) adds the stage cost of all T+1 states + one terminal
-    total = cost.value + (T + 1) * controller._stage_const + controller._term_const
+    spec = getattr(controller, "_eval_cost", None) or controller._cost
+    total = cost.value + (T + 1) * spec.stage_const + spec.term_const
     return SimResult(obs, ctrls, total)            # like the reference trajectory: last control row is zero
 
 
-def simulate(controller, init_obs, term_cond=None, dynamics=None, sim_model=None, max_steps=10000, silent=True):
-    """Returns ``SimResult(obs (T+1,nx), ctrls (T+1,nu), cost)``; ``cost`` is ``task.get_cost()(traj)``
-    (``autompc/costs/cost.py:27-41``) for the controller's QuadCost, accumulated on the device in float64."""
+def simulate(controller, init_obs, term_cond=None, dynamics=None, sim_model=None, max_steps=10000, silent=True,
+             cost=None):
+    """Returns ``SimResult(obs (T+1,nx), ctrls (T+1,nu), cost)``; ``cost`` is ``cost(traj)`` as ``Cost.__call__``
+    evaluates it (``autompc/costs/cost.py:27-41``), accumulated on the device in float64, for the ``cost`` argument
+    (engine-only; default: the controller's own task cost)."""
     _check(controller, term_cond, dynamics, sim_model)
     sim = _sim_handle(controller, sim_model)
+    _set_eval_cost(controller, cost)
     _start(controller, sim, init_obs, int(max_steps))
     return _finish(controller, int(max_steps))
 
 
-def evaluate_candidates(controllers, init_obs, max_steps, sim_model, group=None):
+def evaluate_candidates(controllers, init_obs, max_steps, sim_model, group=None, cost=None):
     """Closed-loop evaluation of independent candidate controllers (tuning/pipeline_tuner.py:213-239).
     All closed loops of this rank are in flight together (one stream per controller).  With ``group`` the
-    candidates are dealt round-robin over the ranks and the costs are gathered (list of floats, every rank)."""
+    candidates are dealt round-robin over the ranks and the costs are gathered (list of floats, every rank).
+    ``cost``: the cost object every trajectory is scored with (the tuner uses the task's, pipeline_tuner.py:230-231);
+    default: each controller's own."""
     rank, world = 0, 1
     if group is not None:
         import torch.distributed as dist
@@ -85,13 +111,17 @@ def evaluate_candidates(controllers, init_obs, max_steps, sim_model, group=None)
         if c.device not in sims:
             sims[c.device] = _sim_handle(c, sim_model)
         c.reset()                                   # pipeline_tuner.py:222
+        _set_eval_cost(c, cost)
         _start(c, sims[c.device], init_obs, T)
     results = {i: _finish(controllers[i], T) for i in mine}
     costs = [results[i].cost if i in results else 0.0 for i in range(len(controllers))]
     if group is not None:
         import torch
         import torch.distributed as dist
-        dev = torch.device("cuda", controllers[mine[0]].device) if mine else torch.device("cuda")
+        if dist.get_backend(group) == "nccl":
+            dev = torch.device("cuda", controllers[mine[0]].device) if mine else torch.device("cuda")
+        else:
+            dev = torch.device("cpu")
         t = torch.tensor(costs, dtype=torch.float64, device=dev)
         dist.all_reduce(t, group=group)             # result gather of len(controllers) scalars, not on the data path
         costs = t.cpu().tolist()

@@ -174,6 +174,9 @@ struct AmpcMppiParams {
   int world, rank;
   unsigned int seq;         // solve sequence number (> 0), identical on all ranks; selects the mailbox slot
   float *u_out;           // (nu,)
+  // threshold stage costs (thresh_cost.py): n_box terms, each [lo (nx) | hi (nx) | weight] in `box`
+  int n_box;
+  const float *box;
   // host-buffer entry point: the observation rides in the kernel parameters (no H2D copy on the stream) ...
   int x0_inline;          // != 0: use x0_val instead of x0
   float x0_val[32];       // nx <= 32 on this path

@@ -27,7 +27,7 @@ struct IlqrParams {
   AmpcMlpF64 net;
   int H, nx, nu, bounded, max_iter, ls_max_iter;
   double dt, ls_discount, ls_cost_threshold, u_threshold;
-  const double *Q, *R, *F, *goal, *umin, *umax, *alphas;   // device
+  const double *Q, *R, *F, *goal, *goalF, *umin, *umax, *alphas;   // device (goalF: goal of the terminal term)
   const double *x0, *uguess;                       // device (uguess may be null)
   // scratch / outputs (device)
   double *states, *ctrls, *Ks, *ks, *Jacs, *ls_states, *ls_ctrls, *step_cost;
@@ -63,7 +63,7 @@ __device__ __forceinline__ void step_costs(const IlqrParams &P, const double *xs
     if (i < P.H)
       c[i] = P.dt * (quad_form(P.Q, xs + (size_t)i * P.nx, P.goal, P.nx) + quad_form(P.R, us + (size_t)i * P.nu, nullptr, P.nu));
     else
-      c[i] = quad_form(P.F, xs + (size_t)P.H * P.nx, P.goal, P.nx);
+      c[i] = quad_form(P.F, xs + (size_t)P.H * P.nx, P.goalF, P.nx);
   }
 }
 
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
       const double *xs = P.ls_states + (size_t)j * (H + 1) * nx, *us = P.ls_ctrls + (size_t)j * H * nu;
       double c;
       if (i < H) c = P.dt * (quad_form(P.Q, xs + (size_t)i * nx, P.goal, nx) + quad_form(P.R, us + (size_t)i * nu, nullptr, nu));
-      else c = quad_form(P.F, xs + (size_t)H * nx, P.goal, nx);
+      else c = quad_form(P.F, xs + (size_t)H * nx, P.goalF, nx);
       P.step_cost[(H + 1) + t] = c;
     }
     __syncthreads();
@@ -385,7 +385,7 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
   const int nb = H > LS ? H : LS;   // widest MLP batch (Jacobian refresh over H steps / LS line-search rollouts)
   size_t off = 0;
   auto take = [&](size_t cnt) { size_t o = off; off += (cnt + 1) & ~(size_t)1; return o; };
-  const size_t oQ = take(nx * nx), oR = take(nu * nu), oF = take(nx * nx), og = take(nx), oumin = take(nu), oumax = take(nu), oal = take(LS);
+  const size_t oQ = take(nx * nx), oR = take(nu * nu), oF = take(nx * nx), og = take(nx), ogF = take(nx), oumin = take(nu), oumax = take(nu), oal = take(LS);
   h->o_x0 = take(nx); h->o_ug = take((size_t)H * nu);
   const size_t ost = take((size_t)(H + 1) * nx), oct = take((size_t)H * nu), oKs = take((size_t)H * nu * nx), oks = take((size_t)H * nu);
   const size_t oJ = take((size_t)H * nx * n), ols = take((size_t)LS * (H + 1) * nx), olc = take((size_t)LS * H * nu);
@@ -398,12 +398,12 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
   std::vector<double> hc(h->o_x0, 0.0);
   for (int i = 0; i < nx * nx; ++i) { hc[oQ + i] = cost->Q[i]; hc[oF + i] = cost->F[i]; }
   for (int i = 0; i < nu * nu; ++i) hc[oR + i] = cost->R[i];
-  for (int i = 0; i < nx; ++i) hc[og + i] = cost->goal[i];
+  for (int i = 0; i < nx; ++i) { hc[og + i] = cost->goal[i]; hc[ogF + i] = cost->goal_term ? cost->goal_term[i] : cost->goal[i]; }
   for (int i = 0; i < nu; ++i) { hc[oumin + i] = cost->umin[i]; hc[oumax + i] = cost->umax[i]; }
   for (int i = 0; i < LS; ++i) hc[oal + i] = pow(cfg->ls_discount, (double)i);   // ls_discount**i, ilqr.py:196
   if (e == cudaSuccess) e = cudaMemcpy(h->d_work, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice);
   double *w = h->d_work;
-  P.Q = w + oQ; P.R = w + oR; P.F = w + oF; P.goal = w + og; P.umin = w + oumin; P.umax = w + oumax; P.alphas = w + oal;
+  P.Q = w + oQ; P.R = w + oR; P.F = w + oF; P.goal = w + og; P.goalF = w + ogF; P.umin = w + oumin; P.umax = w + oumax; P.alphas = w + oal;
   P.x0 = w + h->o_x0; P.uguess = nullptr;
   P.states = w + ost; P.ctrls = w + oct; P.Ks = w + oKs; P.ks = w + oks; P.Jacs = w + oJ;
   P.ls_states = w + ols; P.ls_ctrls = w + olc; P.step_cost = w + osc;

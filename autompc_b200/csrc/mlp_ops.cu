@@ -26,6 +26,18 @@ namespace {
 
 constexpr int NT = 128;
 
+// threshold terms of a trajectory cost (thresh_cost.py:27-32, :73-77): n_box x [lo (nx) | hi (nx) | weight]
+__device__ __forceinline__ double ampc_box_cost_f64(const double *box, int n_box, int nx, const double *x) {
+  double c = 0.0;
+  for (int b = 0; b < n_box; ++b) {
+    const double *bx = box + (size_t)b * (2 * nx + 1);
+    bool out = false;
+    for (int j = 0; j < nx; ++j) out = out || (x[j] < bx[j]) || (x[j] > bx[nx + j]);
+    if (out) c += bx[2 * nx];
+  }
+  return c;
+}
+
 __global__ void __launch_bounds__(NT) pred_batch_kernel(const AmpcMlpF64 net, int batch, const double *X,
                                                         const double *U, double *Xn) {
   extern __shared__ double sm_d[];
@@ -98,7 +110,7 @@ __global__ void __launch_bounds__(NT) rollout_batch_kernel(const AmpcMlpF64 net,
 // next solve reads, the trajectory record and the running trajectory cost of Cost.__call__ (cost.py:27-41).
 __global__ void __launch_bounds__(NT) sim_step_kernel(const AmpcMlpF64 net, double *x, const float *u, float *x32,
                                                       double *obs_next, double *ctrl_t, const double *Q, const double *R,
-                                                      const double *goal, double *cost) {
+                                                      const double *goal, const double *box, int n_box, double *cost) {
   extern __shared__ double sm_d[];
   double *h0 = sm_d, *h1 = sm_d + net.max_width;
   const int nx = net.nx, nu = net.nu;
@@ -118,7 +130,7 @@ __global__ void __launch_bounds__(NT) sim_step_kernel(const AmpcMlpF64 net, doub
       for (int i = 0; i < nu; ++i) col += (double)u[i] * R[i * nu + j];
       c += col * (double)u[j];
     }
-    *cost += c;
+    *cost += c + ampc_box_cost_f64(box, n_box, nx, x);
   }
   __syncthreads();
   const double *out = ampc_mlp_f64_forward(net, h0, h1, nullptr, threadIdx.x, NT);
@@ -134,8 +146,7 @@ __global__ void __launch_bounds__(NT) sim_step_kernel(const AmpcMlpF64 net, doub
 
 // terminal part of Cost.__call__: obs cost of the last state (its control is zero) + terminal cost
 __global__ void traj_cost_final_kernel(int nx, const double *x, const double *Q, const double *F, const double *goal,
-                                       const double *goalF,
-                                       double *cost) {
+                                       const double *goalF, const double *box, int n_box, double *cost) {
   if (threadIdx.x != 0) return;
   double c = 0.0;
   for (int pass = 0; pass < 2; ++pass) {
@@ -147,7 +158,7 @@ __global__ void traj_cost_final_kernel(int nx, const double *x, const double *Q,
       c += col * (x[j] - goal_p[j]);
     }
   }
-  *cost += c;
+  *cost += c + ampc_box_cost_f64(box, n_box, nx, x);   // the last state's stage cost includes the threshold terms
 }
 
 }  // namespace
@@ -157,16 +168,18 @@ int ampc_mlp_nx(const ampc_mlp *m) { return m->net.nx; }
 int ampc_mlp_nu(const ampc_mlp *m) { return m->net.nu; }
 
 int ampc_mlp_sim_step_launch(ampc_mlp *m, double *d_x, const float *d_u, float *d_x32, double *d_obs_next, double *d_ctrl_t,
-                             const double *d_Q, const double *d_R, const double *d_goal, double *d_cost, cudaStream_t s) {
-  sim_step_kernel<<<1, NT, m->smem_pred, s>>>(m->net, d_x, d_u, d_x32, d_obs_next, d_ctrl_t, d_Q, d_R, d_goal, d_cost);
+                             const double *d_Q, const double *d_R, const double *d_goal, const double *d_box, int n_box,
+                             double *d_cost, cudaStream_t s) {
+  sim_step_kernel<<<1, NT, m->smem_pred, s>>>(m->net, d_x, d_u, d_x32, d_obs_next, d_ctrl_t, d_Q, d_R, d_goal, d_box, n_box,
+                                              d_cost);
   ampc_count_launch();
   AMPC_CUDA_CHECK(cudaGetLastError());
   return AMPC_OK;
 }
 
 int ampc_traj_cost_final_launch(int nx, const double *d_x, const double *d_Q, const double *d_F, const double *d_goal,
-                                const double *d_goalF, double *d_cost, cudaStream_t s) {
-  traj_cost_final_kernel<<<1, 32, 0, s>>>(nx, d_x, d_Q, d_F, d_goal, d_goalF, d_cost);
+                                const double *d_goalF, const double *d_box, int n_box, double *d_cost, cudaStream_t s) {
+  traj_cost_final_kernel<<<1, 32, 0, s>>>(nx, d_x, d_Q, d_F, d_goal, d_goalF, d_box, n_box, d_cost);
   ampc_count_launch();
   AMPC_CUDA_CHECK(cudaGetLastError());
   return AMPC_OK;

@@ -81,7 +81,13 @@ struct ampc_mppi {
   // device-resident closed loop
   double *d_cl = nullptr;          // [ x (nx) | cost (1) | Q | R | F | goal | goal_term | obs (T+1, nx) | ctrl (T, nu) ]
   int cl_T = 0;
-  std::vector<double> h_cost;      // Q, R, F, goal, goal_term as given at create (float64)
+  std::vector<double> h_cost;      // Q, R, F, goal, goal_term of the closed loop's trajectory cost (float64)
+  // threshold (box) cost terms
+  float *d_box = nullptr;          // rollout kernels: n_box x [lo (nx) | hi (nx) | weight], float32
+  int n_box = 0;
+  double *d_evalbox = nullptr;     // closed loop's trajectory cost: the same layout in float64
+  int n_evalbox = 0;
+  bool eval_cost_set = false;      // ampc_mppi_set_eval_cost was called: h_cost / d_evalbox no longer follow the controller's cost
 };
 
 namespace {
@@ -184,6 +190,7 @@ void free_handle(ampc_mppi *h) {
   if (h->h_eps) cudaFreeHost(h->h_eps);
   for (void *q : h->ipc_opened) cudaIpcCloseMemHandle(q);
   cudaFree(h->d_mail); cudaFree(h->d_rec); cudaFree(h->d_peer); cudaFree(h->d_cl);
+  cudaFree(h->d_box); cudaFree(h->d_evalbox);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -205,6 +212,8 @@ int launch_rollout(ampc_mppi *h, const float *dev_x0, const float *dev_eps, uint
   p.u_out = dev_u;
   p.record_out = dev_record;
   p.peer_mail = nullptr;
+  p.n_box = h->n_box;
+  p.box = h->d_box;
   if (fused) {
     p.record_out = h->d_rec;
     p.peer_mail = h->d_peer;
@@ -448,6 +457,91 @@ extern "C" int ampc_mppi_solve_host(ampc_mppi *h, const double *host_x0, const d
   return solve_host_impl(h, host_x0, host_eps, seed, counter, host_u, false);
 }
 
+namespace {
+// (n, lo, hi, weight) -> host block n x [lo (nx) | hi (nx) | weight]
+template <typename T>
+int pack_box(int nx, int32_t n_terms, const double *lo, const double *hi, const double *weight, std::vector<T> *out) {
+  AMPC_REQUIRE(n_terms >= 0 && n_terms <= AMPC_MAX_BOX_TERMS, AMPC_ERR_INVALID, "n_terms %d outside 0..%d", n_terms,
+               AMPC_MAX_BOX_TERMS);
+  AMPC_REQUIRE(n_terms == 0 || (lo && hi), AMPC_ERR_INVALID, "null box limits");
+  out->assign((size_t)n_terms * (2 * nx + 1), T(0));
+  for (int b = 0; b < n_terms; ++b) {
+    T *row = out->data() + (size_t)b * (2 * nx + 1);
+    for (int j = 0; j < nx; ++j) {
+      AMPC_REQUIRE(!isnan(lo[b * nx + j]) && !isnan(hi[b * nx + j]), AMPC_ERR_INVALID, "NaN box limit");
+      row[j] = (T)lo[b * nx + j];
+      row[nx + j] = (T)hi[b * nx + j];
+    }
+    row[2 * nx] = weight ? (T)weight[b] : T(1);
+  }
+  return AMPC_OK;
+}
+}  // namespace
+
+extern "C" int ampc_mppi_set_box_costs(ampc_mppi *h, int32_t n_terms, const double *lo, const double *hi,
+                                       const double *weight) {
+  AMPC_REQUIRE(h, AMPC_ERR_INVALID, "null handle");
+  DeviceGuard g(h->device);
+  std::vector<float> blk;
+  int rc = pack_box<float>(h->cfg.nx, n_terms, lo, hi, weight, &blk);
+  if (rc) return rc;
+  AMPC_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  cudaFree(h->d_box);
+  h->d_box = nullptr;
+  h->n_box = 0;
+  if (n_terms > 0) {
+    AMPC_CUDA_CHECK(cudaMalloc(&h->d_box, blk.size() * sizeof(float)));
+    AMPC_CUDA_CHECK(cudaMemcpy(h->d_box, blk.data(), blk.size() * sizeof(float), cudaMemcpyHostToDevice));
+    h->n_box = n_terms;
+  }
+  if (!h->eval_cost_set) {                     // the closed loop's trajectory cost defaults to the controller's cost
+    std::vector<double> blk64;
+    rc = pack_box<double>(h->cfg.nx, n_terms, lo, hi, weight, &blk64);
+    if (rc) return rc;
+    cudaFree(h->d_evalbox);
+    h->d_evalbox = nullptr;
+    h->n_evalbox = 0;
+    if (n_terms > 0) {
+      AMPC_CUDA_CHECK(cudaMalloc(&h->d_evalbox, blk64.size() * sizeof(double)));
+      AMPC_CUDA_CHECK(cudaMemcpy(h->d_evalbox, blk64.data(), blk64.size() * sizeof(double), cudaMemcpyHostToDevice));
+      h->n_evalbox = n_terms;
+    }
+  }
+  return AMPC_OK;
+}
+
+extern "C" int ampc_mppi_set_eval_cost(ampc_mppi *h, const ampc_quad_cost *quad, int32_t n_terms, const double *lo,
+                                       const double *hi, const double *weight) {
+  AMPC_REQUIRE(h, AMPC_ERR_INVALID, "null handle");
+  DeviceGuard g(h->device);
+  const int nx = h->cfg.nx, nu = h->cfg.nu;
+  std::vector<double> blk64;
+  int rc = pack_box<double>(nx, n_terms, lo, hi, weight, &blk64);
+  if (rc) return rc;
+  AMPC_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  std::vector<double> hc((size_t)2 * nx * nx + (size_t)nu * nu + 2 * (size_t)nx, 0.0);
+  if (quad) {
+    AMPC_REQUIRE(quad->Q && quad->R && quad->F && quad->goal, AMPC_ERR_INVALID, "null cost matrix");
+    double *q = hc.data();
+    memcpy(q, quad->Q, sizeof(double) * nx * nx); q += nx * nx;
+    memcpy(q, quad->R, sizeof(double) * nu * nu); q += nu * nu;
+    memcpy(q, quad->F, sizeof(double) * nx * nx); q += nx * nx;
+    memcpy(q, quad->goal, sizeof(double) * nx); q += nx;
+    memcpy(q, quad->goal_term ? quad->goal_term : quad->goal, sizeof(double) * nx);
+  }
+  h->h_cost = hc;
+  h->eval_cost_set = true;
+  cudaFree(h->d_evalbox);
+  h->d_evalbox = nullptr;
+  h->n_evalbox = 0;
+  if (n_terms > 0) {
+    AMPC_CUDA_CHECK(cudaMalloc(&h->d_evalbox, blk64.size() * sizeof(double)));
+    AMPC_CUDA_CHECK(cudaMemcpy(h->d_evalbox, blk64.data(), blk64.size() * sizeof(double), cudaMemcpyHostToDevice));
+    h->n_evalbox = n_terms;
+  }
+  return AMPC_OK;
+}
+
 extern "C" int ampc_mppi_get_costs(ampc_mppi *h, double *host_costs, double *term_const) {
   AMPC_REQUIRE(h && host_costs, AMPC_ERR_INVALID, "null argument");
   DeviceGuard g(h->device);
@@ -606,10 +700,10 @@ int ampc_mlp_device(const ampc_mlp *m);
 int ampc_mlp_nx(const ampc_mlp *m);
 int ampc_mlp_nu(const ampc_mlp *m);
 int ampc_mlp_sim_step_launch(ampc_mlp *m, double *d_x, const float *d_u, float *d_x32, double *d_obs_next, double *d_ctrl_t,
-                             const double *d_Q, const double *d_R, const double *d_goal, double *d_cost, cudaStream_t s);
+                             const double *d_Q, const double *d_R, const double *d_goal, const double *d_box, int n_box,
+                             double *d_cost, cudaStream_t s);
 int ampc_traj_cost_final_launch(int nx, const double *d_x, const double *d_Q, const double *d_F, const double *d_goal,
-                                const double *d_goalF,
-                                double *d_cost, cudaStream_t s);
+                                const double *d_goalF, const double *d_box, int n_box, double *d_cost, cudaStream_t s);
 
 extern "C" int ampc_mppi_closed_loop_start(ampc_mppi *h, ampc_mlp *sim, const double *x0, int32_t T, uint64_t seed,
                                            uint64_t counter0) {
@@ -643,10 +737,10 @@ extern "C" int ampc_mppi_closed_loop_start(ampc_mppi *h, ampc_mlp *sim, const do
     int rc = launch_rollout(h, h->d_x0, nullptr, seed, counter0 + (uint64_t)t, h->d_u, nullptr, h->stream);
     if (rc) return rc;
     rc = ampc_mlp_sim_step_launch(sim, d_x, h->d_u, h->d_x0, d_obs + (size_t)(t + 1) * nx, d_ctrl + (size_t)t * nu, d_Q,
-                                  d_R, d_goal, d_cost, h->stream);
+                                  d_R, d_goal, h->d_evalbox, h->n_evalbox, d_cost, h->stream);
     if (rc) return rc;
   }
-  return ampc_traj_cost_final_launch(nx, d_x, d_Q, d_F, d_goal, d_goalF, d_cost, h->stream);
+  return ampc_traj_cost_final_launch(nx, d_x, d_Q, d_F, d_goal, d_goalF, h->d_evalbox, h->n_evalbox, d_cost, h->stream);
 }
 
 extern "C" int ampc_mppi_closed_loop_finish(ampc_mppi *h, int32_t T, double *obs_out, double *ctrl_out, double *cost_out) {

@@ -181,6 +181,15 @@ __global__ void __launch_bounds__(NTHR) mppi_rollout_fp32_kernel(const AmpcMppiP
     // ---- stage cost at the pre-step state (mppi.py:142; cost.py:79-81, :131-132) + z-score (mlp.py:20-24)
     cost_acc += quad_rows(c_Q, s_x, c_goal, nx, p.q_diag, warp, lane);
     cost_acc += quad_rows(c_R, s_u, nullptr, nu, p.r_diag, warp, lane);
+    for (int b = warp; b < p.n_box; b += NWARP) {          // threshold terms (thresh_cost.py:27-32, :73-77)
+      const float *bx = p.box + (size_t)b * (2 * nx + 1);
+      bool out = false;
+      for (int j = 0; j < nx; ++j) {
+        const float x = s_x[j * BM + lane];
+        out = out || (x < __ldg(bx + j)) || (x > __ldg(bx + nx + j));
+      }
+      if (out) cost_acc += __ldg(bx + 2 * nx);
+    }
     for (int j = warp; j < nx + nu; j += NWARP) {
       const float v = (j < nx) ? s_x[j * BM + lane] : s_u[(j - nx) * BM + lane];
       s_h0[j * BM + lane] = (v - c_mean[j]) * c_inv[j];

@@ -674,6 +674,18 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
           } else {                                      // stage cost (x_i - g)^T Q (x_i - g), x_i = z * std + mean   (mppi.py:142)
             asm volatile("bar.sync %0, %1;" ::"n"(BAR_X), "n"(NEPI) : "memory");
             trace(i, 0xB1);                             // state copy visible
+            if (p.n_box > 0) {                          // threshold terms (thresh_cost.py:27-32, :73-77), x = z * std + mean
+              for (int b = 0; b < p.n_box; ++b) {
+                const float *bx = p.box + (size_t)b * (2 * nx + 1);
+                bool out = false;
+                for (int j = 0; j < nx; ++j) {
+                  const float2 xc = s_xc[j];
+                  const float x = fmaf(s_x[j * TM + t], xc.x, xc.y);
+                  out = out || (x < __ldg(bx + j)) || (x > __ldg(bx + nx + j));
+                }
+                if (out) cost_acc += __ldg(bx + 2 * nx);
+              }
+            }
             if (p.q_diag) {
               float c = 0.f;
 #pragma unroll 8

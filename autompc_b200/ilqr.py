@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _abi
 from .mlp import MLPWeights
-from .mppi import _quad_cost_of
+from .mppi import cost_spec_of
 from .plugin import Controller, ControllerFactory
 
 
@@ -43,15 +43,15 @@ class IterativeLQR(Controller):
         self.weights = MLPWeights.from_model(model)
         nx, nu = self.weights.nx, self.weights.nu
         self._mlp_holder = _abi.MlpDescHolder(self.weights)
-        cost = task.get_cost()
-        try:
-            Q, R, F = cost.get_cost_matrices()
-            goal = cost.get_goal()
-        except Exception as e:
-            raise ValueError("the B200 iLQR engine supports quadratic costs only (QuadCost): %s" % e)
         lo = self.ubounds[0] if self.ubounds is not None else np.full(nu, -np.inf)
         hi = self.ubounds[1] if self.ubounds is not None else np.full(nu, np.inf)
-        self._cost_holder = _abi.QuadCostHolder(Q, R, F, goal, lo, hi, nx, nu)
+        # QuadCost, or a SumCost of quadratics folded into one (their gradients / Hessians add up to the folded
+        # quadratic's; the terminal ones ignore the goals altogether, cost.py:194-211).  Threshold costs are not
+        # differentiable (thresh_cost.py:22-25): iLQR refuses them like the reference's eval_*_diff would.
+        spec = cost_spec_of(task.get_cost(), np.stack([lo, hi], axis=1), nx, nu)
+        if spec.n_box or not spec.quad:
+            raise ValueError("IterativeLQR needs a twice-differentiable cost (QuadCost or a SumCost of them)")
+        self._cost_holder = spec.holder
         cfg = _abi.IlqrCfg(self.horizon, nx, nu, float(self.dt), 1 if self.ubounds is not None else 0,
                            self.max_iter, int(ls_max_iter), float(ls_discount), float(ls_cost_threshold),
                            float(u_threshold), self.device)

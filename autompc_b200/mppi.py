@@ -66,29 +66,73 @@ def fold_quadratic_terms(terms):
     return M, g, const
 
 
-def _quad_cost_of(task, nx, nu):
-    """Reads the task's cost as ONE quadratic (Q, R, F, goal [, terminal goal]) plus constants.
+def box_of_threshold_cost(term, nx):
+    """(lo, hi) of the box whose complement a reference threshold cost charges 1 for, or None if `term` is not one.
+    ``ThresholdCost`` (autompc/costs/thresh_cost.py:8-32): ||x - goal||_inf > threshold over obs_range, i.e. outside
+    goal -+ threshold on those dimensions;  ``BoxThresholdCost`` (:40-77): outside ``limits``."""
+    if hasattr(term, "_limits"):
+        lim = np.asarray(term._limits, dtype=np.float64).reshape(nx, 2)
+        return lim[:, 0].copy(), lim[:, 1].copy()
+    if hasattr(term, "_threshold") and hasattr(term, "_obs_range"):
+        goal = np.asarray(term._goal, dtype=np.float64).reshape(nx)
+        thr = float(np.asarray(term._threshold))
+        lo, hi = np.full(nx, -np.inf), np.full(nx, np.inf)
+        a, b = int(term._obs_range[0]), int(term._obs_range[1])
+        lo[a:b], hi[a:b] = goal[a:b] - thr, goal[a:b] + thr
+        return lo, hi
+    return None
+
+
+class CostSpec:
+    """A task cost as the engine sees it: ONE quadratic (Q, R, F, goal [, terminal goal]) plus constants common to
+    all samples, plus threshold (box) terms.  ``quad`` is False when the cost has no quadratic term at all."""
+
+    def __init__(self, holder, stage_const, term_const, box_lo, box_hi, box_w, quad):
+        self.holder, self.stage_const, self.term_const = holder, stage_const, term_const
+        self.box_lo, self.box_hi, self.box_w, self.quad = box_lo, box_hi, box_w, quad
+
+    @property
+    def n_box(self):
+        return len(self.box_w)
+
+
+def cost_spec_of(cost, bounds, nx, nu):
+    """Reads a reference cost object:
 
     * a ``QuadCost`` (autompc/costs/quad_cost.py:7-51) is taken as is;
-    * a ``SumCost`` (autompc/costs/sum_cost.py:9-81) of quadratic terms -- e.g. ``QuadCostFactory + GaussRegFactory``,
-      whose goals differ so that the reference evaluates the sum term by term -- is folded
+    * ``ThresholdCost`` / ``BoxThresholdCost`` (autompc/costs/thresh_cost.py) become box terms evaluated per step by the
+      kernels (``ampc_mppi_set_box_costs``);
+    * a ``SumCost`` (autompc/costs/sum_cost.py:9-81) of such terms -- e.g. ``QuadCostFactory + GaussRegFactory``, whose
+      goals differ so that the reference evaluates the sum term by term -- has its quadratic terms folded
       (``fold_quadratic_terms``): the engine's kernels see one quadratic, the constants ride along on the host
       (they are common to all samples, i.e. they cancel in the MPPI weights, mppi.py:115-116).
-    Returns (holder, stage_const, term_const)."""
-    cost = task.get_cost()
-    bounds = np.asarray(task.get_ctrl_bounds(), dtype=np.float64)
+    Anything else raises ValueError (no CPU fallback for arbitrary Python costs)."""
     terms = list(cost.costs) if hasattr(cost, "costs") else [cost]
-    try:
-        parts = [(t.get_cost_matrices(), np.asarray(t.get_goal(), dtype=np.float64)) for t in terms]
-    except Exception as e:
-        raise ValueError("the B200 MPPI engine supports quadratic costs only (QuadCost, or a SumCost of them): %s" % e)
+    parts, lo, hi, w = [], [], [], []
+    for t in terms:
+        box = box_of_threshold_cost(t, nx)
+        if box is not None:
+            lo.append(box[0]); hi.append(box[1]); w.append(1.0)
+            continue
+        try:
+            parts.append((t.get_cost_matrices(), np.asarray(t.get_goal(), dtype=np.float64)))
+        except Exception as e:
+            raise ValueError("the B200 engine supports QuadCost, ThresholdCost, BoxThresholdCost and SumCosts of "
+                             "them: %s (%s)" % (type(t).__name__, e))
+    bounds = np.asarray(bounds, dtype=np.float64)
+    box = (np.array(lo).reshape(len(w), nx), np.array(hi).reshape(len(w), nx), np.array(w))
+    if not parts:
+        z = np.zeros
+        return CostSpec(_abi.QuadCostHolder(z((nx, nx)), z((nu, nu)), z((nx, nx)), z(nx), bounds[:, 0], bounds[:, 1], nx, nu),
+                        0.0, 0.0, *box, quad=False)
     if len(parts) == 1:
         (Q, R, F), goal = parts[0]
-        return _abi.QuadCostHolder(Q, R, F, goal, bounds[:, 0], bounds[:, 1], nx, nu), 0.0, 0.0
+        return CostSpec(_abi.QuadCostHolder(Q, R, F, goal, bounds[:, 0], bounds[:, 1], nx, nu), 0.0, 0.0, *box, quad=True)
     Q, g, c_stage = fold_quadratic_terms([(np.asarray(m[0], dtype=np.float64), gl) for m, gl in parts])
     F, gF, c_term = fold_quadratic_terms([(np.asarray(m[2], dtype=np.float64), gl) for m, gl in parts])
     R = sum(np.asarray(m[1], dtype=np.float64) for m, _ in parts)
-    return _abi.QuadCostHolder(Q, R, F, g, bounds[:, 0], bounds[:, 1], nx, nu, goal_term=gF), c_stage, c_term
+    return CostSpec(_abi.QuadCostHolder(Q, R, F, g, bounds[:, 0], bounds[:, 1], nx, nu, goal_term=gF), c_stage, c_term,
+                    *box, quad=True)
 
 
 class MPPI(Controller):
@@ -132,7 +176,9 @@ class MPPI(Controller):
         # --- engine handle
         self._mlp_holder = _abi.MlpDescHolder(self.weights)
         self._host_io = None
-        self._cost_holder, self._stage_const, self._term_const = _quad_cost_of(task, nx, nu)
+        self._cost = cost_spec_of(task.get_cost(), task.get_ctrl_bounds(), nx, nu)
+        self._cost_holder, self._stage_const, self._term_const = (self._cost.holder, self._cost.stage_const,
+                                                                  self._cost.term_const)
         lib = _abi.lib()
         self._h = None
         order = {"auto": ["fp16", "bf16", "fp32"], "fp32": ["fp32"], "bf16": ["bf16"], "fp16": ["fp16"]}.get(precision)
@@ -154,6 +200,9 @@ class MPPI(Controller):
                 _abi.check(rc)
         if self._h is None:
             _abi.check(err)
+        if self._cost.n_box:                                               # thresh_cost.py terms -> per-step predicates
+            _abi.check(lib.ampc_mppi_set_box_costs(self._h, self._cost.n_box, _abi.dptr(self._cost.box_lo),
+                                                   _abi.dptr(self._cost.box_hi), _abi.dptr(self._cost.box_w)))
         self._dev_bufs = None
         if self.world > 1 and self.exchange == "nvlink":
             self._connect_peers()

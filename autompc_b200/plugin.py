@@ -12,6 +12,7 @@ behaviour are defined so the same host code runs:
 * ``Task`` (cost + control bounds only)   <- ``autompc/tasks/task.py:5-267``
 * ``QuadCost``                            <- ``autompc/costs/quad_cost.py:7-51``, ``cost.py:43-64``
 * ``SumCost`` (``+`` of costs)            <- ``autompc/costs/sum_cost.py:9-137``, ``cost.py:213-220``
+* ``ThresholdCost`` / ``BoxThresholdCost`` <- ``autompc/costs/thresh_cost.py:8-83``
 """
 from abc import ABC, abstractmethod
 
@@ -97,6 +98,64 @@ except Exception:  # pragma: no cover - exercised on boxes without the reference
         @property
         def is_diff(self):
             return not getattr(self, "pred_diff") is None
+
+
+try:
+    from autompc.costs.thresh_cost import ThresholdCost, BoxThresholdCost  # type: ignore
+except Exception:  # pragma: no cover
+
+    class _ThreshBase:
+        def eval_ctrl_cost(self, ctrl):                  # thresh_cost.py:33-34, :78-79
+            return 0.0
+
+        def eval_term_obs_cost(self, obs):               # thresh_cost.py:36-37, :81-82
+            return 0.0
+
+        def get_cost_matrices(self):                     # cost.py:43-51
+            raise ValueError("Cost is not quadratic.")
+
+        def __add__(self, other):                        # cost.py:213-220
+            more = other.costs if isinstance(other, SumCost) else [other]
+            return SumCost(self.system, [self, *more])
+
+        def __call__(self, traj):                        # cost.py:27-41
+            c = 0.0
+            for i in range(len(traj)):
+                c += self.eval_obs_cost(traj[i].obs) + self.eval_ctrl_cost(traj[i].ctrl)
+            return c + self.eval_term_obs_cost(traj[-1].obs)
+
+    class ThresholdCost(_ThreshBase):
+        """1 per step where ||x - goal||_inf > threshold over obs_range (thresh_cost.py:8-32)."""
+
+        def __init__(self, system, goal, obs_range, threshold):
+            self.system = system
+            self._goal, self._threshold, self._obs_range = np.copy(goal), np.copy(threshold), obs_range[:]
+            self.is_quad, self.has_goal = False, True
+
+        def get_goal(self):
+            return np.copy(self._goal)
+
+        def eval_obs_cost(self, obs):
+            a, b = self._obs_range[0], self._obs_range[1]
+            return 1.0 if np.linalg.norm(obs[a:b] - self._goal[a:b], np.inf) > self._threshold else 0.0
+
+    class BoxThresholdCost(_ThreshBase):
+        """1 per step where the observation is outside of limits (obs_dim, 2) (thresh_cost.py:40-77)."""
+
+        def __init__(self, system, limits, goal=None):
+            self.system = system
+            self._limits = np.copy(limits)
+            self.is_quad, self.has_goal = False, goal is not None
+            if goal is not None:
+                self._goal = np.copy(goal)
+
+        def get_goal(self):
+            if not self.has_goal:
+                raise ValueError("Cost does not have goal")
+            return np.copy(self._goal)
+
+        def eval_obs_cost(self, obs):
+            return 1.0 if ((obs < self._limits[:, 0]).any() or (obs > self._limits[:, 1]).any()) else 0.0
 
 
 try:

@@ -124,6 +124,16 @@ int ampc_mppi_solve_host(ampc_mppi *h, const double *host_x0, const double *host
 int ampc_mppi_solve(ampc_mppi *h, const float *dev_x0, const float *dev_eps, uint64_t seed,
                     uint64_t counter, float *dev_u, void *stream);
 
+/* Threshold stage costs -- autompc.costs.thresh_cost.ThresholdCost (autompc/costs/thresh_cost.py:8-38) and
+ * BoxThresholdCost (:40-83), alone or as terms of a SumCost next to the quadratic (autompc/costs/sum_cost.py:49-81).
+ * Term b adds weight[b] (1.0 in the reference) to a sample's cost at every horizon step whose PRE-step state x
+ * (mppi.py:142) leaves the box: x[j] < lo[b][j] or x[j] > hi[b][j] for some j (+-inf = unbounded).
+ * ThresholdCost(goal, obs_range, threshold) is the box goal[j] -+ threshold on j in obs_range.  No control or
+ * terminal part (thresh_cost.py:33-38, :78-83).  lo, hi: (n_terms, nx) HOST float64; n_terms <= AMPC_MAX_BOX_TERMS;
+ * n_terms = 0 removes them.  Call after create(), before the next solve.                                         */
+#define AMPC_MAX_BOX_TERMS 8
+int ampc_mppi_set_box_costs(ampc_mppi *h, int32_t n_terms, const double *lo, const double *hi, const double *weight);
+
 /* Parity taps (synchronous).  costs: (K,) what do_rollouts returns (mppi.py:152)
  * WITHOUT the terminal_mode-0 scalar, which is returned separately.            */
 int ampc_mppi_get_costs(ampc_mppi *h, double *host_costs, double *term_const);
@@ -189,6 +199,13 @@ int ampc_mlp_pred_diff_batch(ampc_mlp *m, int32_t batch, const double *X, const 
  * counters counter0 .. counter0+T-1.                                                                        */
 int ampc_mppi_closed_loop_start(ampc_mppi *h, ampc_mlp *sim, const double *x0, int32_t T, uint64_t seed,
                                 uint64_t counter0);
+/* The cost the closed loop accumulates over the trajectory (Cost.__call__, cost.py:27-41) defaults to the
+ * controller's own.  The tuner scores a candidate with the TASK's cost instead, which differs from the cost the
+ * controller optimises (tuning/pipeline_tuner.py:230-231; e.g. the cartpole benchmark's ThresholdCost,
+ * benchmarks/cartpole.py:38-60): set_eval_cost replaces it by quad (NULL = no quadratic part; umin/umax ignored)
+ * plus n_terms box terms as in ampc_mppi_set_box_costs.                                                       */
+int ampc_mppi_set_eval_cost(ampc_mppi *h, const ampc_quad_cost *quad, int32_t n_terms, const double *lo,
+                            const double *hi, const double *weight);
 int ampc_mppi_closed_loop_finish(ampc_mppi *h, int32_t T, double *obs_out, double *ctrl_out, double *cost_out);
 
 /* ------------------------------------------------------------------ iLQR --- */

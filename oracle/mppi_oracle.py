@@ -13,6 +13,10 @@ What is restated, with the reference lines each function follows
   ``:166-183`` for a ``QuadCost`` (``autompc/costs/quad_cost.py:7-51``).
 * ``SumQuadCostParams`` <- ``autompc/costs/sum_cost.py:9-81``;  ``model_rmse`` <-
   ``autompc/evaluation/model_metrics.py:12-43``.
+* ``ThresholdCostParams`` / ``BoxThresholdCostParams`` <- ``autompc/costs/thresh_cost.py:8-83``;
+  ``traj_cost`` <- ``Cost.__call__`` (``autompc/costs/cost.py:27-41``).
+* ``linear_pred_batch`` <- ``autompc/sysid/arx.py:151-154`` == ``autompc/sysid/koopman.py:170-173``;
+  ``nmpc_constraint`` / ``nmpc_jacobian`` <- ``autompc/control/nmpc.py:102-110``, ``:148-187``.
 * ``MPPIOracle`` <- ``autompc/control/mppi.py:66-181``: ctor draw ``:97-99``,
   ``do_rollouts`` ``:120-152``, ``update`` ``:110-118``, ``run`` ``:154-168``.
 
@@ -203,6 +207,98 @@ class SumQuadCostParams:
 
     def ctrl_cost_batch(self, U):
         return sum(t.ctrl_cost_batch(U) for t in self.terms)
+
+
+class ThresholdCostParams:
+    """``ThresholdCost`` (autompc/costs/thresh_cost.py:8-38): 1 per step where
+    ``||obs[a:b] - goal[a:b]||_inf > threshold``; no control or terminal part."""
+
+    def __init__(self, goal, obs_range, threshold):
+        self.goal = np.array(goal, dtype=np.float64)
+        self.obs_range = (int(obs_range[0]), int(obs_range[1]))
+        self.threshold = float(threshold)
+
+    def eval_obs_cost(self, obs):                        # thresh_cost.py:27-32
+        a, b = self.obs_range
+        return 1.0 if np.linalg.norm(obs[a:b] - self.goal[a:b], np.inf) > self.threshold else 0.0
+
+    def eval_ctrl_cost(self, ctrl):                      # thresh_cost.py:33-34
+        return 0.0
+
+    def eval_term_obs_cost(self, obs):                   # thresh_cost.py:36-37
+        return 0.0
+
+    def obs_cost_batch(self, X):
+        a, b = self.obs_range
+        return (np.abs(X[:, a:b] - self.goal[a:b]).max(axis=1) > self.threshold).astype(np.float64)
+
+    def ctrl_cost_batch(self, U):
+        return np.zeros(U.shape[0])
+
+
+class BoxThresholdCostParams:
+    """``BoxThresholdCost`` (autompc/costs/thresh_cost.py:40-83): 1 per step where the observation is outside
+    ``limits`` (obs_dim, 2); no control or terminal part."""
+
+    def __init__(self, limits):
+        self.limits = np.array(limits, dtype=np.float64)
+
+    def eval_obs_cost(self, obs):                        # thresh_cost.py:73-77
+        return 1.0 if ((obs < self.limits[:, 0]).any() or (obs > self.limits[:, 1]).any()) else 0.0
+
+    def eval_ctrl_cost(self, ctrl):
+        return 0.0
+
+    def eval_term_obs_cost(self, obs):
+        return 0.0
+
+    def obs_cost_batch(self, X):
+        return ((X < self.limits[:, 0]).any(axis=1) | (X > self.limits[:, 1]).any(axis=1)).astype(np.float64)
+
+    def ctrl_cost_batch(self, U):
+        return np.zeros(U.shape[0])
+
+
+def traj_cost(cost, obs, ctrls):
+    """``Cost.__call__`` (autompc/costs/cost.py:27-41): obs (T+1,nx), ctrls (T+1,nu) as a reference Trajectory holds
+    them (the last control row is whatever the trajectory holds -- zeros after ``simulate``)."""
+    c = 0.0
+    for i in range(obs.shape[0]):
+        c += cost.eval_obs_cost(obs[i])
+        c += cost.eval_ctrl_cost(ctrls[i])
+    return c + cost.eval_term_obs_cost(obs[-1])
+
+
+def linear_pred_batch(A, B, states, ctrls):
+    """ARX / Koopman ``pred_batch`` (autompc/sysid/arx.py:151-154, koopman.py:170-173)."""
+    return (A @ states.T + B @ ctrls.T).T
+
+
+def nmpc_constraint(p, H, x):
+    """``NonLinearMPCProblem.get_constraint`` (autompc/control/nmpc.py:102-110) for an MLP model: decision vector
+    x = [states (H+1, nx) | ctrls (H, nu)], c[i] = -state[i+1] + pred(state[i], ctrl[i])."""
+    nx, nu = p.nx, p.nu
+    st = x[:(H + 1) * nx].reshape(H + 1, nx)
+    ct = x[(H + 1) * nx:].reshape(H, nu)
+    return (-st[1:] + mlp_pred_batch(p, st[:H], ct)).reshape(-1)
+
+
+def nmpc_jacobian(p, H, x):
+    """``NonLinearMPCProblem.get_jacobian`` (autompc/control/nmpc.py:148-187): (rows, cols, values) in the
+    reference's order: per step the dense state Jacobian, the dense control Jacobian, then -1 on x_{i+1}."""
+    nx, nu = p.nx, p.nu
+    st = x[:(H + 1) * nx].reshape(H + 1, nx)
+    ct = x[(H + 1) * nx:].reshape(H, nu)
+    _, Jx, Ju = mlp_pred_diff_batch(p, st[:H], ct)
+    rows, cols, vals = [], [], []
+    base_u = nx * (H + 1)
+    for i in range(H):
+        r, c = np.meshgrid(np.arange(nx), np.arange(nx), indexing="ij")
+        rows.append(i * nx + r.ravel()); cols.append(i * nx + c.ravel()); vals.append(Jx[i].ravel())
+        r, c = np.meshgrid(np.arange(nx), np.arange(nu), indexing="ij")
+        rows.append(i * nx + r.ravel()); cols.append(base_u + i * nu + c.ravel()); vals.append(Ju[i].ravel())
+        rows.append(i * nx + np.arange(nx)); cols.append((i + 1) * nx + np.arange(nx)); vals.append(-np.ones(nx))
+    return np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
 
 
 def model_rmse(p, obs_list, ctrl_list, horizon=1):

@@ -1,0 +1,138 @@
+"""GPU parity for SURVEY.md 8(f) row 2, second half: ThresholdCost / BoxThresholdCost (autompc/costs/thresh_cost.py)
+as per-step predicates inside both rollout kernels and inside the closed loop's trajectory cost.
+
+Checker: fixtures recorded from the UNMODIFIED reference MPPI (oracle/make_golden_r2.py) and the oracle's
+``traj_cost`` (pinned to the reference's ``Cost.__call__`` in tests/test_oracle_golden_r2.py).
+
+A threshold term is an indicator: a sample whose state lies within the arithmetic's rounding of a box limit may be
+counted on the other side (the state is float32 on the device, float64 in the reference).  The tests therefore allow a
+stated small fraction of samples to differ by (near-)integer amounts and hold all others to the usual tolerance.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.mppi_oracle import (BoxThresholdCostParams, QuadCostParams, SumQuadCostParams, ThresholdCostParams,
+                                traj_cost)
+from tests.helpers import GOLDEN, load_cartpole
+
+pytestmark = pytest.mark.gpu
+
+COST_RTOL = {"fp32": 2e-5, "fp16": 1e-3, "bf16": 6e-3}      # of the cost scale, on cost differences (unstable cartpole model)
+ACT_ATOL = {"fp32": 2e-3, "fp16": 1e-2, "bf16": 5e-2}
+MAX_FLIP_FRAC = {"fp32": 0.005, "fp16": 0.03, "bf16": 0.10}
+
+
+def _problem(z, kind):
+    from autompc_b200 import B200MLP
+    from autompc_b200.plugin import BoxThresholdCost, QuadCost, System, Task, ThresholdCost
+    from tests.gpu_helpers import weights_of
+    mlp, _, umin, umax, _, _ = load_cartpole()
+    system = System(["theta", "omega", "x", "dx"], ["u"])
+    system.dt = 0.05
+    task = Task(system)
+    task.set_ctrl_bounds(np.asarray(umin, dtype=np.float64), np.asarray(umax, dtype=np.float64))
+    thr = ThresholdCost(system, z["thr_goal"], [int(v) for v in z["thr_range"]], float(z["thr_threshold"]))
+    if kind == "sum":
+        cost = QuadCost(system, z["Q"], z["R"], z["F"], goal=np.zeros(4)) + thr + BoxThresholdCost(system, z["box_limits"])
+    else:
+        cost = thr
+    task.set_cost(cost)
+    return system, task, B200MLP(system, weights_of(mlp))
+
+
+@pytest.mark.parametrize("name,kind", [("mppi_cartpole_thresh_K256_H20", "sum"),
+                                       ("mppi_cartpole_threshonly_K128_H15", "lone")])
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
+def test_mppi_threshold_costs_match_unmodified_reference(name, kind, precision):
+    from autompc_b200 import MPPI
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    system, task, model = _problem(z, kind)
+    np.random.seed(int(z["seed"]))
+    ctl = MPPI(system, task, model, horizon=int(z["H"]), num_path=int(z["K"]), sigma=float(z["sigma"]),
+               lmda=float(z["lmda"]), noise="numpy", precision=precision)
+    assert ctl.precision == precision
+    np.testing.assert_allclose(ctl.act_sequence, z["act0"], rtol=0, atol=1e-7)
+    constate = np.zeros(5)
+    for s in range(int(z["n_steps"])):
+        if s > 0:
+            ctl.act_sequence = z["act_%d" % (s - 1)]
+        u, constate = ctl.run(constate, z["x0_%d" % s])
+        costs, term = ctl.last_costs()
+        ref = z["costs_%d" % s]
+        scale = max(np.abs(ref).max(), 1.0)
+        d = (costs - costs.min()) - (ref - ref.min())
+        off = np.abs(d) > COST_RTOL[precision] * scale
+        # samples counted on the other side of a limit differ by ~ +-1, +-2, ...: few, and (near-)integers
+        assert off.mean() <= MAX_FLIP_FRAC[precision], "%.3f of the samples differ" % off.mean()
+        if precision == "fp32" and off.any():
+            assert np.all(np.abs(d[off] - np.round(d[off])) < 0.05)
+        if not off.any():
+            assert int(np.argmin(costs)) == int(z["argmin_%d" % s])
+            np.testing.assert_allclose(ctl.act_sequence, z["act_%d" % s], rtol=0, atol=ACT_ATOL[precision])
+            np.testing.assert_allclose(u, z["u_%d" % s], rtol=0, atol=ACT_ATOL[precision] * 20.0)
+    ctl.close()
+
+
+def test_threshold_terms_are_counted_per_step():
+    """One sample-level identity that holds in every arithmetic: with Q = R = F = 0 and lmda/sigma -> the action cost
+    only, cost(threshold task) - cost(zero-cost task) is an integer in [0, H] for every sample."""
+    from autompc_b200 import MPPI, B200MLP
+    from autompc_b200.plugin import BoxThresholdCost, QuadCost, System, Task
+    from tests.gpu_helpers import weights_of
+    mlp, _, umin, umax, _, _ = load_cartpole()
+    system = System(["theta", "omega", "x", "dx"], ["u"])
+    system.dt = 0.05
+    model = B200MLP(system, weights_of(mlp))
+    z4, z1 = np.zeros((4, 4)), np.zeros((1, 1))
+    lim = np.array([[-0.3, 0.3], [-np.inf, np.inf], [-np.inf, 0.05], [-np.inf, np.inf]])
+    x0 = np.array([0.2, 0.1, 0.0, 0.0])
+    out = {}
+    for kind in ("zero", "box"):
+        task = Task(system)
+        task.set_ctrl_bounds(np.asarray(umin, dtype=np.float64), np.asarray(umax, dtype=np.float64))
+        cost = QuadCost(system, z4, z1, z4, goal=np.zeros(4))
+        task.set_cost(cost + BoxThresholdCost(system, lim) if kind == "box" else cost)
+        np.random.seed(5)
+        ctl = MPPI(system, task, model, horizon=12, num_path=700, seed=3, precision="fp32")
+        ctl.solve(x0)
+        out[kind] = ctl.last_costs()[0]
+        ctl.close()
+    d = out["box"] - out["zero"]
+    assert np.all(np.abs(d - np.round(d)) < 1e-3) and d.min() >= -1e-3 and d.max() <= 12 + 1e-3 and d.max() >= 1
+
+
+def test_closed_loop_eval_cost_with_threshold_terms():
+    """The tuner scores a candidate with the TASK's cost (pipeline_tuner.py:230-231), e.g. the cartpole benchmark's
+    ThresholdCost: ``simulate(..., cost=)`` accumulates Cost.__call__ (cost.py:27-41) of that cost on the device; it
+    must equal the oracle's value on the very trajectory the closed loop returns (integers: exactly)."""
+    from autompc_b200 import MPPI, simulate
+    from autompc_b200.plugin import BoxThresholdCost, QuadCost, ThresholdCost
+    zc = np.load(os.path.join(GOLDEN, "cost_call_thresh.npz"))
+    z = {k: zc[k] for k in zc.files}
+    system, task, model = _problem(z, "lone")
+    # the controller optimises a quadratic; the score is something else
+    task.set_cost(QuadCost(system, z["Q"], z["R"], z["F"], goal=np.zeros(4)))
+    np.random.seed(1)
+    ctl = MPPI(system, task, model, horizon=15, num_path=512, seed=4, precision="fp32")
+    x0 = np.array([0.6, 0.0, 0.0, 0.0])
+    thr = ThresholdCost(system, z["thr_goal"], [int(v) for v in z["thr_range"]], float(z["thr_threshold"]))
+    box = BoxThresholdCost(system, z["box_limits"])
+    quad2 = QuadCost(system, np.diag([1.0, 2.0, 3.0, 4.0]), np.diag([0.5]), np.diag([4.0, 3.0, 2.0, 1.0]), goal=np.full(4, 0.1))
+    o_thr = ThresholdCostParams(z["thr_goal"], z["thr_range"], float(z["thr_threshold"]))
+    o_box = BoxThresholdCostParams(z["box_limits"])
+    o_quad2 = QuadCostParams(np.diag([1.0, 2.0, 3.0, 4.0]), np.diag([0.5]), np.diag([4.0, 3.0, 2.0, 1.0]), np.full(4, 0.1))
+    own = QuadCostParams(z["Q"], z["R"], z["F"], np.zeros(4))
+    T = 25
+    for cost, ocost, exact in [(thr, o_thr, True), (box, o_box, True), (thr + box, SumQuadCostParams([o_thr, o_box]), True),
+                               (quad2 + thr, SumQuadCostParams([o_quad2, o_thr]), False), (None, own, False)]:
+        np.random.seed(1)
+        ctl.reset()
+        r = simulate(ctl, x0, sim_model=model, max_steps=T, cost=cost)
+        want = traj_cost(ocost, r.obs, r.ctrls)
+        if exact:
+            assert r.cost == want and 0 < want <= T + 1
+        else:
+            np.testing.assert_allclose(r.cost, want, rtol=1e-12)
+    ctl.close()
