@@ -9,6 +9,8 @@ from .mppi import MPPI, MPPIFactory  # noqa: F401
 from .ilqr import IterativeLQR, IterativeLQRFactory  # noqa: F401
 from .closed_loop import simulate, evaluate_candidates  # noqa: F401
 from .evaluation import get_model_rmse  # noqa: F401
+from .linear import B200Linear  # noqa: F401
+from .nmpc import NonLinearMPCProblem  # noqa: F401
 
 __all__ = ["MPPI", "MPPIFactory", "IterativeLQR", "IterativeLQRFactory", "B200MLP", "MLPWeights", "simulate",
-           "evaluate_candidates", "get_model_rmse"]
+           "evaluate_candidates", "get_model_rmse", "B200Linear", "NonLinearMPCProblem"]

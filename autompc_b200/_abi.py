@@ -71,6 +71,11 @@ EXPORTS = {
     "ampc_mlp_pred_batch": [C.c_void_p, C.c_int32, _dp, _dp, _dp],
     "ampc_mlp_rollout_batch": [C.c_void_p, C.c_int32, C.c_int32, _dp, _dp, _dp],
     "ampc_mlp_pred_diff_batch": [C.c_void_p, C.c_int32, _dp, _dp, _dp, _dp, _dp],
+    "ampc_mlp_nmpc_constraint": [C.c_void_p, C.c_int32, _dp, _dp],
+    "ampc_mlp_nmpc_jacobian": [C.c_void_p, C.c_int32, _dp, _dp],
+    "ampc_linear_create": [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _dp, _dp, C.c_int32],
+    "ampc_linear_destroy": [C.c_void_p],
+    "ampc_linear_pred_batch": [C.c_void_p, C.c_int32, _dp, _dp, _dp],
     "ampc_ilqr_create": [C.POINTER(C.c_void_p), C.POINTER(IlqrCfg), C.POINTER(MlpDesc), C.POINTER(QuadCost)],
     "ampc_ilqr_destroy": [C.c_void_p],
     "ampc_ilqr_solve_host": [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libampc_b200.so")
-SOURCES = ["mppi_api.cu", "mppi_fp32.cu", "mppi_tc.cu", "mlp_ops.cu", "ilqr.cu"]
+SOURCES = ["mppi_api.cu", "mppi_fp32.cu", "mppi_tc.cu", "mlp_ops.cu", "ilqr.cu", "linear.cu"]
 # the tcgen05 kernel template is instantiated once per (cta_group, NXP, ReLU, trace) combination, each as its own
 # compilation of mppi_tc_inst.cu, so that the matrix builds in parallel
 TC_INSTANCES = [(cg, nxp, relu, f16, 0) for f16 in (0, 1) for cg in (1, 2) for relu in (0, 1)

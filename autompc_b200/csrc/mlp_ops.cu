@@ -80,6 +80,43 @@ __global__ void __launch_bounds__(NT) pred_diff_kernel(const AmpcMlpF64 net, int
   }
 }
 
+// Direct-transcription callbacks (autompc/control/nmpc.py:102-110, :148-187) for an MLP model, one CTA per knot i.
+// Decision vector x = [ states (H+1, nx) | ctrls (H, nu) ].  WANT_JAC = false: c[i] = -state[i+1] + pred(state[i], ctrl[i])
+// (get_constraint).  WANT_JAC = true: the values of get_jacobian(x, False) in the reference's order, per knot
+// [ d pred / d state (nx*nx, row-major) | d pred / d ctrl (nx*nu) | -1 x nx ].
+template <bool WANT_JAC>
+__global__ void __launch_bounds__(NT) nmpc_knot_kernel(const AmpcMlpF64 net, int H, const double *xvec, double *out) {
+  extern __shared__ double sm_d[];
+  const int i = blockIdx.x;
+  if (i >= H) return;
+  const int nx = net.nx, nu = net.nu, nin = nx + nu;
+  const double *xs = xvec + (size_t)i * nx, *xn = xvec + (size_t)(i + 1) * nx;
+  const double *us = xvec + (size_t)(H + 1) * nx + (size_t)i * nu;
+  double *h0 = sm_d, *h1 = h0 + net.max_width, *g = h1 + net.max_width;
+  for (int j = threadIdx.x; j < nin; j += NT) {
+    const double v = j < nx ? xs[j] : us[j - nx];
+    h0[j] = (v - net.xu_mean[j]) / net.xu_std[j];
+  }
+  __syncthreads();
+  if constexpr (!WANT_JAC) {
+    const double *o = ampc_mlp_f64_forward(net, h0, h1, nullptr, threadIdx.x, NT);
+    for (int j = threadIdx.x; j < nx; j += NT)
+      out[(size_t)i * nx + j] = -xn[j] + (xs[j] + (o[j] * net.dy_std[j] + net.dy_mean[j]));     // nmpc.py:109
+  } else {
+    double *J0 = g + net.max_width, *J1 = J0 + (size_t)net.max_width * nin;
+    const double *J;
+    ampc_mlp_f64_forward_jac(net, h0, h1, g, J0, J1, &J, threadIdx.x, NT);
+    double *o = out + (size_t)i * (nx * nx + nx * nu + nx);
+    for (int t = threadIdx.x; t < nx * nin; t += NT) {
+      const int r = t / nin, c = t - r * nin;
+      const double v = J[t] * net.dy_std[r];                                                  // mlp.py:298
+      if (c < nx) o[r * nx + c] = v + (r == c ? 1.0 : 0.0);                                   // nmpc.py:180-181
+      else o[nx * nx + r * nu + (c - nx)] = v;                                                // nmpc.py:182-183
+    }
+    for (int j = threadIdx.x; j < nx; j += NT) o[nx * nx + nx * nu + j] = -1.0;               // nmpc.py:184-185
+  }
+}
+
 // k-step open-loop prediction: window s starts at X0[s] and is advanced `horizon` times with the recorded controls
 // U[k][s] -- the inner loop of get_model_rmse (autompc/evaluation/model_metrics.py:33-35) as one launch.  Each step
 // is pred_batch_kernel's arithmetic, so the result equals `horizon` chained pred_batch calls bit for bit.
@@ -251,6 +288,8 @@ extern "C" int ampc_mlp_create(ampc_mlp **out, const ampc_mlp_desc *mlp, int32_t
   m->smem_pred = 2 * (size_t)m->net.max_width * sizeof(double);
   m->smem_diff = (3 * (size_t)m->net.max_width + 2 * (size_t)m->net.max_width * (nx + nu)) * sizeof(double);
   cudaError_t e = ampc_raise_smem_limit((const void *)pred_diff_kernel, m->smem_diff);
+  if (e == cudaSuccess) e = ampc_raise_smem_limit((const void *)nmpc_knot_kernel<true>, m->smem_diff);
+  if (e == cudaSuccess) e = ampc_raise_smem_limit((const void *)nmpc_knot_kernel<false>, m->smem_diff);
   if (e != cudaSuccess) {
     ampc_set_error("pred_diff kernel needs %zu B shared memory: %s", m->smem_diff, cudaGetErrorString(e));
     cudaFree(m->d_blob);
@@ -326,4 +365,33 @@ extern "C" int ampc_mlp_rollout_batch(ampc_mlp *m, int32_t batch, int32_t horizo
   cudaFree(d);
   AMPC_CUDA_CHECK(e);
   return AMPC_OK;
+}
+
+static int run_nmpc(ampc_mlp *m, int32_t H, const double *x, double *out, bool jac) {
+  AMPC_REQUIRE(m && x && out && H >= 1, AMPC_ERR_INVALID, "bad argument");
+  AMPC_CUDA_CHECK(cudaSetDevice(m->device));
+  const int nx = m->net.nx, nu = m->net.nu;
+  const size_t n_in = (size_t)(H + 1) * nx + (size_t)H * nu;
+  const size_t n_out = jac ? (size_t)H * (nx * nx + nx * nu + nx) : (size_t)H * nx;
+  double *d = nullptr;
+  AMPC_CUDA_CHECK(cudaMalloc(&d, (n_in + n_out) * sizeof(double)));
+  cudaError_t e = cudaMemcpy(d, x, n_in * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    if (jac) nmpc_knot_kernel<true><<<H, NT, m->smem_diff>>>(m->net, H, d, d + n_in);
+    else nmpc_knot_kernel<false><<<H, NT, m->smem_diff>>>(m->net, H, d, d + n_in);
+    ampc_count_launch();
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, d + n_in, n_out * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  AMPC_CUDA_CHECK(e);
+  return AMPC_OK;
+}
+
+extern "C" int ampc_mlp_nmpc_constraint(ampc_mlp *m, int32_t H, const double *x, double *c) {
+  return run_nmpc(m, H, x, c, false);
+}
+
+extern "C" int ampc_mlp_nmpc_jacobian(ampc_mlp *m, int32_t H, const double *x, double *jac) {
+  return run_nmpc(m, H, x, jac, true);
 }

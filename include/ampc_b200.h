@@ -188,6 +188,24 @@ int ampc_mlp_rollout_batch(ampc_mlp *m, int32_t batch, int32_t horizon, const do
 int ampc_mlp_pred_diff_batch(ampc_mlp *m, int32_t batch, const double *X, const double *U,
                              double *Xn, double *Jx, double *Ju);
 
+/* Direct-transcription callbacks of autompc.control.nmpc.NonLinearMPCProblem for an MLP model (the NLP solver, IPOPT,
+ * stays on the host).  x: the decision vector [ states (H+1, nx) | ctrls (H, nu) ] (nmpc.py:56-66).
+ *   constraint: c (H*nx)  = get_constraint(x)  (nmpc.py:102-110):  c[i] = -state[i+1] + pred(state[i], ctrl[i]);
+ *   jacobian:   jac (H*(nx*nx + nx*nu + nx)) = get_jacobian(x, False) (nmpc.py:170-187): per knot the dense state
+ *               Jacobian (row-major), the dense control Jacobian, then -1 for state[i+1]; the (row, col) pattern of
+ *               get_jacobian(x, True) (nmpc.py:148-169) is index arithmetic and stays on the host.                */
+int ampc_mlp_nmpc_constraint(ampc_mlp *m, int32_t H, const double *x, double *c);
+int ampc_mlp_nmpc_jacobian(ampc_mlp *m, int32_t H, const double *x, double *jac);
+
+/* ------------------------------------------------------- linear models --- */
+/* Replaces ARX.pred / pred_batch (autompc/sysid/arx.py:146-154) and Koopman.pred / pred_batch
+ * (autompc/sysid/koopman.py:165-173):  Xn = (A @ X.T + B @ U.T).T,  A (ns,ns), B (ns,nu) row-major HOST float64, ns =
+ * the model's state_dim (history stack / lifted observation).  float64 on the device, HOST buffers, synchronous.    */
+typedef struct ampc_linear ampc_linear;
+int ampc_linear_create(ampc_linear **out, int32_t ns, int32_t nu, const double *A, const double *B, int32_t device);
+int ampc_linear_destroy(ampc_linear *h);
+int ampc_linear_pred_batch(ampc_linear *h, int32_t batch, const double *X, const double *U, double *Xn);
+
 /* ------------------------------------------------- device-resident closed loop --- */
 /* Replaces autompc.utils.simulation.simulate (autompc/utils/simulation.py:11-64) for an MPPI controller and an
  * MLP simulation model when term_cond is None:  T x [ u = controller.run(x) ; x = sim_model.pred(x, u) ]

@@ -492,8 +492,10 @@ def test_mppi_sumcost_per_sample_terminal_matches_oracle(precision):
     costs_o, eps_c = o.do_rollouts(x0, eps.copy())
     costs_o = costs_o - o.term_const + np.array([SumQuadCostParams(terms).eval_term_obs_cost(x) for x in o.last_path])
     costs, _ = ctl.last_costs()
-    # x10: the learned cartpole dynamics amplify rounding (see the fixture test above); the check here is the fold
-    np.testing.assert_allclose(costs + ctl._term_const, costs_o, rtol=TOL[precision]["cost_rtol"] * 10,
+    # the learned cartpole dynamics amplify rounding (see the fixture tests); the check here is the fold, so the
+    # tolerance is the cost tolerance of the synthetic cases x10 (fp32) / x20 (bf16)
+    k = 10 if precision == "fp32" else 20
+    np.testing.assert_allclose(costs + ctl._term_const, costs_o, rtol=TOL[precision]["cost_rtol"] * k,
                                atol=TOL[precision]["cost_rtol"] * np.abs(costs_o).max())
     ctl.close()
 

@@ -125,14 +125,14 @@ def test_closed_loop_eval_cost_with_threshold_terms():
     o_quad2 = QuadCostParams(np.diag([1.0, 2.0, 3.0, 4.0]), np.diag([0.5]), np.diag([4.0, 3.0, 2.0, 1.0]), np.full(4, 0.1))
     own = QuadCostParams(z["Q"], z["R"], z["F"], np.zeros(4))
     T = 25
-    for cost, ocost, exact in [(thr, o_thr, True), (box, o_box, True), (thr + box, SumQuadCostParams([o_thr, o_box]), True),
-                               (quad2 + thr, SumQuadCostParams([o_quad2, o_thr]), False), (None, own, False)]:
+    for cost, ocost, exact in [(thr, o_thr, 1), (box, o_box, 1), (thr + box, SumQuadCostParams([o_thr, o_box]), 2),
+                               (quad2 + thr, SumQuadCostParams([o_quad2, o_thr]), 0), (None, own, 0)]:
         np.random.seed(1)
         ctl.reset()
         r = simulate(ctl, x0, sim_model=model, max_steps=T, cost=cost)
         want = traj_cost(ocost, r.obs, r.ctrls)
         if exact:
-            assert r.cost == want and 0 < want <= T + 1
+            assert r.cost == want and 0 < want <= exact * (T + 1)      # a count of (term, step) violations
         else:
             np.testing.assert_allclose(r.cost, want, rtol=1e-12)
     ctl.close()
