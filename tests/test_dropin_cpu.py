@@ -1,0 +1,111 @@
+"""CPU (build container only): the engine's host side under the UNMODIFIED reference's own ``Pipeline`` and
+``simulate()`` -- SURVEY.md 8(a) row a13 / 8(b) "drops into pipeline.py unchanged".
+
+What runs, in a subprocess (so that ``autompc_b200.plugin`` binds to the reference's ABCs):
+
+* ``autompc.pipeline.Pipeline(system, <reference MLP model>, <reference QuadCostFactory>, autompc_b200.MPPIFactory)``
+  -- the ``isinstance`` sorting (pipeline.py:51-81), ``get_configuration_space()`` with the ``_ctrlr:`` / ``_cost:``
+  prefixes (pipeline.py:90-105), and ``__call__(cfg, task, trajs)`` (pipeline.py:107-168), which builds the engine's
+  controller through the reference's ``ControllerFactory.__call__`` (controller.py:30-33);
+* ``autompc.utils.simulation.simulate(controller, init_obs, sim_model=model, max_steps=T)`` (simulation.py:11-64)
+  driving ``controller.traj_to_state`` / ``run``;
+* the same closed loop with the reference's OWN ``autompc.control.mppi.MPPI`` built by the same pipeline recipe, from
+  the same NumPy seed: the two trajectories must agree (the engine draws the noise in the reference's order,
+  mppi.py:99, :126).
+
+There is no GPU in the build container and no reference on the GPU box, so here the C library behind
+``autompc_b200._abi`` is replaced by ``tests/oracle_backed_lib.py`` (the float64 oracle answering the same C-ABI
+calls with the same ctypes structures); everything above the ABI is the shipped code.  On the GPU the same classes
+drive the CUDA library (tests/test_mppi_gpu.py::test_closed_loop_through_plugin_surface and the fixture tests).
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from oracle import ref_loader
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r'''
+import sys, os, importlib, copy
+sys.path.insert(0, %(root)r)
+import numpy as np
+from oracle import configspace_shim
+configspace_shim.install()
+from oracle import ref_loader
+ns = ref_loader.load()
+with ref_loader.quiet():
+    importlib.import_module("autompc.costs.cost_factory")
+    costs_pkg = sys.modules["autompc.costs"]
+    costs_pkg.QuadCost = ns.QuadCost                      # quad_cost_factory.py:5 does `from . import QuadCost`
+    QuadCostFactory = importlib.import_module("autompc.costs.quad_cost_factory").QuadCostFactory
+    Pipeline = importlib.import_module("autompc.pipeline").Pipeline
+    simulate = importlib.import_module("autompc.utils.simulation").simulate
+    RefMPPIFactory = importlib.import_module("autompc.control.mppi").MPPIFactory
+
+import autompc_b200
+from autompc_b200 import _abi, plugin
+assert plugin.HAVE_AUTOMPC, "plugin.py must bind to the reference ABCs when autompc is importable"
+from tests.oracle_backed_lib import OracleBackedLib
+fake = OracleBackedLib()
+_abi._lib = fake                                          # the CUDA library's stand-in (no GPU here)
+
+from oracle.make_golden import make_cartpole
+from oracle.make_golden_f import reference_mlp_from_npz
+z = np.load(os.path.join(%(root)r, "tests", "golden", "cartpole_mlp.npz"))
+system, task = make_cartpole(ns)
+model = reference_mlp_from_npz(ns, system, z)
+
+def build(factory):
+    pipe = Pipeline(system, model, QuadCostFactory(system), factory)
+    cs = pipe.get_configuration_space()
+    names = cs.get_hyperparameter_names()
+    cfg = cs.get_default_configuration()
+    cfg["_ctrlr:horizon"] = 9
+    cfg["_ctrlr:num_path"] = 150
+    cfg["_ctrlr:sigma"] = 0.7
+    cfg["_ctrlr:lmda"] = 0.6
+    cfg["_cost:theta_Q"] = 12.0
+    cfg["_cost:omega_F"] = 3.0
+    np.random.seed(42)
+    with ref_loader.quiet():
+        controller, new_task, m = pipe(cfg, task, [])
+    return pipe, names, controller, new_task, m
+
+# ---- the engine's factory inside the reference pipeline
+pipe, names, ctl, new_task, m = build(autompc_b200.MPPIFactory(system, noise="numpy", precision="fp32"))
+assert pipe.controller_factory is not None and pipe.model is model and pipe.cost_factory is not None
+for n in ("_ctrlr:horizon", "_ctrlr:sigma", "_ctrlr:lmda", "_ctrlr:num_path", "_cost:theta_Q", "_cost:u_R", "_cost:dx_F"):
+    assert n in names, (n, names)
+assert isinstance(ctl, autompc_b200.MPPI) and isinstance(ctl, ns.Controller)
+assert ctl.H == 9 and ctl.num_path == 150 and ctl.sigma == 0.7 and ctl.lmda == 0.6 and m is model
+Q, R, F = new_task.get_cost().get_cost_matrices()
+assert Q[0, 0] == 12.0 and F[1, 1] == 3.0 and ctl.task is new_task
+assert ctl.state_dim == 5
+with ref_loader.quiet():
+    traj = simulate(ctl, task.get_init_obs(), sim_model=model, max_steps=6, silent=True)
+assert fake.calls.count("solve_host") == 6 and len(traj) == 7
+
+# ---- the reference's own MPPI through the same recipe, same seed
+pipe_r, names_r, ctl_r, _, _ = build(RefMPPIFactory(system))
+assert sorted(names_r) == sorted(names)                   # same hyper-parameter names and prefixes
+with ref_loader.quiet():
+    traj_r = simulate(ctl_r, task.get_init_obs(), sim_model=model, max_steps=6, silent=True)
+np.testing.assert_allclose(traj.obs, traj_r.obs, rtol=0, atol=1e-5)     # act_sequence rides through float32 on the device
+np.testing.assert_allclose(traj.ctrls, traj_r.ctrls, rtol=0, atol=1e-4)
+# reset() redraws like the reference (mppi.py:107-108)
+np.random.seed(7); ctl.reset(); a = ctl.act_sequence.copy()
+np.random.seed(7)
+with ref_loader.quiet():
+    ctl_r.reset()
+np.testing.assert_allclose(a, ctl_r.act_sequence, rtol=0, atol=1e-7)
+print("dropin ok", float(np.abs(traj.obs - traj_r.obs).max()))
+'''
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree only exists in the build container")
+def test_engine_controller_under_reference_pipeline_and_simulate():
+    out = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0 and "dropin ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
