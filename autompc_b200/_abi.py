@@ -79,6 +79,7 @@ EXPORTS = {
     "ampc_ilqr_create": [C.POINTER(C.c_void_p), C.POINTER(IlqrCfg), C.POINTER(MlpDesc), C.POINTER(QuadCost)],
     "ampc_ilqr_destroy": [C.c_void_p],
     "ampc_ilqr_solve_host": [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
+    "ampc_ilqr_launch": [C.c_void_p, C.c_void_p],
     "ampc_last_error": [],
     "ampc_version": [],
     "ampc_launch_count": [],

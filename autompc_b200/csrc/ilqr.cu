@@ -20,8 +20,10 @@
 
 namespace {
 
-constexpr int NT = 512;
+constexpr int NT = 640;            // 20 warps: warp 0 runs the Riccati recursion, line-search rollouts use G warps each
+constexpr int NWARPS = NT / 32;
 constexpr int MAX_NU = 16;
+constexpr int MAX_LS = 20;
 
 struct IlqrParams {
   AmpcMlpF64 net;
@@ -29,10 +31,15 @@ struct IlqrParams {
   double dt, ls_discount, ls_cost_threshold, u_threshold;
   const double *Q, *R, *F, *goal, *goalF, *umin, *umax, *alphas;   // device (goalF: goal of the terminal term)
   const double *x0, *uguess;                       // device (uguess may be null)
-  // scratch / outputs (device)
+  // scratch / outputs (device, global).  With traj_smem != 0 the kernel keeps the trajectories, gains, Jacobians and
+  // line-search rollouts in shared memory instead and writes the outputs back once at the end.
   double *states, *ctrls, *Ks, *ks, *Jacs, *ls_states, *ls_ctrls, *step_cost;
   double *hA, *hB, *hG, *JA, *JB;
   int *info, *alpha_idx;
+  int w_smem;                      // != 0: the network's weights and biases are staged into shared memory
+  int traj_smem;
+  size_t net_doubles;              // weights + biases + normalisers as laid out by ampc_mlp_f64_upload
+  const double *net_blob;
 };
 
 __device__ __forceinline__ double block_sum(double v, double *s_red, int tid) {
@@ -40,7 +47,7 @@ __device__ __forceinline__ double block_sum(double v, double *s_red, int tid) {
   if ((tid & 31) == 0) s_red[tid >> 5] = v;
   __syncthreads();
   double r = 0.0;
-  for (int w = 0; w < NT / 32; ++w) r += s_red[w];
+  for (int w = 0; w < NWARPS; ++w) r += s_red[w];
   __syncthreads();
   return r;
 }
@@ -67,31 +74,108 @@ __device__ __forceinline__ void step_costs(const IlqrParams &P, const double *xs
   }
 }
 
+// dot(Wt[:, j], h), four partial sums like ampc_dot_col but with plain loads: Wt may be shared OR global memory
+__device__ __forceinline__ double dot_col_any(const double *Wt, int N, int j, const double *h, int Kin) {
+  double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+  int k = 0;
+  for (; k + 4 <= Kin; k += 4) {
+    p0 = fma(Wt[(size_t)(k + 0) * N + j], h[k + 0], p0);
+    p1 = fma(Wt[(size_t)(k + 1) * N + j], h[k + 1], p1);
+    p2 = fma(Wt[(size_t)(k + 2) * N + j], h[k + 2], p2);
+    p3 = fma(Wt[(size_t)(k + 3) * N + j], h[k + 3], p3);
+  }
+  for (; k < Kin; ++k) p0 = fma(Wt[(size_t)k * N + j], h[k], p0);
+  return (p0 + p1) + (p2 + p3);
+}
+
+// barrier over the `nthr` threads of one line-search group (named barrier `id` >= 1), or a warp barrier
+__device__ __forceinline__ void group_sync(int id, int nthr) {
+  if (nthr == 32) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory");
+}
+
+// One MLP forward for ONE sample by a group of `gthr` threads (`gl` = rank inside the group): h0 holds the z-scored
+// input, h0/h1 ping-pong (shared memory), returns the buffer with the raw outputs.  Same arithmetic per output as
+// ampc_mlp_f64_forward_batch (bit-identical results).
+__device__ __forceinline__ const double *group_forward(const AmpcMlpF64 &net, double *h0, double *h1, int gl, int gthr,
+                                                       int bar) {
+  double *hin = h0, *hout = h1;
+  for (int l = 0; l < net.n_layers; ++l) {
+    const int Kin = net.dims[l], N = net.dims[l + 1];
+    const bool last = (l == net.n_layers - 1);
+    for (int j = gl; j < N; j += gthr) {
+      const double y = net.b[l][j] + dot_col_any(net.Wt[l], N, j, hin, Kin);
+      hout[j] = last ? y : ampc_act<double>(net.act, y);
+    }
+    group_sync(bar, gthr);
+    double *t2 = hin; hin = hout; hout = t2;
+  }
+  return hin;
+}
+
 // Jacobians of x' = x + dy(x,u) at (xs[i], us[i]) for i < H  ->  Jacs (H, nx, nx+nu)   (mlp.py:281-305)
-__device__ void jac_batch(const IlqrParams &P, const double *xs, const double *us, int tid) {
-  const AmpcMlpF64 &net = P.net;
+// All NT threads; scratch (hA, hB, hG, JA, JB) is global (L1/L2 resident), weights come through `net` (shared or global).
+__device__ void jac_batch(const IlqrParams &P, const AmpcMlpF64 &net, const double *xs, const double *us, double *Jacs,
+                          int tid) {
   const int nx = P.nx, nu = P.nu, nin = nx + nu, H = P.H, mw = net.max_width;
   for (int t = tid; t < H * nin; t += NT) {
     const int s = t / nin, j = t - s * nin;
     const double v = j < nx ? xs[(size_t)s * nx + j] : us[(size_t)s * nu + (j - nx)];
-    P.hA[(size_t)s * mw + j] = (v - __ldg(net.xu_mean + j)) / __ldg(net.xu_std + j);
+    P.hA[(size_t)s * mw + j] = (v - net.xu_mean[j]) / net.xu_std[j];
   }
   __syncthreads();
-  const double *J;
-  ampc_mlp_f64_forward_jac_batch(net, H, P.hA, P.hB, P.hG, mw, P.JA, P.JB, mw * nin, &J, tid, NT);
+  double *hin = P.hA, *hout = P.hB, *Jp = P.JA, *Jn = P.JB, *g = P.hG;
+  const int jstride = mw * nin;
+  for (int l = 0; l < net.n_layers; ++l) {
+    const int Kin = net.dims[l], N = net.dims[l + 1];
+    const bool last = (l == net.n_layers - 1);
+    for (int t = tid; t < H * N; t += NT) {
+      const int s = t / N, j = t - s * N;
+      const double y = net.b[l][j] + dot_col_any(net.Wt[l], N, j, hin + (size_t)s * mw, Kin);
+      hout[(size_t)s * mw + j] = last ? y : ampc_act<double>(net.act, y);
+      g[(size_t)s * mw + j] = last ? 1.0 : ampc_act_grad<double>(net.act, y);
+    }
+    __syncthreads();
+    const int per = N * nin;
+    for (int t = tid; t < H * per; t += NT) {
+      const int s = t / per, r = t - s * per;
+      const int c = r / N, j = r - c * N;   // j fastest: neighbouring threads read neighbouring weights
+      const double *jp = Jp + (size_t)s * jstride;
+      double v;
+      if (l == 0) {
+        v = net.Wt[0][(size_t)c * N + j] / net.xu_std[c];
+      } else {
+        double p0 = 0.0, p1 = 0.0;
+        int k = 0;
+        for (; k + 2 <= Kin; k += 2) {
+          p0 = fma(net.Wt[l][(size_t)k * N + j], jp[(size_t)k * nin + c], p0);
+          p1 = fma(net.Wt[l][(size_t)(k + 1) * N + j], jp[(size_t)(k + 1) * nin + c], p1);
+        }
+        if (k < Kin) p0 = fma(net.Wt[l][(size_t)k * N + j], jp[(size_t)k * nin + c], p0);
+        v = p0 + p1;
+      }
+      Jn[(size_t)s * jstride + (size_t)j * nin + c] = v * g[(size_t)s * mw + j];
+    }
+    __syncthreads();
+    double *t2 = hin; hin = hout; hout = t2;
+    double *t3 = Jp; Jp = Jn; Jn = t3;
+  }
   for (int t = tid; t < H * nx * nin; t += NT) {
     const int s = t / (nx * nin), r = t - s * (nx * nin);
     const int a = r / nin, c = r - a * nin;
-    P.Jacs[t] = J[(size_t)s * mw * nin + r] * __ldg(net.dy_std + a) + ((c == a) ? 1.0 : 0.0);
+    Jacs[t] = Jp[(size_t)s * jstride + r] * net.dy_std[a] + ((c == a) ? 1.0 : 0.0);
   }
   __syncthreads();
 }
 
 __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
   extern __shared__ double sm[];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nx = P.nx, nu = P.nu, n = nx + nu, H = P.H, LS = P.ls_max_iter, mw = P.net.max_width;
-  const AmpcMlpF64 &net = P.net;
+  // line-search groups: G warps per alpha (2 when they fit), group j = warps [j*G, (j+1)*G)
+  const int G = (2 * LS <= NWARPS) ? 2 : 1;
+  const int gthr = 32 * G;
+  const int grp = warp / G, gl = tid - grp * gthr;
   // shared-memory carve
   double *s_Ct = sm;                 // n*n   dt*blkdiag(Q+Q^T, R+R^T)           ilqr.py:170-171
   double *s_Fs = s_Ct + n * n;       // nx*nx F+F^T                             cost.py:208-211
@@ -104,10 +188,41 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
   double *s_qt = s_Qt + n * n;       // n
   double *s_K = s_qt + n;            // nu*nx
   double *s_k = s_K + nu * nx;       // nu
-  double *s_red = s_k + nu;          // NT/32
-  double *s_obj = s_red + NT / 32;   // LS + 4
-  __shared__ int s_flag[4];          // [0]=continue loop, [1]=used idx, [2]=refresh jac
+  double *s_LU = s_k + nu;           // nu*nu  LU factors of Quu
+  double *s_red = s_LU + nu * nu;    // NWARPS
+  double *s_obj = s_red + NWARPS;    // LS + 4
+  double *s_h = s_obj + LS + 4;      // LS * 2 * mw: per-group activation ping-pong
+  double *s_next = s_h + (size_t)LS * 2 * mw;
+  __shared__ int s_flag[4];          // [0]=line search failed, [1]=used idx, [2]=refresh jac
+  __shared__ int s_piv[MAX_NU];
   __shared__ double s_lin, s_quad;
+
+  // ---- the network: weights staged into shared memory when they fit (plain loads serve both placements)
+  AmpcMlpF64 net = P.net;
+  if (P.w_smem) {
+    double *s_net = s_next;
+    s_next += P.net_doubles;
+    for (size_t t = tid; t < P.net_doubles; t += NT) s_net[t] = P.net_blob[t];
+    for (int l = 0; l < net.n_layers; ++l) {
+      net.Wt[l] = s_net + (P.net.Wt[l] - P.net_blob);
+      net.b[l] = s_net + (P.net.b[l] - P.net_blob);
+    }
+    net.xu_mean = s_net + (P.net.xu_mean - P.net_blob); net.xu_std = s_net + (P.net.xu_std - P.net_blob);
+    net.dy_mean = s_net + (P.net.dy_mean - P.net_blob); net.dy_std = s_net + (P.net.dy_std - P.net_blob);
+  }
+  // ---- trajectories, gains, Jacobians, line-search rollouts: shared memory when they fit
+  double *states = P.states, *ctrls = P.ctrls, *Ks = P.Ks, *ks = P.ks, *Jacs = P.Jacs, *ls_states = P.ls_states,
+         *ls_ctrls = P.ls_ctrls, *step_cost = P.step_cost;
+  if (P.traj_smem) {
+    states = s_next; s_next += (size_t)(H + 1) * nx;
+    ctrls = s_next; s_next += (size_t)H * nu;
+    Ks = s_next; s_next += (size_t)H * nu * nx;
+    ks = s_next; s_next += (size_t)H * nu;
+    Jacs = s_next; s_next += (size_t)H * nx * n;
+    ls_states = s_next; s_next += (size_t)LS * (H + 1) * nx;
+    ls_ctrls = s_next; s_next += (size_t)LS * H * nu;
+    step_cost = s_next; s_next += (size_t)(LS + 1) * (H + 1);
+  }
 
   for (int t = tid; t < n * n; t += NT) {
     const int r = t / n, c = t - r * n;
@@ -120,184 +235,193 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
     const int r = t / nx, c = t - r * nx;
     s_Fs[t] = P.F[r * nx + c] + P.F[c * nx + r];
   }
-  for (int t = tid; t < nx; t += NT) P.states[t] = P.x0[t];
-  for (int t = tid; t < H * nu; t += NT) P.ctrls[t] = P.uguess ? P.uguess[t] : 0.0;
+  for (int t = tid; t < nx; t += NT) states[t] = P.x0[t];
+  for (int t = tid; t < H * nu; t += NT) ctrls[t] = P.uguess ? P.uguess[t] : 0.0;
   for (int t = tid; t < P.max_iter; t += NT) P.alpha_idx[t] = -1;
   __syncthreads();
 
-  // ---- initial rollout (ilqr.py:141-147); Jacobians are evaluated in one batch afterwards
-  for (int i = 0; i < H; ++i) {
-    for (int j = tid; j < n; j += NT) {
-      const double v = j < nx ? P.states[(size_t)i * nx + j] : P.ctrls[(size_t)i * nu + (j - nx)];
-      P.hA[j] = (v - __ldg(net.xu_mean + j)) / __ldg(net.xu_std + j);
+  // ---- initial rollout (ilqr.py:141-147) by line-search group 0; Jacobians are evaluated in one batch afterwards
+  if (grp == 0) {
+    double *h0 = s_h, *h1 = s_h + mw;
+    for (int i = 0; i < H; ++i) {
+      for (int j = gl; j < n; j += gthr) {
+        const double v = j < nx ? states[(size_t)i * nx + j] : ctrls[(size_t)i * nu + (j - nx)];
+        h0[j] = (v - net.xu_mean[j]) / net.xu_std[j];
+      }
+      group_sync(1, gthr);
+      const double *out = group_forward(net, h0, h1, gl, gthr, 1);
+      for (int j = gl; j < nx; j += gthr)
+        states[(size_t)(i + 1) * nx + j] = states[(size_t)i * nx + j] + (out[j] * net.dy_std[j] + net.dy_mean[j]);
+      group_sync(1, gthr);
     }
-    __syncthreads();
-    const double *out = ampc_mlp_f64_forward_batch(net, 1, P.hA, P.hB, mw, tid, NT);
-    for (int j = tid; j < nx; j += NT)
-      P.states[(size_t)(i + 1) * nx + j] = P.states[(size_t)i * nx + j] + (out[j] * __ldg(net.dy_std + j) + __ldg(net.dy_mean + j));
-    __syncthreads();
   }
-  jac_batch(P, P.states, P.ctrls, tid);
-  step_costs(P, P.states, P.ctrls, P.step_cost, tid, NT);
+  __syncthreads();
+  jac_batch(P, net, states, ctrls, Jacs, tid);
+  step_costs(P, states, ctrls, step_cost, tid, NT);
   __syncthreads();
   double obj = 0.0;       // every thread tracks the same scalars (uniform control flow)
-  for (int i = 0; i <= H; ++i) obj += P.step_cost[i];     // sequential like eval_obj, ilqr.py:124-129
+  for (int i = 0; i <= H; ++i) obj += step_cost[i];     // sequential like eval_obj, ilqr.py:124-129
   __syncthreads();
 
   int converged = 0, n_iter = 0, ls_fail = 0;
   for (int itr = 0; itr < P.max_iter; ++itr) {
     n_iter = itr + 1;
-    // ---- backward pass (ilqr.py:159-187)
-    double *Vn = s_V0, *Vnn = s_V1, *vn = s_v0, *vnn = s_v1;
-    for (int t = tid; t < nx * nx; t += NT) Vn[t] = s_Fs[t];
-    for (int a = tid; a < nx; a += NT) {
-      double acc = 0.0;
-      for (int b = 0; b < nx; ++b) acc += s_Fs[a * nx + b] * P.states[(size_t)H * nx + b];   // no goal: cost.py:208
-      vn[a] = acc;
-    }
-    if (tid == 0) { s_lin = 0.0; s_quad = 0.0; }
-    __syncthreads();
-    for (int t = H; t >= 1; --t) {
-      const double *J = P.Jacs + (size_t)(t - 1) * nx * n;
-      const double *xt = P.states + (size_t)(t - 1) * nx, *ut = P.ctrls + (size_t)(t - 1) * nu;
-      for (int e = tid; e < nx * n; e += NT) {         // T = Vn @ J
-        const int a = e / n, c = e - a * n;
+    // ---- backward pass (ilqr.py:159-187): ONE warp, warp barriers only (the matrices are (nx+nu)^2)
+    if (warp == 0) {
+      double *Vn = s_V0, *Vnn = s_V1, *vn = s_v0, *vnn = s_v1;
+      for (int t = lane; t < nx * nx; t += 32) Vn[t] = s_Fs[t];
+      for (int a = lane; a < nx; a += 32) {
         double acc = 0.0;
-        for (int b = 0; b < nx; ++b) acc += Vn[a * nx + b] * J[b * n + c];
-        s_T[e] = acc;
+        for (int b = 0; b < nx; ++b) acc += s_Fs[a * nx + b] * states[(size_t)H * nx + b];   // no goal: cost.py:208
+        vn[a] = acc;
       }
-      __syncthreads();
-      for (int e = tid; e < n * n + n; e += NT) {      // Qt = Ct + J^T T ; qt = ct + J^T vn
-        if (e < n * n) {
-          const int r = e / n, c = e - r * n;
+      double lin_acc = 0.0, quad_acc = 0.0;               // lane 0's running sums (ilqr.py:178-179)
+      __syncwarp();
+      for (int t = H; t >= 1; --t) {
+        const double *J = Jacs + (size_t)(t - 1) * nx * n;
+        const double *xt = states + (size_t)(t - 1) * nx, *ut = ctrls + (size_t)(t - 1) * nu;
+        for (int e = lane; e < nx * n; e += 32) {         // T = Vn @ J
+          const int a = e / n, c = e - a * n;
           double acc = 0.0;
-          for (int a = 0; a < nx; ++a) acc += J[a * n + r] * s_T[a * n + c];
-          s_Qt[e] = s_Ct[e] + acc;
-        } else {
-          const int r = e - n * n;
-          double ct = 0.0;
-          if (r < nx) { for (int b = 0; b < nx; ++b) ct += s_Ct[r * n + b] * (xt[b] - P.goal[b]); }
-          else { for (int b = 0; b < nu; ++b) ct += s_Ct[r * n + nx + b] * ut[b]; }
-          double acc = 0.0;
-          for (int a = 0; a < nx; ++a) acc += J[a * n + r] * vn[a];
-          s_qt[r] = ct + acc;
+          for (int b = 0; b < nx; ++b) acc += Vn[a * nx + b] * J[b * n + c];
+          s_T[e] = acc;
         }
-      }
-      __syncthreads();
-      if (tid == 0) {                                   // K = -Quu^-1 Qux, k = -Quu^-1 qu   (ilqr.py:176-177)
-        double A[MAX_NU][MAX_NU];
-        int piv[MAX_NU];
-        for (int r = 0; r < nu; ++r) for (int c = 0; c < nu; ++c) A[r][c] = s_Qt[(nx + r) * n + nx + c];
-        for (int c = 0; c < nu; ++c) {                  // LU with partial pivoting (LAPACK gesv)
-          int pr = c; double best = fabs(A[c][c]);
-          for (int r = c + 1; r < nu; ++r) if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); pr = r; }
-          piv[c] = pr;
-          if (pr != c) for (int q = 0; q < nu; ++q) { double tmp = A[c][q]; A[c][q] = A[pr][q]; A[pr][q] = tmp; }
-          for (int r = c + 1; r < nu; ++r) {
-            A[r][c] /= A[c][c];
-            for (int q = c + 1; q < nu; ++q) A[r][q] -= A[r][c] * A[c][q];
+        __syncwarp();
+        for (int e = lane; e < n * n + n; e += 32) {      // Qt = Ct + J^T T ; qt = ct + J^T vn
+          if (e < n * n) {
+            const int r = e / n, c = e - r * n;
+            double acc = 0.0;
+            for (int a = 0; a < nx; ++a) acc += J[a * n + r] * s_T[a * n + c];
+            s_Qt[e] = s_Ct[e] + acc;
+          } else {
+            const int r = e - n * n;
+            double ct = 0.0;
+            if (r < nx) { for (int b = 0; b < nx; ++b) ct += s_Ct[r * n + b] * (xt[b] - P.goal[b]); }
+            else { for (int b = 0; b < nu; ++b) ct += s_Ct[r * n + nx + b] * ut[b]; }
+            double acc = 0.0;
+            for (int a = 0; a < nx; ++a) acc += J[a * n + r] * vn[a];
+            s_qt[r] = ct + acc;
           }
         }
-        for (int col = 0; col <= nx; ++col) {
+        __syncwarp();
+        if (lane == 0) {                                  // LU of Quu with partial pivoting (LAPACK gesv)
+          for (int r = 0; r < nu; ++r) for (int c = 0; c < nu; ++c) s_LU[r * nu + c] = s_Qt[(nx + r) * n + nx + c];
+          for (int c = 0; c < nu; ++c) {
+            int pr = c; double best = fabs(s_LU[c * nu + c]);
+            for (int r = c + 1; r < nu; ++r) if (fabs(s_LU[r * nu + c]) > best) { best = fabs(s_LU[r * nu + c]); pr = r; }
+            s_piv[c] = pr;
+            if (pr != c) for (int q = 0; q < nu; ++q) { double tmp = s_LU[c * nu + q]; s_LU[c * nu + q] = s_LU[pr * nu + q]; s_LU[pr * nu + q] = tmp; }
+            for (int r = c + 1; r < nu; ++r) {
+              s_LU[r * nu + c] /= s_LU[c * nu + c];
+              for (int q = c + 1; q < nu; ++q) s_LU[r * nu + q] -= s_LU[r * nu + c] * s_LU[c * nu + q];
+            }
+          }
+        }
+        __syncwarp();
+        for (int col = lane; col <= nx; col += 32) {      // K = -Quu^-1 Qux, k = -Quu^-1 qu: one right-hand side per lane
           double y[MAX_NU];
           for (int r = 0; r < nu; ++r) y[r] = (col < nx) ? s_Qt[(nx + r) * n + col] : s_qt[nx + r];
-          for (int c = 0; c < nu; ++c) { if (piv[c] != c) { double tmp = y[c]; y[c] = y[piv[c]]; y[piv[c]] = tmp; } }
-          for (int r = 1; r < nu; ++r) for (int q = 0; q < r; ++q) y[r] -= A[r][q] * y[q];
-          for (int r = nu - 1; r >= 0; --r) { for (int q = r + 1; q < nu; ++q) y[r] -= A[r][q] * y[q]; y[r] /= A[r][r]; }
+          for (int c = 0; c < nu; ++c) { const int pc = s_piv[c]; if (pc != c) { double tmp = y[c]; y[c] = y[pc]; y[pc] = tmp; } }
+          for (int r = 1; r < nu; ++r) for (int q = 0; q < r; ++q) y[r] -= s_LU[r * nu + q] * y[q];
+          for (int r = nu - 1; r >= 0; --r) { for (int q = r + 1; q < nu; ++q) y[r] -= s_LU[r * nu + q] * y[q]; y[r] /= s_LU[r * nu + r]; }
           for (int r = 0; r < nu; ++r) { if (col < nx) s_K[r * nx + col] = -y[r]; else s_k[r] = -y[r]; }
         }
-        double lin = 0.0, quad = 0.0;
-        for (int r = 0; r < nu; ++r) {
-          lin += s_qt[nx + r] * s_k[r];
-          double row = 0.0;
-          for (int c = 0; c < nu; ++c) row += s_Qt[(nx + r) * n + nx + c] * s_k[c];
-          quad += s_k[r] * row;
-        }
-        s_lin += lin; s_quad += quad;                   // ilqr.py:178-179
-      }
-      __syncthreads();
-      for (int e = tid; e < nu * nx + nu; e += NT) {
-        if (e < nu * nx) P.Ks[(size_t)(t - 1) * nu * nx + e] = s_K[e];
-        else P.ks[(size_t)(t - 1) * nu + (e - nu * nx)] = s_k[e - nu * nx];
-      }
-      for (int e = tid; e < nx * nx + nx; e += NT) {    // value update (ilqr.py:186-187)
-        if (e < nx * nx) {
-          const int a = e / nx, b = e - a * nx;
-          double acc = s_Qt[a * n + b];
-          for (int r = 0; r < nu; ++r) acc += s_Qt[a * n + nx + r] * s_K[r * nx + b];
-          for (int r = 0; r < nu; ++r) acc += s_K[r * nx + a] * s_Qt[(nx + r) * n + b];
+        __syncwarp();
+        if (lane == 0) {
+          double lin = 0.0, quad = 0.0;
           for (int r = 0; r < nu; ++r) {
+            lin += s_qt[nx + r] * s_k[r];
             double row = 0.0;
-            for (int c = 0; c < nu; ++c) row += s_Qt[(nx + r) * n + nx + c] * s_K[c * nx + b];
-            acc += s_K[r * nx + a] * row;
+            for (int c = 0; c < nu; ++c) row += s_Qt[(nx + r) * n + nx + c] * s_k[c];
+            quad += s_k[r] * row;
           }
-          Vnn[e] = acc;
-        } else {
-          const int a = e - nx * nx;
-          double acc = s_qt[a];
-          for (int r = 0; r < nu; ++r) acc += s_Qt[a * n + nx + r] * s_k[r];
-          for (int r = 0; r < nu; ++r) {
-            double inner = s_qt[nx + r];
-            for (int c = 0; c < nu; ++c) inner += s_Qt[(nx + r) * n + nx + c] * s_k[c];
-            acc += s_K[r * nx + a] * inner;
-          }
-          vnn[a] = acc;
+          lin_acc += lin; quad_acc += quad;
         }
+        for (int e = lane; e < nu * nx + nu; e += 32) {
+          if (e < nu * nx) Ks[(size_t)(t - 1) * nu * nx + e] = s_K[e];
+          else ks[(size_t)(t - 1) * nu + (e - nu * nx)] = s_k[e - nu * nx];
+        }
+        for (int e = lane; e < nx * nx + nx; e += 32) {   // value update (ilqr.py:186-187)
+          if (e < nx * nx) {
+            const int a = e / nx, b = e - a * nx;
+            double acc = s_Qt[a * n + b];
+            for (int r = 0; r < nu; ++r) acc += s_Qt[a * n + nx + r] * s_K[r * nx + b];
+            for (int r = 0; r < nu; ++r) acc += s_K[r * nx + a] * s_Qt[(nx + r) * n + b];
+            for (int r = 0; r < nu; ++r) {
+              double row = 0.0;
+              for (int c = 0; c < nu; ++c) row += s_Qt[(nx + r) * n + nx + c] * s_K[c * nx + b];
+              acc += s_K[r * nx + a] * row;
+            }
+            Vnn[e] = acc;
+          } else {
+            const int a = e - nx * nx;
+            double acc = s_qt[a];
+            for (int r = 0; r < nu; ++r) acc += s_Qt[a * n + nx + r] * s_k[r];
+            for (int r = 0; r < nu; ++r) {
+              double inner = s_qt[nx + r];
+              for (int c = 0; c < nu; ++c) inner += s_Qt[(nx + r) * n + nx + c] * s_k[c];
+              acc += s_K[r * nx + a] * inner;
+            }
+            vnn[a] = acc;
+          }
+        }
+        __syncwarp();
+        double *tp = Vn; Vn = Vnn; Vnn = tp;
+        tp = vn; vn = vnn; vnn = tp;
       }
-      __syncthreads();
-      double *tp = Vn; Vn = Vnn; Vnn = tp;
-      tp = vn; vn = vnn; vnn = tp;
-    }
-    const double lin_cost_reduce = s_lin, quad_cost_reduce = s_quad;
-    double ksq = 0.0;
-    for (int t = tid; t < H * nu; t += NT) ksq += P.ks[t] * P.ks[t];
-    const double ks_norm = sqrt(block_sum(ksq, s_red, tid));
-
-    // ---- line-search rollouts for all alphas (ilqr.py:190-205)
-    for (int t = tid; t < LS * nx; t += NT) {
-      const int j = t / nx, a = t - j * nx;
-      P.ls_states[(size_t)j * (H + 1) * nx + a] = P.x0[a];
+      if (lane == 0) { s_lin = lin_acc; s_quad = quad_acc; }
     }
     __syncthreads();
-    for (int i = 0; i < H; ++i) {
-      for (int t = tid; t < LS * nu; t += NT) {
-        const int j = t / nu, a = t - j * nu;
-        const double alpha = P.alphas[j];
-        const double *xs = P.ls_states + ((size_t)j * (H + 1) + i) * nx;
-        double fb = 0.0;
-        for (int b = 0; b < nx; ++b) fb += P.Ks[((size_t)i * nu + a) * nx + b] * (xs[b] - P.states[(size_t)i * nx + b]);
-        double u = alpha * P.ks[(size_t)i * nu + a] + P.ctrls[(size_t)i * nu + a] + fb;
-        if (P.bounded) u = fmin(fmax(u, P.umin[a]), P.umax[a]);     // np.clip, ilqr.py:203-204
-        P.ls_ctrls[((size_t)j * H + i) * nu + a] = u;
+    const double lin_cost_reduce = s_lin, quad_cost_reduce = s_quad;
+    double ksq = 0.0;
+    for (int t = tid; t < H * nu; t += NT) ksq += ks[t] * ks[t];
+    const double ks_norm = sqrt(block_sum(ksq, s_red, tid));
+
+    // ---- line-search rollouts (ilqr.py:190-205): alpha j is rolled out by group j on its own, H sequential steps with
+    //      group barriers only; alphas beyond the number of groups are taken in further rounds
+    const int n_groups = NWARPS / G;
+    for (int j = grp; j < LS; j += n_groups) {
+      const int bar = 1 + (grp % 15);
+      double *h0 = s_h + (size_t)(grp % LS) * 2 * mw, *h1 = h0 + mw;
+      double *xs = ls_states + (size_t)j * (H + 1) * nx, *us = ls_ctrls + (size_t)j * H * nu;
+      const double alpha = P.alphas[j];
+      for (int a = gl; a < nx; a += gthr) xs[a] = P.x0[a];
+      group_sync(bar, gthr);
+      for (int i = 0; i < H; ++i) {
+        const double *xi = xs + (size_t)i * nx;
+        for (int a = gl; a < nu; a += gthr) {
+          double fb = 0.0;
+          for (int b = 0; b < nx; ++b) fb += Ks[((size_t)i * nu + a) * nx + b] * (xi[b] - states[(size_t)i * nx + b]);
+          double u = alpha * ks[(size_t)i * nu + a] + ctrls[(size_t)i * nu + a] + fb;
+          if (P.bounded) u = fmin(fmax(u, P.umin[a]), P.umax[a]);     // np.clip, ilqr.py:203-204
+          us[(size_t)i * nu + a] = u;
+        }
+        group_sync(bar, gthr);
+        for (int c = gl; c < n; c += gthr) {
+          const double v = c < nx ? xi[c] : us[(size_t)i * nu + (c - nx)];
+          h0[c] = (v - net.xu_mean[c]) / net.xu_std[c];
+        }
+        group_sync(bar, gthr);
+        const double *out = group_forward(net, h0, h1, gl, gthr, bar);
+        for (int a = gl; a < nx; a += gthr)
+          xs[(size_t)(i + 1) * nx + a] = xi[a] + (out[a] * net.dy_std[a] + net.dy_mean[a]);
+        group_sync(bar, gthr);
       }
-      __syncthreads();
-      for (int t = tid; t < LS * n; t += NT) {
-        const int j = t / n, c = t - j * n;
-        const double v = c < nx ? P.ls_states[((size_t)j * (H + 1) + i) * nx + c] : P.ls_ctrls[((size_t)j * H + i) * nu + (c - nx)];
-        P.hA[(size_t)j * mw + c] = (v - __ldg(net.xu_mean + c)) / __ldg(net.xu_std + c);
-      }
-      __syncthreads();
-      const double *out = ampc_mlp_f64_forward_batch(net, LS, P.hA, P.hB, mw, tid, NT);
-      for (int t = tid; t < LS * nx; t += NT) {
-        const int j = t / nx, a = t - j * nx;
-        P.ls_states[((size_t)j * (H + 1) + i + 1) * nx + a] =
-            P.ls_states[((size_t)j * (H + 1) + i) * nx + a] + (out[(size_t)j * mw + a] * __ldg(net.dy_std + a) + __ldg(net.dy_mean + a));
-      }
-      __syncthreads();
     }
+    __syncthreads();
     // objective of every alpha: per-step costs in parallel, then a sequential sum per alpha
     for (int t = tid; t < LS * (H + 1); t += NT) {
       const int j = t / (H + 1), i = t - j * (H + 1);
-      const double *xs = P.ls_states + (size_t)j * (H + 1) * nx, *us = P.ls_ctrls + (size_t)j * H * nu;
+      const double *xs = ls_states + (size_t)j * (H + 1) * nx, *us = ls_ctrls + (size_t)j * H * nu;
       double c;
       if (i < H) c = P.dt * (quad_form(P.Q, xs + (size_t)i * nx, P.goal, nx) + quad_form(P.R, us + (size_t)i * nu, nullptr, nu));
       else c = quad_form(P.F, xs + (size_t)H * nx, P.goalF, nx);
-      P.step_cost[(H + 1) + t] = c;
+      step_cost[(H + 1) + t] = c;
     }
     __syncthreads();
     if (tid < LS) {
       double o = 0.0;
-      for (int i = 0; i <= H; ++i) o += P.step_cost[(H + 1) + tid * (H + 1) + i];
+      for (int i = 0; i <= H; ++i) o += step_cost[(H + 1) + tid * (H + 1) + i];
       s_obj[tid] = o;
     }
     __syncthreads();
@@ -328,18 +452,24 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
     __syncthreads();
     if (s_flag[0]) { ls_fail = 1; break; }
     const int used = s_flag[1];
-    const double *nxs = P.ls_states + (size_t)used * (H + 1) * nx, *nus = P.ls_ctrls + (size_t)used * H * nu;
-    if (s_flag[2]) jac_batch(P, nxs, nus, tid);          // ilqr.py:232 (stale Jacobians otherwise, as in the reference)
+    const double *nxs = ls_states + (size_t)used * (H + 1) * nx, *nus = ls_ctrls + (size_t)used * H * nu;
+    if (s_flag[2]) jac_batch(P, net, nxs, nus, Jacs, tid);   // ilqr.py:232 (stale Jacobians otherwise, as in the reference)
     if (tid == 0) P.alpha_idx[itr] = used;
     double dsq = 0.0;
-    for (int t = tid; t < H * nu; t += NT) { const double d = nus[t] - P.ctrls[t]; dsq += d * d; }
+    for (int t = tid; t < H * nu; t += NT) { const double d = nus[t] - ctrls[t]; dsq += d * d; }
     const double du_norm = sqrt(block_sum(dsq, s_red, tid));   // ilqr.py:246
     if (du_norm < P.u_threshold) converged = 1;
-    for (int t = tid; t < (H + 1) * nx; t += NT) P.states[t] = nxs[t];
-    for (int t = tid; t < H * nu; t += NT) P.ctrls[t] = nus[t];
+    for (int t = tid; t < (H + 1) * nx; t += NT) states[t] = nxs[t];
+    for (int t = tid; t < H * nu; t += NT) ctrls[t] = nus[t];
     obj = s_obj[LS];
     __syncthreads();
     if (converged) break;
+  }
+  if (P.traj_smem) {                                     // outputs back to global memory
+    __syncthreads();
+    for (int t = tid; t < (H + 1) * nx; t += NT) P.states[t] = states[t];
+    for (int t = tid; t < H * nu; t += NT) { P.ctrls[t] = ctrls[t]; P.ks[t] = ks[t]; }
+    for (int t = tid; t < H * nu * nx; t += NT) P.Ks[t] = Ks[t];
   }
   if (tid == 0) { P.info[0] = converged; P.info[1] = n_iter; P.info[2] = ls_fail; }
 }
@@ -363,8 +493,8 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
   *out = nullptr;
   AMPC_REQUIRE(cfg->H >= 1 && cfg->nx >= 1 && cfg->nu >= 1 && cfg->nu <= MAX_NU, AMPC_ERR_INVALID,
                "bad iLQR dims H=%d nx=%d nu=%d (nu <= %d)", cfg->H, cfg->nx, cfg->nu, MAX_NU);
-  AMPC_REQUIRE(cfg->max_iter >= 1 && cfg->ls_max_iter >= 1 && cfg->ls_max_iter <= 32, AMPC_ERR_INVALID,
-               "bad iteration limits");
+  AMPC_REQUIRE(cfg->max_iter >= 1 && cfg->ls_max_iter >= 1 && cfg->ls_max_iter <= MAX_LS, AMPC_ERR_INVALID,
+               "bad iteration limits (1 <= ls_max_iter <= %d)", MAX_LS);
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   AMPC_REQUIRE(ce == cudaSuccess && ndev > 0, AMPC_ERR_CUDA, "no CUDA device: libampc_b200 has no CPU fallback (%s)",
@@ -409,7 +539,31 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
   P.ls_states = w + ols; P.ls_ctrls = w + olc; P.step_cost = w + osc;
   P.hA = w + ohA; P.hB = w + ohB; P.hG = w + ohG; P.JA = w + oJA; P.JB = w + oJB;
   P.info = h->d_int; P.alpha_idx = h->d_int + 3;
-  h->smem = ((size_t)n * n * 2 + (size_t)nx * nx * 3 + 2 * nx + (size_t)nx * n + n + (size_t)nu * nx + nu + NT / 32 + LS + 4) * sizeof(double);
+  {
+    // shared memory: the small matrices always; the network and the trajectories / gains / Jacobians / line-search
+    // rollouts when they fit next to them (the cartpole problem: 37 KB + 37 KB)
+    size_t fixed = (size_t)n * n * 2 + (size_t)nx * nx * 3 + 2 * nx + (size_t)nx * n + n + (size_t)nu * nx + nu +
+                   (size_t)nu * nu + NWARPS + LS + 4 + (size_t)LS * 2 * mw;
+    size_t netd = 2 * (size_t)(nx + nu) + 2 * (size_t)nx;
+    for (int l = 0; l < mlp->n_layers; ++l) netd += (size_t)mlp->dims[l] * mlp->dims[l + 1] + mlp->dims[l + 1];
+    const size_t traj = (size_t)(H + 1) * nx + (size_t)H * nu * 2 + (size_t)H * nu * nx + (size_t)H * nx * n +
+                        (size_t)LS * (H + 1) * nx + (size_t)LS * H * nu + (size_t)(LS + 1) * (H + 1);
+    int max_optin = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+    const size_t cap = (size_t)max_optin > 2048 ? ((size_t)max_optin - 2048) / sizeof(double) : 0;
+    P.net_doubles = netd;
+    P.net_blob = h->d_blob;
+    P.w_smem = (fixed + netd <= cap) ? 1 : 0;
+    if (P.w_smem) fixed += netd;
+    P.traj_smem = (fixed + traj <= cap) ? 1 : 0;
+    if (P.traj_smem) fixed += traj;
+    if (getenv("AMPC_ILQR_NO_SMEM")) {   // debugging / A-B: everything in global memory like the round-1 kernel
+      fixed -= (P.w_smem ? netd : 0) + (P.traj_smem ? traj : 0);
+      P.w_smem = P.traj_smem = 0;
+    }
+    h->smem = fixed * sizeof(double);
+    AMPC_REQUIRE(fixed <= cap || e != cudaSuccess, AMPC_ERR_UNSUPPORTED, "iLQR: %zu B of shared memory needed", h->smem);
+  }
   if (e == cudaSuccess) e = ampc_raise_smem_limit((const void *)ilqr_kernel, h->smem);
   if (e != cudaSuccess) {
     ampc_set_error("iLQR create: %s", cudaGetErrorString(e));
@@ -426,6 +580,17 @@ extern "C" int ampc_ilqr_destroy(ampc_ilqr *h) {
   cudaSetDevice(h->device);
   cudaFree(h->d_blob); cudaFree(h->d_work); cudaFree(h->d_int);
   delete h;
+  return AMPC_OK;
+}
+
+// Re-runs the solve on whatever x0 / uguess the last solve_host left on the device, asynchronously on `stream`: no
+// host copies.  Used to time the kernel alone (bench.py --workload c4); outputs stay on the device.
+extern "C" int ampc_ilqr_launch(ampc_ilqr *h, void *stream) {
+  AMPC_REQUIRE(h, AMPC_ERR_INVALID, "null handle");
+  AMPC_CUDA_CHECK(cudaSetDevice(h->device));
+  ilqr_kernel<<<1, NT, h->smem, (cudaStream_t)stream>>>(h->P);
+  ampc_count_launch();
+  AMPC_CUDA_CHECK(cudaGetLastError());
   return AMPC_OK;
 }
 

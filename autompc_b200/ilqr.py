@@ -95,6 +95,10 @@ class IterativeLQR(Controller):
                               alpha_idx=[int(a) for a in alpha if a >= 0])
         return bool(info[0]), states, ctrls, Ks, ks
 
+    def launch_device(self, stream=0):
+        """Re-runs the last solve's problem asynchronously on `stream` with no host copies (kernel-only timing)."""
+        _abi.check(_abi.lib().ampc_ilqr_launch(self._h, stream))
+
     def run(self, constate, new_obs, silent=True):                          # ilqr.py:267-295
         nu = self.system.ctrl_dim
         constate = np.asarray(constate)

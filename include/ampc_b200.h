@@ -236,7 +236,7 @@ typedef struct ampc_ilqr_cfg {
   double dt;
   int32_t bounded;         /* clip controls to [umin,umax] (ilqr.py:203-204)   */
   int32_t max_iter;        /* 50  */
-  int32_t ls_max_iter;     /* 10  */
+  int32_t ls_max_iter;     /* 10 (at most 20: one or two warps per line-search rollout) */
   double ls_discount;      /* 0.2 */
   double ls_cost_threshold;/* 0.3 */
   double u_threshold;      /* 1e-3 */
@@ -252,6 +252,9 @@ int ampc_ilqr_destroy(ampc_ilqr *h);
  *      alpha_idx (max_iter,) adopted line-search index per iteration (-1 past the end). */
 int ampc_ilqr_solve_host(ampc_ilqr *h, const double *x0, const double *uguess, double *states,
                          double *ctrls, double *Ks, double *ks, int32_t *info, int32_t *alpha_idx);
+/* The same solve again from the x0 the last solve_host call uploaded (uguess = zeros), asynchronous on `stream`, no
+ * host copies; results stay on the device.  Measurement hook: the kernel alone under CUDA events.               */
+int ampc_ilqr_launch(ampc_ilqr *h, void *stream);
 
 /* ------------------------------------------------------------------ misc --- */
 const char *ampc_last_error(void);
