@@ -80,6 +80,7 @@ EXPORTS = {
     "ampc_ilqr_destroy": [C.c_void_p],
     "ampc_ilqr_solve_host": [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
     "ampc_ilqr_launch": [C.c_void_p, C.c_void_p],
+    "ampc_ilqr_debug_profile": [C.c_void_p, C.POINTER(C.c_uint64)],
     "ampc_last_error": [],
     "ampc_version": [],
     "ampc_launch_count": [],

@@ -33,22 +33,38 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _obj_dir():
+    """Objects are cached OUTSIDE the repo (only the .so travels with the snapshot): a source whose object is newer
+    than the source and every header is not recompiled."""
+    d = os.environ.get("AMPC_OBJ_DIR", os.path.join("/tmp", "ampc_b200_obj"))
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def _fresh(obj, src):
+    if not os.path.exists(obj):
+        return False
+    t = os.path.getmtime(obj)
+    deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps += [os.path.join(os.path.dirname(HERE), "include", "ampc_b200.h"), os.path.abspath(__file__)]
+    return all(os.path.getmtime(d) <= t for d in deps)
+
+
 def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a (up to os.cpu_count() nvcc processes at a time) and link the library."""
     if not force and not needs_build():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    for f in os.listdir(LIB_DIR):                        # stale objects of an older source layout
-        if f.endswith(".o"):
-            os.remove(os.path.join(LIB_DIR, f))
-    jobs = [(src, os.path.join(LIB_DIR, src.replace(".cu", ".o")), []) for src in SOURCES]
+    odir = _obj_dir()
+    jobs = [(src, os.path.join(odir, src.replace(".cu", ".o")), []) for src in SOURCES]
     for cg, nxp, relu, f16, tr in TC_INSTANCES:
-        obj = os.path.join(LIB_DIR, "mppi_tc_inst_cg%d_nxp%d_relu%d_f16%d_trace%d.o" % (cg, nxp, relu, f16, tr))
+        obj = os.path.join(odir, "mppi_tc_inst_cg%d_nxp%d_relu%d_f16%d_trace%d.o" % (cg, nxp, relu, f16, tr))
         jobs.append(("mppi_tc_inst.cu", obj, ["-DAMPC_TC_INST_CG=%d" % cg, "-DAMPC_TC_INST_NXP=%d" % nxp,
                                               "-DAMPC_TC_INST_RELU=%d" % relu, "-DAMPC_TC_INST_F16=%d" % f16,
                                               "-DAMPC_TC_INST_TRACE=%d" % tr]))
     max_par = max(1, min(len(jobs), int(os.environ.get("AMPC_BUILD_JOBS", os.cpu_count() or 4))))
-    pending, running, objs = list(jobs), [], []
+    objs = [obj for _, obj, _ in jobs]
+    pending, running = [j for j in jobs if force or not _fresh(j[1], j[0])], []
 
     def reap(src, pr):
         out, _ = pr.communicate()
@@ -65,12 +81,9 @@ def build(force=False, verbose=False):
             cmd = [_nvcc()] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + [
                 "-c", os.path.join(CSRC, src), "-o", obj]
             running.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-            objs.append(obj)
         reap(*running.pop(0))
     cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
-    for obj in objs:                                     # only the .so travels with the repo snapshot
-        os.remove(obj)
     return LIB
 
 

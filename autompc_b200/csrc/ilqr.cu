@@ -34,10 +34,13 @@ struct IlqrParams {
   // scratch / outputs (device, global).  With traj_smem != 0 the kernel keeps the trajectories, gains, Jacobians and
   // line-search rollouts in shared memory instead and writes the outputs back once at the end.
   double *states, *ctrls, *Ks, *ks, *Jacs, *ls_states, *ls_ctrls, *step_cost;
-  double *hA, *hB, *hG, *JA, *JB;
+  double *hA;                      // global per-warp scratch of the Jacobian refresh (when it does not fit shared memory)
   int *info, *alpha_idx;
+  unsigned long long *prof;        // [0..5] cycles of thread 0 in: setup+init rollout, backward passes, line-search rollouts,
+                                   // objective + acceptance, Jacobian refreshes, copy-out; [6] = total, [7] = iterations
   int w_smem;                      // != 0: the network's weights and biases are staged into shared memory
   int traj_smem;
+  int jac_smem;                    // != 0: the per-warp scratch of the Jacobian refresh is shared memory (else hA)
   size_t net_doubles;              // weights + biases + normalisers as laid out by ampc_mlp_f64_upload
   const double *net_blob;
 };
@@ -78,6 +81,7 @@ __device__ __forceinline__ void step_costs(const IlqrParams &P, const double *xs
 __device__ __forceinline__ double dot_col_any(const double *Wt, int N, int j, const double *h, int Kin) {
   double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
   int k = 0;
+#pragma unroll 4
   for (; k + 4 <= Kin; k += 4) {
     p0 = fma(Wt[(size_t)(k + 0) * N + j], h[k + 0], p0);
     p1 = fma(Wt[(size_t)(k + 1) * N + j], h[k + 1], p1);
@@ -114,62 +118,79 @@ __device__ __forceinline__ const double *group_forward(const AmpcMlpF64 &net, do
 }
 
 // Jacobians of x' = x + dy(x,u) at (xs[i], us[i]) for i < H  ->  Jacs (H, nx, nx+nu)   (mlp.py:281-305)
-// All NT threads; scratch (hA, hB, hG, JA, JB) is global (L1/L2 resident), weights come through `net` (shared or global).
+// One WARP per sample (samples warp, warp + NWARPS, ...), warp barriers only.  Forward-mode propagation of the
+// [width x nin] panel through the layer stack; per layer a lane owns output rows j = lane, lane + 32, ... and keeps a
+// CB-column strip of its row in registers while it walks k, so a weight is loaded once per CB multiply-adds and the
+// previous panel's row k is a broadcast load.  `wk` = this warp's scratch: h0, h1, g (mw each) and two panels
+// (mw * nin each) -- shared memory when they fit, else a per-warp region of the global scratch.
+constexpr int JAC_CB = 8;
 __device__ void jac_batch(const IlqrParams &P, const AmpcMlpF64 &net, const double *xs, const double *us, double *Jacs,
-                          int tid) {
+                          double *wk, int warp, int lane) {
   const int nx = P.nx, nu = P.nu, nin = nx + nu, H = P.H, mw = net.max_width;
-  for (int t = tid; t < H * nin; t += NT) {
-    const int s = t / nin, j = t - s * nin;
-    const double v = j < nx ? xs[(size_t)s * nx + j] : us[(size_t)s * nu + (j - nx)];
-    P.hA[(size_t)s * mw + j] = (v - net.xu_mean[j]) / net.xu_std[j];
-  }
-  __syncthreads();
-  double *hin = P.hA, *hout = P.hB, *Jp = P.JA, *Jn = P.JB, *g = P.hG;
-  const int jstride = mw * nin;
-  for (int l = 0; l < net.n_layers; ++l) {
-    const int Kin = net.dims[l], N = net.dims[l + 1];
-    const bool last = (l == net.n_layers - 1);
-    for (int t = tid; t < H * N; t += NT) {
-      const int s = t / N, j = t - s * N;
-      const double y = net.b[l][j] + dot_col_any(net.Wt[l], N, j, hin + (size_t)s * mw, Kin);
-      hout[(size_t)s * mw + j] = last ? y : ampc_act<double>(net.act, y);
-      g[(size_t)s * mw + j] = last ? 1.0 : ampc_act_grad<double>(net.act, y);
+  double *h0 = wk, *h1 = h0 + mw, *g = h1 + mw, *J0 = g + mw, *J1 = J0 + (size_t)mw * nin;
+  for (int s = warp; s < H; s += NWARPS) {
+    for (int j = lane; j < nin; j += 32) {
+      const double v = j < nx ? xs[(size_t)s * nx + j] : us[(size_t)s * nu + (j - nx)];
+      h0[j] = (v - net.xu_mean[j]) / net.xu_std[j];
     }
-    __syncthreads();
-    const int per = N * nin;
-    for (int t = tid; t < H * per; t += NT) {
-      const int s = t / per, r = t - s * per;
-      const int c = r / N, j = r - c * N;   // j fastest: neighbouring threads read neighbouring weights
-      const double *jp = Jp + (size_t)s * jstride;
-      double v;
-      if (l == 0) {
-        v = net.Wt[0][(size_t)c * N + j] / net.xu_std[c];
-      } else {
-        double p0 = 0.0, p1 = 0.0;
-        int k = 0;
-        for (; k + 2 <= Kin; k += 2) {
-          p0 = fma(net.Wt[l][(size_t)k * N + j], jp[(size_t)k * nin + c], p0);
-          p1 = fma(net.Wt[l][(size_t)(k + 1) * N + j], jp[(size_t)(k + 1) * nin + c], p1);
-        }
-        if (k < Kin) p0 = fma(net.Wt[l][(size_t)k * N + j], jp[(size_t)k * nin + c], p0);
-        v = p0 + p1;
+    __syncwarp();
+    double *hin = h0, *hout = h1, *Jp = J0, *Jn = J1;
+    for (int l = 0; l < net.n_layers; ++l) {
+      const int Kin = net.dims[l], N = net.dims[l + 1];
+      const bool last = (l == net.n_layers - 1);
+      const double *Wt = net.Wt[l];
+      for (int j = lane; j < N; j += 32) {
+        const double y = net.b[l][j] + dot_col_any(Wt, N, j, hin, Kin);
+        hout[j] = last ? y : ampc_act<double>(net.act, y);
+        g[j] = last ? 1.0 : ampc_act_grad<double>(net.act, y);
       }
-      Jn[(size_t)s * jstride + (size_t)j * nin + c] = v * g[(size_t)s * mw + j];
+      __syncwarp();
+      for (int j = lane; j < N; j += 32) {
+        const double gj = g[j];
+        if (l == 0) {
+          for (int c = 0; c < nin; ++c) Jn[(size_t)j * nin + c] = Wt[(size_t)c * N + j] / net.xu_std[c] * gj;
+        } else {
+          for (int c0 = 0; c0 < nin; c0 += JAC_CB) {
+            double acc0[JAC_CB], acc1[JAC_CB];          // even / odd k, like the two partial sums of the batch routine
+#pragma unroll
+            for (int q = 0; q < JAC_CB; ++q) { acc0[q] = 0.0; acc1[q] = 0.0; }
+            int k = 0;
+            for (; k + 2 <= Kin; k += 2) {
+              const double w0 = Wt[(size_t)k * N + j], w1 = Wt[(size_t)(k + 1) * N + j];
+              const double *r0 = Jp + (size_t)k * nin + c0, *r1 = r0 + nin;
+#pragma unroll
+              for (int q = 0; q < JAC_CB; ++q)
+                if (c0 + q < nin) { acc0[q] = fma(w0, r0[q], acc0[q]); acc1[q] = fma(w1, r1[q], acc1[q]); }
+            }
+            if (k < Kin) {
+              const double w0 = Wt[(size_t)k * N + j];
+              const double *r0 = Jp + (size_t)k * nin + c0;
+#pragma unroll
+              for (int q = 0; q < JAC_CB; ++q)
+                if (c0 + q < nin) acc0[q] = fma(w0, r0[q], acc0[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < JAC_CB; ++q)
+              if (c0 + q < nin) Jn[(size_t)j * nin + c0 + q] = (acc0[q] + acc1[q]) * gj;
+          }
+        }
+      }
+      __syncwarp();
+      double *t2 = hin; hin = hout; hout = t2;
+      double *t3 = Jp; Jp = Jn; Jn = t3;
     }
-    __syncthreads();
-    double *t2 = hin; hin = hout; hout = t2;
-    double *t3 = Jp; Jp = Jn; Jn = t3;
-  }
-  for (int t = tid; t < H * nx * nin; t += NT) {
-    const int s = t / (nx * nin), r = t - s * (nx * nin);
-    const int a = r / nin, c = r - a * nin;
-    Jacs[t] = Jp[(size_t)s * jstride + r] * net.dy_std[a] + ((c == a) ? 1.0 : 0.0);
+    for (int r = lane; r < nx * nin; r += 32) {
+      const int a = r / nin, c = r - a * nin;
+      Jacs[(size_t)s * nx * nin + r] = Jp[r] * net.dy_std[a] + ((c == a) ? 1.0 : 0.0);
+    }
+    __syncwarp();
   }
   __syncthreads();
 }
 
 __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
   extern __shared__ double sm[];
+  const long long t_entry = clock64();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nx = P.nx, nu = P.nu, n = nx + nu, H = P.H, LS = P.ls_max_iter, mw = P.net.max_width;
   // line-search groups: G warps per alpha (2 when they fit), group j = warps [j*G, (j+1)*G)
@@ -224,6 +245,10 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
     step_cost = s_next; s_next += (size_t)(LS + 1) * (H + 1);
   }
 
+  // per-warp scratch of the Jacobian refresh
+  const size_t jac_per_warp = 3 * (size_t)mw + 2 * (size_t)mw * n;
+  double *jac_wk = P.jac_smem ? s_next + (size_t)warp * jac_per_warp : P.hA + (size_t)warp * jac_per_warp;
+
   for (int t = tid; t < n * n; t += NT) {
     const int r = t / n, c = t - r * n;
     double v = 0.0;
@@ -256,13 +281,18 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
     }
   }
   __syncthreads();
-  jac_batch(P, net, states, ctrls, Jacs, tid);
+  jac_batch(P, net, states, ctrls, Jacs, jac_wk, warp, lane);
   step_costs(P, states, ctrls, step_cost, tid, NT);
   __syncthreads();
   double obj = 0.0;       // every thread tracks the same scalars (uniform control flow)
   for (int i = 0; i <= H; ++i) obj += step_cost[i];     // sequential like eval_obj, ilqr.py:124-129
   __syncthreads();
 
+  long long t_mark = clock64();
+  const long long t_begin = t_entry;
+  unsigned long long cyc[6] = {0, 0, 0, 0, 0, 0};
+  auto lap = [&](int slot) { const long long now = clock64(); cyc[slot] += (unsigned long long)(now - t_mark); t_mark = now; };
+  cyc[0] = (unsigned long long)(t_mark - t_begin);
   int converged = 0, n_iter = 0, ls_fail = 0;
   for (int itr = 0; itr < P.max_iter; ++itr) {
     n_iter = itr + 1;
@@ -372,6 +402,7 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
       if (lane == 0) { s_lin = lin_acc; s_quad = quad_acc; }
     }
     __syncthreads();
+    lap(1);
     const double lin_cost_reduce = s_lin, quad_cost_reduce = s_quad;
     double ksq = 0.0;
     for (int t = tid; t < H * nu; t += NT) ksq += ks[t] * ks[t];
@@ -409,6 +440,7 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
       }
     }
     __syncthreads();
+    lap(2);
     // objective of every alpha: per-step costs in parallel, then a sequential sum per alpha
     for (int t = tid; t < LS * (H + 1); t += NT) {
       const int j = t / (H + 1), i = t - j * (H + 1);
@@ -450,10 +482,12 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
       s_obj[LS] = new_obj;
     }
     __syncthreads();
+    lap(3);
     if (s_flag[0]) { ls_fail = 1; break; }
     const int used = s_flag[1];
     const double *nxs = ls_states + (size_t)used * (H + 1) * nx, *nus = ls_ctrls + (size_t)used * H * nu;
-    if (s_flag[2]) jac_batch(P, net, nxs, nus, Jacs, tid);   // ilqr.py:232 (stale Jacobians otherwise, as in the reference)
+    if (s_flag[2]) jac_batch(P, net, nxs, nus, Jacs, jac_wk, warp, lane);   // ilqr.py:232 (stale Jacobians otherwise, as in the reference)
+    lap(4);
     if (tid == 0) P.alpha_idx[itr] = used;
     double dsq = 0.0;
     for (int t = tid; t < H * nu; t += NT) { const double d = nus[t] - ctrls[t]; dsq += d * d; }
@@ -463,6 +497,7 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
     for (int t = tid; t < H * nu; t += NT) ctrls[t] = nus[t];
     obj = s_obj[LS];
     __syncthreads();
+    lap(3);
     if (converged) break;
   }
   if (P.traj_smem) {                                     // outputs back to global memory
@@ -471,7 +506,13 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
     for (int t = tid; t < H * nu; t += NT) { P.ctrls[t] = ctrls[t]; P.ks[t] = ks[t]; }
     for (int t = tid; t < H * nu * nx; t += NT) P.Ks[t] = Ks[t];
   }
-  if (tid == 0) { P.info[0] = converged; P.info[1] = n_iter; P.info[2] = ls_fail; }
+  if (tid == 0) {
+    P.info[0] = converged; P.info[1] = n_iter; P.info[2] = ls_fail;
+    lap(5);
+    for (int q = 0; q < 6; ++q) P.prof[q] = cyc[q];
+    P.prof[6] = (unsigned long long)(clock64() - t_begin);
+    P.prof[7] = (unsigned long long)n_iter;
+  }
 }
 
 }  // namespace
@@ -483,6 +524,7 @@ struct ampc_ilqr {
   double *d_blob = nullptr;   // MLP weights
   double *d_work = nullptr;   // everything else
   int *d_int = nullptr;
+  unsigned long long *d_prof = nullptr;
   size_t smem = 0;
   size_t o_x0 = 0, o_ug = 0;
 };
@@ -512,7 +554,6 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
   P.H = H; P.nx = nx; P.nu = nu; P.bounded = cfg->bounded; P.max_iter = cfg->max_iter; P.ls_max_iter = LS;
   P.dt = cfg->dt; P.ls_discount = cfg->ls_discount; P.ls_cost_threshold = cfg->ls_cost_threshold;
   P.u_threshold = cfg->u_threshold;
-  const int nb = H > LS ? H : LS;   // widest MLP batch (Jacobian refresh over H steps / LS line-search rollouts)
   size_t off = 0;
   auto take = [&](size_t cnt) { size_t o = off; off += (cnt + 1) & ~(size_t)1; return o; };
   const size_t oQ = take(nx * nx), oR = take(nu * nu), oF = take(nx * nx), og = take(nx), ogF = take(nx), oumin = take(nu), oumax = take(nu), oal = take(LS);
@@ -520,11 +561,13 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
   const size_t ost = take((size_t)(H + 1) * nx), oct = take((size_t)H * nu), oKs = take((size_t)H * nu * nx), oks = take((size_t)H * nu);
   const size_t oJ = take((size_t)H * nx * n), ols = take((size_t)LS * (H + 1) * nx), olc = take((size_t)LS * H * nu);
   const size_t osc = take((size_t)(LS + 1) * (H + 1));
-  const size_t ohA = take((size_t)nb * mw), ohB = take((size_t)nb * mw), ohG = take((size_t)nb * mw);
-  const size_t oJA = take((size_t)H * mw * n), oJB = take((size_t)H * mw * n);
+  const size_t jac_per_warp = 3 * (size_t)mw + 2 * (size_t)mw * n;
+  const size_t ohA = take((size_t)NWARPS * jac_per_warp);
   cudaError_t e = cudaMalloc(&h->d_work, off * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(h->d_work, 0, off * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&h->d_int, (3 + cfg->max_iter) * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_prof, 8 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->d_prof, 0, 8 * sizeof(unsigned long long));
   std::vector<double> hc(h->o_x0, 0.0);
   for (int i = 0; i < nx * nx; ++i) { hc[oQ + i] = cost->Q[i]; hc[oF + i] = cost->F[i]; }
   for (int i = 0; i < nu * nu; ++i) hc[oR + i] = cost->R[i];
@@ -537,8 +580,8 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
   P.x0 = w + h->o_x0; P.uguess = nullptr;
   P.states = w + ost; P.ctrls = w + oct; P.Ks = w + oKs; P.ks = w + oks; P.Jacs = w + oJ;
   P.ls_states = w + ols; P.ls_ctrls = w + olc; P.step_cost = w + osc;
-  P.hA = w + ohA; P.hB = w + ohB; P.hG = w + ohG; P.JA = w + oJA; P.JB = w + oJB;
-  P.info = h->d_int; P.alpha_idx = h->d_int + 3;
+  P.hA = w + ohA;
+  P.info = h->d_int; P.alpha_idx = h->d_int + 3; P.prof = h->d_prof;
   {
     // shared memory: the small matrices always; the network and the trajectories / gains / Jacobians / line-search
     // rollouts when they fit next to them (the cartpole problem: 37 KB + 37 KB)
@@ -557,9 +600,12 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
     if (P.w_smem) fixed += netd;
     P.traj_smem = (fixed + traj <= cap) ? 1 : 0;
     if (P.traj_smem) fixed += traj;
+    const size_t jacs = (size_t)NWARPS * jac_per_warp;
+    P.jac_smem = (fixed + jacs <= cap) ? 1 : 0;
+    if (P.jac_smem) fixed += jacs;
     if (getenv("AMPC_ILQR_NO_SMEM")) {   // debugging / A-B: everything in global memory like the round-1 kernel
-      fixed -= (P.w_smem ? netd : 0) + (P.traj_smem ? traj : 0);
-      P.w_smem = P.traj_smem = 0;
+      fixed -= (P.w_smem ? netd : 0) + (P.traj_smem ? traj : 0) + (P.jac_smem ? jacs : 0);
+      P.w_smem = P.traj_smem = P.jac_smem = 0;
     }
     h->smem = fixed * sizeof(double);
     AMPC_REQUIRE(fixed <= cap || e != cudaSuccess, AMPC_ERR_UNSUPPORTED, "iLQR: %zu B of shared memory needed", h->smem);
@@ -567,7 +613,7 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
   if (e == cudaSuccess) e = ampc_raise_smem_limit((const void *)ilqr_kernel, h->smem);
   if (e != cudaSuccess) {
     ampc_set_error("iLQR create: %s", cudaGetErrorString(e));
-    cudaFree(h->d_blob); cudaFree(h->d_work); cudaFree(h->d_int);
+    cudaFree(h->d_blob); cudaFree(h->d_work); cudaFree(h->d_int); cudaFree(h->d_prof);
     delete h;
     return AMPC_ERR_CUDA;
   }
@@ -578,8 +624,17 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
 extern "C" int ampc_ilqr_destroy(ampc_ilqr *h) {
   if (!h) return AMPC_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_blob); cudaFree(h->d_work); cudaFree(h->d_int);
+  cudaFree(h->d_blob); cudaFree(h->d_work); cudaFree(h->d_int); cudaFree(h->d_prof);
   delete h;
+  return AMPC_OK;
+}
+
+// Debug tap, no reference counterpart: SM cycles thread 0 of the last solve spent per phase (see IlqrParams::prof).
+extern "C" int ampc_ilqr_debug_profile(ampc_ilqr *h, unsigned long long *out8) {
+  AMPC_REQUIRE(h && out8, AMPC_ERR_INVALID, "null argument");
+  AMPC_CUDA_CHECK(cudaSetDevice(h->device));
+  AMPC_CUDA_CHECK(cudaDeviceSynchronize());
+  AMPC_CUDA_CHECK(cudaMemcpy(out8, h->d_prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return AMPC_OK;
 }
 

@@ -86,6 +86,7 @@ struct ampc_mppi {
   float *d_box = nullptr;          // rollout kernels: n_box x [lo (nx) | hi (nx) | weight], float32
   int n_box = 0;
   double *d_evalbox = nullptr;     // closed loop's trajectory cost: the same layout in float64
+  size_t evalbox_cap = 0;          // doubles allocated at d_evalbox
   int n_evalbox = 0;
   bool eval_cost_set = false;      // ampc_mppi_set_eval_cost was called: h_cost / d_evalbox no longer follow the controller's cost
 };
@@ -478,6 +479,8 @@ int pack_box(int nx, int32_t n_terms, const double *lo, const double *hi, const 
 }
 }  // namespace
 
+static int upload_evalbox(ampc_mppi *h, const std::vector<double> &blk, int n_terms);
+
 extern "C" int ampc_mppi_set_box_costs(ampc_mppi *h, int32_t n_terms, const double *lo, const double *hi,
                                        const double *weight) {
   AMPC_REQUIRE(h, AMPC_ERR_INVALID, "null handle");
@@ -498,15 +501,27 @@ extern "C" int ampc_mppi_set_box_costs(ampc_mppi *h, int32_t n_terms, const doub
     std::vector<double> blk64;
     rc = pack_box<double>(h->cfg.nx, n_terms, lo, hi, weight, &blk64);
     if (rc) return rc;
-    cudaFree(h->d_evalbox);
-    h->d_evalbox = nullptr;
-    h->n_evalbox = 0;
-    if (n_terms > 0) {
-      AMPC_CUDA_CHECK(cudaMalloc(&h->d_evalbox, blk64.size() * sizeof(double)));
-      AMPC_CUDA_CHECK(cudaMemcpy(h->d_evalbox, blk64.data(), blk64.size() * sizeof(double), cudaMemcpyHostToDevice));
-      h->n_evalbox = n_terms;
-    }
+    return upload_evalbox(h, blk64, n_terms);
   }
+  return AMPC_OK;
+}
+
+// (re)fills a device block without a device-wide synchronisation when it already has the capacity (cudaFree would
+// wait for every closed loop in flight on the other handles' streams)
+static int upload_evalbox(ampc_mppi *h, const std::vector<double> &blk, int n_terms) {
+  if (n_terms > 0) {
+    if (h->evalbox_cap < blk.size()) {
+      cudaFree(h->d_evalbox);
+      h->d_evalbox = nullptr;
+      h->evalbox_cap = 0;
+      const size_t cap = (size_t)AMPC_MAX_BOX_TERMS * (2 * h->cfg.nx + 1);
+      AMPC_CUDA_CHECK(cudaMalloc(&h->d_evalbox, cap * sizeof(double)));
+      h->evalbox_cap = cap;
+    }
+    // pageable source: the copy is staged before the call returns, `blk` may go out of scope
+    AMPC_CUDA_CHECK(cudaMemcpyAsync(h->d_evalbox, blk.data(), blk.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  h->n_evalbox = n_terms;
   return AMPC_OK;
 }
 
@@ -518,7 +533,6 @@ extern "C" int ampc_mppi_set_eval_cost(ampc_mppi *h, const ampc_quad_cost *quad,
   std::vector<double> blk64;
   int rc = pack_box<double>(nx, n_terms, lo, hi, weight, &blk64);
   if (rc) return rc;
-  AMPC_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   std::vector<double> hc((size_t)2 * nx * nx + (size_t)nu * nu + 2 * (size_t)nx, 0.0);
   if (quad) {
     AMPC_REQUIRE(quad->Q && quad->R && quad->F && quad->goal, AMPC_ERR_INVALID, "null cost matrix");
@@ -529,17 +543,9 @@ extern "C" int ampc_mppi_set_eval_cost(ampc_mppi *h, const ampc_quad_cost *quad,
     memcpy(q, quad->goal, sizeof(double) * nx); q += nx;
     memcpy(q, quad->goal_term ? quad->goal_term : quad->goal, sizeof(double) * nx);
   }
-  h->h_cost = hc;
+  h->h_cost = hc;                       // read by the next closed_loop_start (stream-ordered after this call)
   h->eval_cost_set = true;
-  cudaFree(h->d_evalbox);
-  h->d_evalbox = nullptr;
-  h->n_evalbox = 0;
-  if (n_terms > 0) {
-    AMPC_CUDA_CHECK(cudaMalloc(&h->d_evalbox, blk64.size() * sizeof(double)));
-    AMPC_CUDA_CHECK(cudaMemcpy(h->d_evalbox, blk64.data(), blk64.size() * sizeof(double), cudaMemcpyHostToDevice));
-    h->n_evalbox = n_terms;
-  }
-  return AMPC_OK;
+  return upload_evalbox(h, blk64, n_terms);
 }
 
 extern "C" int ampc_mppi_get_costs(ampc_mppi *h, double *host_costs, double *term_const) {

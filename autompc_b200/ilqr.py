@@ -99,6 +99,14 @@ class IterativeLQR(Controller):
         """Re-runs the last solve's problem asynchronously on `stream` with no host copies (kernel-only timing)."""
         _abi.check(_abi.lib().ampc_ilqr_launch(self._h, stream))
 
+    def debug_profile(self):
+        """SM cycles the last solve spent per phase (debug tap of the kernel)."""
+        out = (C.c_uint64 * 8)()
+        _abi.check(_abi.lib().ampc_ilqr_debug_profile(self._h, out))
+        names = ("setup_init_rollout", "backward", "line_search", "objective_accept", "jacobian", "copy_out", "total",
+                 "iterations")
+        return dict(zip(names, [int(v) for v in out]))
+
     def run(self, constate, new_obs, silent=True):                          # ilqr.py:267-295
         nu = self.system.ctrl_dim
         constate = np.asarray(constate)

