@@ -5,45 +5,77 @@
 //   init rollout (:141-149)  ->  up to max_iter x [ backward Riccati (:159-187),
 //   batched ls_max_iter-alpha line search (:197-225), Jacobian refresh (:226-234),
 //   stopping rule (:235-261) ].
-// The problem is tiny and strictly sequential in H (state recursion forward,
-// value recursion backward), so the whole solve is ONE launch: no host round
-// trips between the ~50 x (H Riccati steps + H line-search steps) stages the
-// reference walks in Python.  float64 keeps the integer outputs (adopted
-// line-search index per iteration, iteration count, converged) equal to the
-// reference's.  The small (nx+nu)^2 value / gain matrices live in shared memory;
-// trajectories, gains and the per-step Jacobian panels live in a global scratch
-// that stays in L1/L2.
+// The problem is tiny and strictly sequential in H (state recursion forward, value recursion backward), so the whole
+// solve is ONE launch: no host round trips between the ~50 x (H Riccati steps + H line-search steps) stages the
+// reference walks in Python.  float64 keeps the integer outputs (adopted line-search index per iteration, iteration
+// count, converged) equal to the reference's.
+//
+// Work decomposition inside the CTA (20 warps):
+//   * backward pass: ONE warp, warp barriers only -- the matrices are (nx+nu)^2; (row, column) of every element comes
+//     from small index tables instead of integer divisions;
+//   * line search: alpha j is rolled out by its own group of 1-2 warps for all H steps with group barriers only (the
+//     reference batches the alphas per step, ilqr.py:197-205: same numbers, no block-wide barrier per step);
+//   * Jacobian refresh (mlp.py:281-305 in closed form): one warp per horizon step, forward-mode propagation of the
+//     [width x (nx+nu)] panel with a strip of each row held in registers.
+// Data placement (template RES): when the network (row-major, rows padded to an odd stride so that lane j reading row j
+// is bank-conflict free), the trajectories / gains / Jacobians / line-search rollouts and the per-warp Jacobian scratch
+// all fit in shared memory (the cartpole problem: 38 + 37 + 66 KB) they live there and every pointer is derived from
+// the shared array, so the compiler emits LDS/STS with immediate offsets; otherwise the same code runs on global
+// scratch.  (ncu on the round-2 first cut, which passed shared and global pointers through one struct: 111 M warp
+// instructions per solve of which 10 M were DFMA -- 64-bit generic address arithmetic was the kernel.)
 #include <vector>
 
 #include "ampc_common.cuh"
-#include "mlp_f64.cuh"
 
 namespace {
 
-constexpr int NT = 640;            // 20 warps: warp 0 runs the Riccati recursion, line-search rollouts use G warps each
+constexpr int NT = 640;            // 20 warps
 constexpr int NWARPS = NT / 32;
+constexpr int JAC_WARPS = 10;      // warps that take part in the Jacobian refresh (bounds its shared-memory scratch)
 constexpr int MAX_NU = 16;
 constexpr int MAX_LS = 20;
+constexpr int MAXL = AMPC_MAX_LAYERS;
+
+struct IlqrNet {                   // offsets in doubles from the base of the network blob
+  int n_layers, act, max_width, total;
+  int dims[MAXL + 1];
+  int woff[MAXL], wstride[MAXL], boff[MAXL];   // W_l row-major (out, in) with row stride wstride (odd)
+  int xu_mean, xu_std, dy_mean, dy_std;
+};
 
 struct IlqrParams {
-  AmpcMlpF64 net;
+  IlqrNet net;
+  const double *net_blob;          // global copy of the blob
   int H, nx, nu, bounded, max_iter, ls_max_iter;
   double dt, ls_discount, ls_cost_threshold, u_threshold;
-  const double *Q, *R, *F, *goal, *goalF, *umin, *umax, *alphas;   // device (goalF: goal of the terminal term)
-  const double *x0, *uguess;                       // device (uguess may be null)
-  // scratch / outputs (device, global).  With traj_smem != 0 the kernel keeps the trajectories, gains, Jacobians and
-  // line-search rollouts in shared memory instead and writes the outputs back once at the end.
-  double *states, *ctrls, *Ks, *ks, *Jacs, *ls_states, *ls_ctrls, *step_cost;
-  double *hA;                      // global per-warp scratch of the Jacobian refresh (when it does not fit shared memory)
+  const double *cst;               // global: Q | R | F | goal | goalF | umin | umax | alphas
+  const double *x0, *uguess;       // global (uguess may be null)
+  double *traj;                    // global scratch for the trajectory block when it is not shared-memory resident
+  double *jac_work;                // global per-warp scratch of the Jacobian refresh (ditto)
+  double *states, *ctrls, *Ks, *ks;   // outputs (global)
   int *info, *alpha_idx;
   unsigned long long *prof;        // [0..5] cycles of thread 0 in: setup+init rollout, backward passes, line-search rollouts,
                                    // objective + acceptance, Jacobian refreshes, copy-out; [6] = total, [7] = iterations
-  int w_smem;                      // != 0: the network's weights and biases are staged into shared memory
-  int traj_smem;
-  int jac_smem;                    // != 0: the per-warp scratch of the Jacobian refresh is shared memory (else hA)
-  size_t net_doubles;              // weights + biases + normalisers as laid out by ampc_mlp_f64_upload
-  const double *net_blob;
 };
+
+// offsets inside the trajectory block
+struct TrajLayout {
+  size_t states, ctrls, Ks, ks, Jacs, ls_states, ls_ctrls, step_cost, total;
+  __host__ __device__ TrajLayout(int H, int nx, int nu, int LS) {
+    const size_t n = nx + nu;
+    size_t o = 0;
+    auto take = [&](size_t c) { size_t r = o; o += (c + 1) & ~(size_t)1; return r; };
+    states = take((size_t)(H + 1) * nx); ctrls = take((size_t)H * nu); Ks = take((size_t)H * nu * nx);
+    ks = take((size_t)H * nu); Jacs = take((size_t)H * nx * n); ls_states = take((size_t)LS * (H + 1) * nx);
+    ls_ctrls = take((size_t)LS * H * nu); step_cost = take((size_t)(LS + 1) * (H + 1));
+    total = o;
+  }
+};
+
+__host__ __device__ inline size_t jac_per_warp(int mw, int n) { return 3 * (size_t)mw + 2 * (size_t)mw * n + 2; }
+__host__ __device__ inline size_t cst_doubles(int nx, int nu, int LS) {
+  return 2 * (size_t)nx * nx + (size_t)nu * nu + 2 * (size_t)nx + 2 * (size_t)nu + LS;
+}
 
 __device__ __forceinline__ double block_sum(double v, double *s_red, int tid) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -66,29 +98,29 @@ __device__ __forceinline__ double quad_form(const double *M, const double *x, co
   return tot;
 }
 
-// per-step cost table for trajectory (xs (H+1,nx), us (H,nu)): c[i] = dt*(obs+ctrl), c[H] = terminal
-__device__ __forceinline__ void step_costs(const IlqrParams &P, const double *xs, const double *us, double *c,
-                                           int tid, int stride_thr) {
-  for (int i = tid; i <= P.H; i += stride_thr) {
-    if (i < P.H)
-      c[i] = P.dt * (quad_form(P.Q, xs + (size_t)i * P.nx, P.goal, P.nx) + quad_form(P.R, us + (size_t)i * P.nu, nullptr, P.nu));
-    else
-      c[i] = quad_form(P.F, xs + (size_t)P.H * P.nx, P.goalF, P.nx);
-  }
-}
-
-// dot(Wt[:, j], h), four partial sums like ampc_dot_col but with plain loads: Wt may be shared OR global memory
-__device__ __forceinline__ double dot_col_any(const double *Wt, int N, int j, const double *h, int Kin) {
+// dot(W[j, :], h): the row is contiguous; four partial sums over k mod 4 and a tail into the first one (the summation
+// order of every float64 MLP routine of this library, so results are bit-identical across them)
+__device__ __forceinline__ double dot_row(const double *__restrict__ w, const double *__restrict__ h, int Kin) {
   double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
   int k = 0;
-#pragma unroll 4
-  for (; k + 4 <= Kin; k += 4) {
-    p0 = fma(Wt[(size_t)(k + 0) * N + j], h[k + 0], p0);
-    p1 = fma(Wt[(size_t)(k + 1) * N + j], h[k + 1], p1);
-    p2 = fma(Wt[(size_t)(k + 2) * N + j], h[k + 2], p2);
-    p3 = fma(Wt[(size_t)(k + 3) * N + j], h[k + 3], p3);
+  for (; k + 8 <= Kin; k += 8) {
+    p0 = fma(w[k + 0], h[k + 0], p0);
+    p1 = fma(w[k + 1], h[k + 1], p1);
+    p2 = fma(w[k + 2], h[k + 2], p2);
+    p3 = fma(w[k + 3], h[k + 3], p3);
+    p0 = fma(w[k + 4], h[k + 4], p0);
+    p1 = fma(w[k + 5], h[k + 5], p1);
+    p2 = fma(w[k + 6], h[k + 6], p2);
+    p3 = fma(w[k + 7], h[k + 7], p3);
   }
-  for (; k < Kin; ++k) p0 = fma(Wt[(size_t)k * N + j], h[k], p0);
+  if (k + 4 <= Kin) {
+    p0 = fma(w[k + 0], h[k + 0], p0);
+    p1 = fma(w[k + 1], h[k + 1], p1);
+    p2 = fma(w[k + 2], h[k + 2], p2);
+    p3 = fma(w[k + 3], h[k + 3], p3);
+    k += 4;
+  }
+  for (; k < Kin; ++k) p0 = fma(w[k], h[k], p0);
   return (p0 + p1) + (p2 + p3);
 }
 
@@ -99,16 +131,17 @@ __device__ __forceinline__ void group_sync(int id, int nthr) {
 }
 
 // One MLP forward for ONE sample by a group of `gthr` threads (`gl` = rank inside the group): h0 holds the z-scored
-// input, h0/h1 ping-pong (shared memory), returns the buffer with the raw outputs.  Same arithmetic per output as
-// ampc_mlp_f64_forward_batch (bit-identical results).
-__device__ __forceinline__ const double *group_forward(const AmpcMlpF64 &net, double *h0, double *h1, int gl, int gthr,
-                                                       int bar) {
+// input, h0/h1 ping-pong (shared memory), returns the buffer with the raw outputs  (mlp.py:55-59).
+__device__ __forceinline__ const double *group_forward(const IlqrNet &net, const double *nb, double *h0, double *h1, int gl,
+                                                       int gthr, int bar) {
   double *hin = h0, *hout = h1;
+#pragma unroll 1
   for (int l = 0; l < net.n_layers; ++l) {
-    const int Kin = net.dims[l], N = net.dims[l + 1];
+    const int Kin = net.dims[l], N = net.dims[l + 1], ws = net.wstride[l];
     const bool last = (l == net.n_layers - 1);
+    const double *W = nb + net.woff[l], *B = nb + net.boff[l];
     for (int j = gl; j < N; j += gthr) {
-      const double y = net.b[l][j] + dot_col_any(net.Wt[l], N, j, hin, Kin);
+      const double y = B[j] + dot_row(W + (size_t)j * ws, hin, Kin);
       hout[j] = last ? y : ampc_act<double>(net.act, y);
     }
     group_sync(bar, gthr);
@@ -118,86 +151,101 @@ __device__ __forceinline__ const double *group_forward(const AmpcMlpF64 &net, do
 }
 
 // Jacobians of x' = x + dy(x,u) at (xs[i], us[i]) for i < H  ->  Jacs (H, nx, nx+nu)   (mlp.py:281-305)
-// One WARP per sample (samples warp, warp + NWARPS, ...), warp barriers only.  Forward-mode propagation of the
+// One WARP per sample (samples warp, warp + JAC_WARPS, ...), warp barriers only.  Forward-mode propagation of the
 // [width x nin] panel through the layer stack; per layer a lane owns output rows j = lane, lane + 32, ... and keeps a
-// CB-column strip of its row in registers while it walks k, so a weight is loaded once per CB multiply-adds and the
-// previous panel's row k is a broadcast load.  `wk` = this warp's scratch: h0, h1, g (mw each) and two panels
-// (mw * nin each) -- shared memory when they fit, else a per-warp region of the global scratch.
+// CB-column strip of its row in registers while it walks k: its weights are a contiguous row, the previous panel's row
+// k is a broadcast load.  `wk` = this warp's scratch: h0, h1, g (mw each) and two panels (mw * nin each).
 constexpr int JAC_CB = 8;
-__device__ void jac_batch(const IlqrParams &P, const AmpcMlpF64 &net, const double *xs, const double *us, double *Jacs,
-                          double *wk, int warp, int lane) {
+__device__ void jac_batch(const IlqrParams &P, const double *nb, const double *xs, const double *us, double *Jacs, double *wk,
+                          int warp, int lane) {
+  const IlqrNet &net = P.net;
   const int nx = P.nx, nu = P.nu, nin = nx + nu, H = P.H, mw = net.max_width;
   double *h0 = wk, *h1 = h0 + mw, *g = h1 + mw, *J0 = g + mw, *J1 = J0 + (size_t)mw * nin;
-  for (int s = warp; s < H; s += NWARPS) {
-    for (int j = lane; j < nin; j += 32) {
-      const double v = j < nx ? xs[(size_t)s * nx + j] : us[(size_t)s * nu + (j - nx)];
-      h0[j] = (v - net.xu_mean[j]) / net.xu_std[j];
-    }
-    __syncwarp();
-    double *hin = h0, *hout = h1, *Jp = J0, *Jn = J1;
-    for (int l = 0; l < net.n_layers; ++l) {
-      const int Kin = net.dims[l], N = net.dims[l + 1];
-      const bool last = (l == net.n_layers - 1);
-      const double *Wt = net.Wt[l];
-      for (int j = lane; j < N; j += 32) {
-        const double y = net.b[l][j] + dot_col_any(Wt, N, j, hin, Kin);
-        hout[j] = last ? y : ampc_act<double>(net.act, y);
-        g[j] = last ? 1.0 : ampc_act_grad<double>(net.act, y);
+  const double *xu_mean = nb + net.xu_mean, *xu_std = nb + net.xu_std, *dy_std = nb + net.dy_std;
+  if (warp < JAC_WARPS) {
+    for (int s = warp; s < H; s += JAC_WARPS) {
+      for (int j = lane; j < nin; j += 32) {
+        const double v = j < nx ? xs[(size_t)s * nx + j] : us[(size_t)s * nu + (j - nx)];
+        h0[j] = (v - xu_mean[j]) / xu_std[j];
       }
       __syncwarp();
-      for (int j = lane; j < N; j += 32) {
-        const double gj = g[j];
-        if (l == 0) {
-          for (int c = 0; c < nin; ++c) Jn[(size_t)j * nin + c] = Wt[(size_t)c * N + j] / net.xu_std[c] * gj;
-        } else {
-          for (int c0 = 0; c0 < nin; c0 += JAC_CB) {
-            double acc0[JAC_CB], acc1[JAC_CB];          // even / odd k, like the two partial sums of the batch routine
+      double *hin = h0, *hout = h1, *Jp = J0, *Jn = J1;
+#pragma unroll 1
+      for (int l = 0; l < net.n_layers; ++l) {
+        const int Kin = net.dims[l], N = net.dims[l + 1], ws = net.wstride[l];
+        const bool last = (l == net.n_layers - 1);
+        const double *W = nb + net.woff[l], *B = nb + net.boff[l];
+        for (int j = lane; j < N; j += 32) {
+          const double y = B[j] + dot_row(W + (size_t)j * ws, hin, Kin);
+          hout[j] = last ? y : ampc_act<double>(net.act, y);
+          g[j] = last ? 1.0 : ampc_act_grad<double>(net.act, y);
+        }
+        __syncwarp();
+        for (int j = lane; j < N; j += 32) {
+          const double gj = g[j];
+          const double *wr = W + (size_t)j * ws;
+          double *out = Jn + (size_t)j * nin;
+          if (l == 0) {
+            for (int c = 0; c < nin; ++c) out[c] = wr[c] / xu_std[c] * gj;
+          } else {
+            for (int c0 = 0; c0 < nin; c0 += JAC_CB) {
+              double acc0[JAC_CB], acc1[JAC_CB];        // even / odd k
 #pragma unroll
-            for (int q = 0; q < JAC_CB; ++q) { acc0[q] = 0.0; acc1[q] = 0.0; }
-            int k = 0;
-            for (; k + 2 <= Kin; k += 2) {
-              const double w0 = Wt[(size_t)k * N + j], w1 = Wt[(size_t)(k + 1) * N + j];
-              const double *r0 = Jp + (size_t)k * nin + c0, *r1 = r0 + nin;
+              for (int q = 0; q < JAC_CB; ++q) { acc0[q] = 0.0; acc1[q] = 0.0; }
+              const double *r0 = Jp + c0;
+              const int cw = nin - c0;                  // live columns of this strip (>= 1)
+              int k = 0;
+              if (cw >= JAC_CB) {
+                for (; k + 2 <= Kin; k += 2, r0 += 2 * nin) {
+                  const double w0 = wr[k], w1 = wr[k + 1];
+#pragma unroll
+                  for (int q = 0; q < JAC_CB; ++q) { acc0[q] = fma(w0, r0[q], acc0[q]); acc1[q] = fma(w1, r0[nin + q], acc1[q]); }
+                }
+              } else {
+                for (; k + 2 <= Kin; k += 2, r0 += 2 * nin) {
+                  const double w0 = wr[k], w1 = wr[k + 1];
+#pragma unroll
+                  for (int q = 0; q < JAC_CB; ++q)
+                    if (q < cw) { acc0[q] = fma(w0, r0[q], acc0[q]); acc1[q] = fma(w1, r0[nin + q], acc1[q]); }
+                }
+              }
+              if (k < Kin) {
+                const double w0 = wr[k];
+#pragma unroll
+                for (int q = 0; q < JAC_CB; ++q)
+                  if (q < cw) acc0[q] = fma(w0, r0[q], acc0[q]);
+              }
 #pragma unroll
               for (int q = 0; q < JAC_CB; ++q)
-                if (c0 + q < nin) { acc0[q] = fma(w0, r0[q], acc0[q]); acc1[q] = fma(w1, r1[q], acc1[q]); }
+                if (q < cw) out[c0 + q] = (acc0[q] + acc1[q]) * gj;
             }
-            if (k < Kin) {
-              const double w0 = Wt[(size_t)k * N + j];
-              const double *r0 = Jp + (size_t)k * nin + c0;
-#pragma unroll
-              for (int q = 0; q < JAC_CB; ++q)
-                if (c0 + q < nin) acc0[q] = fma(w0, r0[q], acc0[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < JAC_CB; ++q)
-              if (c0 + q < nin) Jn[(size_t)j * nin + c0 + q] = (acc0[q] + acc1[q]) * gj;
           }
         }
+        __syncwarp();
+        double *t2 = hin; hin = hout; hout = t2;
+        double *t3 = Jp; Jp = Jn; Jn = t3;
       }
+      double *dst = Jacs + (size_t)s * nx * nin;
+      for (int a = 0; a < nx; ++a)
+        for (int c = lane; c < nin; c += 32) dst[a * nin + c] = Jp[a * nin + c] * dy_std[a] + ((c == a) ? 1.0 : 0.0);
       __syncwarp();
-      double *t2 = hin; hin = hout; hout = t2;
-      double *t3 = Jp; Jp = Jn; Jn = t3;
     }
-    for (int r = lane; r < nx * nin; r += 32) {
-      const int a = r / nin, c = r - a * nin;
-      Jacs[(size_t)s * nx * nin + r] = Jp[r] * net.dy_std[a] + ((c == a) ? 1.0 : 0.0);
-    }
-    __syncwarp();
   }
   __syncthreads();
 }
 
+template <bool RES>
 __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
   extern __shared__ double sm[];
   const long long t_entry = clock64();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nx = P.nx, nu = P.nu, n = nx + nu, H = P.H, LS = P.ls_max_iter, mw = P.net.max_width;
+  const IlqrNet &net = P.net;
+  const int nx = P.nx, nu = P.nu, n = nx + nu, H = P.H, LS = P.ls_max_iter, mw = net.max_width;
   // line-search groups: G warps per alpha (2 when they fit), group j = warps [j*G, (j+1)*G)
   const int G = (2 * LS <= NWARPS) ? 2 : 1;
   const int gthr = 32 * G;
   const int grp = warp / G, gl = tid - grp * gthr;
-  // shared-memory carve
+  // ---- shared-memory carve (doubles, then the index tables)
   double *s_Ct = sm;                 // n*n   dt*blkdiag(Q+Q^T, R+R^T)           ilqr.py:170-171
   double *s_Fs = s_Ct + n * n;       // nx*nx F+F^T                             cost.py:208-211
   double *s_V0 = s_Fs + nx * nx;     // nx*nx value Hessian (ping)
@@ -212,91 +260,90 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
   double *s_LU = s_k + nu;           // nu*nu  LU factors of Quu
   double *s_red = s_LU + nu * nu;    // NWARPS
   double *s_obj = s_red + NWARPS;    // LS + 4
-  double *s_h = s_obj + LS + 4;      // LS * 2 * mw: per-group activation ping-pong
-  double *s_next = s_h + (size_t)LS * 2 * mw;
+  double *s_cst = s_obj + LS + 4;    // Q | R | F | goal | goalF | umin | umax | alphas
+  double *s_h = s_cst + ((cst_doubles(nx, nu, LS) + 1) & ~(size_t)1);   // LS * 2 * mw: per-group activation ping-pong
+  double *s_var = s_h + (size_t)LS * 2 * mw;
+  const TrajLayout tl(H, nx, nu, LS);
+  const size_t jpw = jac_per_warp(mw, n);
+  const size_t net_d = ((size_t)net.total + 1) & ~(size_t)1;
+  // resident: network | trajectory block | Jacobian scratch, all derived from the shared array
+  const double *nb = RES ? s_var : P.net_blob;
+  double *traj = RES ? s_var + net_d : P.traj;
+  double *jac_wk = (RES ? s_var + net_d + tl.total : P.jac_work) + (size_t)(warp < JAC_WARPS ? warp : 0) * jpw;
+  int *s_tab_n = reinterpret_cast<int *>(s_var + (RES ? net_d + tl.total + JAC_WARPS * jpw : 0));   // e -> (e / n) << 16 | e % n
+  int *s_tab_x = s_tab_n + n * n;                                                                    // e -> (e / nx) << 16 | e % nx
   __shared__ int s_flag[4];          // [0]=line search failed, [1]=used idx, [2]=refresh jac
   __shared__ int s_piv[MAX_NU];
   __shared__ double s_lin, s_quad;
 
-  // ---- the network: weights staged into shared memory when they fit (plain loads serve both placements)
-  AmpcMlpF64 net = P.net;
-  if (P.w_smem) {
-    double *s_net = s_next;
-    s_next += P.net_doubles;
-    for (size_t t = tid; t < P.net_doubles; t += NT) s_net[t] = P.net_blob[t];
-    for (int l = 0; l < net.n_layers; ++l) {
-      net.Wt[l] = s_net + (P.net.Wt[l] - P.net_blob);
-      net.b[l] = s_net + (P.net.b[l] - P.net_blob);
-    }
-    net.xu_mean = s_net + (P.net.xu_mean - P.net_blob); net.xu_std = s_net + (P.net.xu_std - P.net_blob);
-    net.dy_mean = s_net + (P.net.dy_mean - P.net_blob); net.dy_std = s_net + (P.net.dy_std - P.net_blob);
-  }
-  // ---- trajectories, gains, Jacobians, line-search rollouts: shared memory when they fit
-  double *states = P.states, *ctrls = P.ctrls, *Ks = P.Ks, *ks = P.ks, *Jacs = P.Jacs, *ls_states = P.ls_states,
-         *ls_ctrls = P.ls_ctrls, *step_cost = P.step_cost;
-  if (P.traj_smem) {
-    states = s_next; s_next += (size_t)(H + 1) * nx;
-    ctrls = s_next; s_next += (size_t)H * nu;
-    Ks = s_next; s_next += (size_t)H * nu * nx;
-    ks = s_next; s_next += (size_t)H * nu;
-    Jacs = s_next; s_next += (size_t)H * nx * n;
-    ls_states = s_next; s_next += (size_t)LS * (H + 1) * nx;
-    ls_ctrls = s_next; s_next += (size_t)LS * H * nu;
-    step_cost = s_next; s_next += (size_t)(LS + 1) * (H + 1);
-  }
+  double *states = traj + tl.states, *ctrls = traj + tl.ctrls, *Ks = traj + tl.Ks, *ks = traj + tl.ks,
+         *Jacs = traj + tl.Jacs, *ls_states = traj + tl.ls_states, *ls_ctrls = traj + tl.ls_ctrls,
+         *step_cost = traj + tl.step_cost;
+  const double *c_Q = s_cst, *c_R = c_Q + nx * nx, *c_F = c_R + nu * nu, *c_goal = c_F + nx * nx, *c_goalF = c_goal + nx,
+               *c_umin = c_goalF + nx, *c_umax = c_umin + nu, *c_alphas = c_umax + nu;
+  const double *xu_mean = nb + net.xu_mean, *xu_std = nb + net.xu_std, *dy_mean = nb + net.dy_mean, *dy_std = nb + net.dy_std;
 
-  // per-warp scratch of the Jacobian refresh
-  const size_t jac_per_warp = 3 * (size_t)mw + 2 * (size_t)mw * n;
-  double *jac_wk = P.jac_smem ? s_next + (size_t)warp * jac_per_warp : P.hA + (size_t)warp * jac_per_warp;
-
+  if (RES) {
+    double *dst = s_var;
+    for (int t = tid; t < net.total; t += NT) dst[t] = P.net_blob[t];
+  }
+  for (int t = tid; t < (int)cst_doubles(nx, nu, LS); t += NT) s_cst[t] = P.cst[t];
+  for (int t = tid; t < n * n; t += NT) s_tab_n[t] = ((t / n) << 16) | (t % n);
+  for (int t = tid; t < nx * nx; t += NT) s_tab_x[t] = ((t / nx) << 16) | (t % nx);
+  __syncthreads();
   for (int t = tid; t < n * n; t += NT) {
     const int r = t / n, c = t - r * n;
     double v = 0.0;
-    if (r < nx && c < nx) v = P.dt * (P.Q[r * nx + c] + P.Q[c * nx + r]);
-    else if (r >= nx && c >= nx) v = P.dt * (P.R[(r - nx) * nu + (c - nx)] + P.R[(c - nx) * nu + (r - nx)]);
+    if (r < nx && c < nx) v = P.dt * (c_Q[r * nx + c] + c_Q[c * nx + r]);
+    else if (r >= nx && c >= nx) v = P.dt * (c_R[(r - nx) * nu + (c - nx)] + c_R[(c - nx) * nu + (r - nx)]);
     s_Ct[t] = v;
   }
   for (int t = tid; t < nx * nx; t += NT) {
     const int r = t / nx, c = t - r * nx;
-    s_Fs[t] = P.F[r * nx + c] + P.F[c * nx + r];
+    s_Fs[t] = c_F[r * nx + c] + c_F[c * nx + r];
   }
   for (int t = tid; t < nx; t += NT) states[t] = P.x0[t];
   for (int t = tid; t < H * nu; t += NT) ctrls[t] = P.uguess ? P.uguess[t] : 0.0;
   for (int t = tid; t < P.max_iter; t += NT) P.alpha_idx[t] = -1;
   __syncthreads();
 
+  // per-step cost table for trajectory (xs (H+1,nx), us (H,nu)): c[i] = dt*(obs+ctrl), c[H] = terminal   (ilqr.py:124-129)
+  auto step_cost_of = [&](const double *xs, const double *us, int i) -> double {
+    if (i < H) return P.dt * (quad_form(c_Q, xs + (size_t)i * nx, c_goal, nx) + quad_form(c_R, us + (size_t)i * nu, nullptr, nu));
+    return quad_form(c_F, xs + (size_t)H * nx, c_goalF, nx);
+  };
+
   // ---- initial rollout (ilqr.py:141-147) by line-search group 0; Jacobians are evaluated in one batch afterwards
   if (grp == 0) {
     double *h0 = s_h, *h1 = s_h + mw;
     for (int i = 0; i < H; ++i) {
+      const double *xi = states + (size_t)i * nx;
       for (int j = gl; j < n; j += gthr) {
-        const double v = j < nx ? states[(size_t)i * nx + j] : ctrls[(size_t)i * nu + (j - nx)];
-        h0[j] = (v - net.xu_mean[j]) / net.xu_std[j];
+        const double v = j < nx ? xi[j] : ctrls[(size_t)i * nu + (j - nx)];
+        h0[j] = (v - xu_mean[j]) / xu_std[j];
       }
       group_sync(1, gthr);
-      const double *out = group_forward(net, h0, h1, gl, gthr, 1);
-      for (int j = gl; j < nx; j += gthr)
-        states[(size_t)(i + 1) * nx + j] = states[(size_t)i * nx + j] + (out[j] * net.dy_std[j] + net.dy_mean[j]);
+      const double *out = group_forward(net, nb, h0, h1, gl, gthr, 1);
+      for (int j = gl; j < nx; j += gthr) states[(size_t)(i + 1) * nx + j] = xi[j] + (out[j] * dy_std[j] + dy_mean[j]);
       group_sync(1, gthr);
     }
   }
   __syncthreads();
-  jac_batch(P, net, states, ctrls, Jacs, jac_wk, warp, lane);
-  step_costs(P, states, ctrls, step_cost, tid, NT);
+  jac_batch(P, nb, states, ctrls, Jacs, jac_wk, warp, lane);
+  for (int i = tid; i <= H; i += NT) step_cost[i] = step_cost_of(states, ctrls, i);
   __syncthreads();
   double obj = 0.0;       // every thread tracks the same scalars (uniform control flow)
   for (int i = 0; i <= H; ++i) obj += step_cost[i];     // sequential like eval_obj, ilqr.py:124-129
   __syncthreads();
 
   long long t_mark = clock64();
-  const long long t_begin = t_entry;
   unsigned long long cyc[6] = {0, 0, 0, 0, 0, 0};
   auto lap = [&](int slot) { const long long now = clock64(); cyc[slot] += (unsigned long long)(now - t_mark); t_mark = now; };
-  cyc[0] = (unsigned long long)(t_mark - t_begin);
+  cyc[0] = (unsigned long long)(t_mark - t_entry);
   int converged = 0, n_iter = 0, ls_fail = 0;
   for (int itr = 0; itr < P.max_iter; ++itr) {
     n_iter = itr + 1;
-    // ---- backward pass (ilqr.py:159-187): ONE warp, warp barriers only (the matrices are (nx+nu)^2)
+    // ---- backward pass (ilqr.py:159-187): ONE warp, warp barriers only
     if (warp == 0) {
       double *Vn = s_V0, *Vnn = s_V1, *vn = s_v0, *vnn = s_v1;
       for (int t = lane; t < nx * nx; t += 32) Vn[t] = s_Fs[t];
@@ -311,50 +358,55 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
         const double *J = Jacs + (size_t)(t - 1) * nx * n;
         const double *xt = states + (size_t)(t - 1) * nx, *ut = ctrls + (size_t)(t - 1) * nu;
         for (int e = lane; e < nx * n; e += 32) {         // T = Vn @ J
-          const int a = e / n, c = e - a * n;
+          const int rc = s_tab_n[e], a = rc >> 16, c = rc & 0xffff;
+          const double *vr = Vn + a * nx, *jc = J + c;
           double acc = 0.0;
-          for (int b = 0; b < nx; ++b) acc += Vn[a * nx + b] * J[b * n + c];
+          for (int b = 0; b < nx; ++b) acc += vr[b] * jc[b * n];
           s_T[e] = acc;
         }
         __syncwarp();
         for (int e = lane; e < n * n + n; e += 32) {      // Qt = Ct + J^T T ; qt = ct + J^T vn
           if (e < n * n) {
-            const int r = e / n, c = e - r * n;
+            const int rc = s_tab_n[e], r = rc >> 16, c = rc & 0xffff;
+            const double *jr = J + r, *tc = s_T + c;
             double acc = 0.0;
-            for (int a = 0; a < nx; ++a) acc += J[a * n + r] * s_T[a * n + c];
+            for (int a = 0; a < nx; ++a) acc += jr[a * n] * tc[a * n];
             s_Qt[e] = s_Ct[e] + acc;
           } else {
             const int r = e - n * n;
+            const double *cr = s_Ct + r * n;
             double ct = 0.0;
-            if (r < nx) { for (int b = 0; b < nx; ++b) ct += s_Ct[r * n + b] * (xt[b] - P.goal[b]); }
-            else { for (int b = 0; b < nu; ++b) ct += s_Ct[r * n + nx + b] * ut[b]; }
+            if (r < nx) { for (int b = 0; b < nx; ++b) ct += cr[b] * (xt[b] - c_goal[b]); }
+            else { for (int b = 0; b < nu; ++b) ct += cr[nx + b] * ut[b]; }
             double acc = 0.0;
             for (int a = 0; a < nx; ++a) acc += J[a * n + r] * vn[a];
             s_qt[r] = ct + acc;
           }
         }
         __syncwarp();
-        if (lane == 0) {                                  // LU of Quu with partial pivoting (LAPACK gesv)
-          for (int r = 0; r < nu; ++r) for (int c = 0; c < nu; ++c) s_LU[r * nu + c] = s_Qt[(nx + r) * n + nx + c];
-          for (int c = 0; c < nu; ++c) {
-            int pr = c; double best = fabs(s_LU[c * nu + c]);
-            for (int r = c + 1; r < nu; ++r) if (fabs(s_LU[r * nu + c]) > best) { best = fabs(s_LU[r * nu + c]); pr = r; }
-            s_piv[c] = pr;
-            if (pr != c) for (int q = 0; q < nu; ++q) { double tmp = s_LU[c * nu + q]; s_LU[c * nu + q] = s_LU[pr * nu + q]; s_LU[pr * nu + q] = tmp; }
-            for (int r = c + 1; r < nu; ++r) {
-              s_LU[r * nu + c] /= s_LU[c * nu + c];
-              for (int q = c + 1; q < nu; ++q) s_LU[r * nu + q] -= s_LU[r * nu + c] * s_LU[c * nu + q];
+        {
+          if (lane == 0) {                                // LU of Quu with partial pivoting (LAPACK gesv)
+            for (int r = 0; r < nu; ++r) for (int c = 0; c < nu; ++c) s_LU[r * nu + c] = s_Qt[(nx + r) * n + nx + c];
+            for (int c = 0; c < nu; ++c) {
+              int pr = c; double best = fabs(s_LU[c * nu + c]);
+              for (int r = c + 1; r < nu; ++r) if (fabs(s_LU[r * nu + c]) > best) { best = fabs(s_LU[r * nu + c]); pr = r; }
+              s_piv[c] = pr;
+              if (pr != c) for (int q = 0; q < nu; ++q) { double tmp = s_LU[c * nu + q]; s_LU[c * nu + q] = s_LU[pr * nu + q]; s_LU[pr * nu + q] = tmp; }
+              for (int r = c + 1; r < nu; ++r) {
+                s_LU[r * nu + c] /= s_LU[c * nu + c];
+                for (int q = c + 1; q < nu; ++q) s_LU[r * nu + q] -= s_LU[r * nu + c] * s_LU[c * nu + q];
+              }
             }
           }
-        }
-        __syncwarp();
-        for (int col = lane; col <= nx; col += 32) {      // K = -Quu^-1 Qux, k = -Quu^-1 qu: one right-hand side per lane
-          double y[MAX_NU];
-          for (int r = 0; r < nu; ++r) y[r] = (col < nx) ? s_Qt[(nx + r) * n + col] : s_qt[nx + r];
-          for (int c = 0; c < nu; ++c) { const int pc = s_piv[c]; if (pc != c) { double tmp = y[c]; y[c] = y[pc]; y[pc] = tmp; } }
-          for (int r = 1; r < nu; ++r) for (int q = 0; q < r; ++q) y[r] -= s_LU[r * nu + q] * y[q];
-          for (int r = nu - 1; r >= 0; --r) { for (int q = r + 1; q < nu; ++q) y[r] -= s_LU[r * nu + q] * y[q]; y[r] /= s_LU[r * nu + r]; }
-          for (int r = 0; r < nu; ++r) { if (col < nx) s_K[r * nx + col] = -y[r]; else s_k[r] = -y[r]; }
+          __syncwarp();
+          for (int col = lane; col <= nx; col += 32) {    // K = -Quu^-1 Qux, k = -Quu^-1 qu: one right-hand side per lane
+            double y[MAX_NU];
+            for (int r = 0; r < nu; ++r) y[r] = (col < nx) ? s_Qt[(nx + r) * n + col] : s_qt[nx + r];
+            for (int c = 0; c < nu; ++c) { const int pc = s_piv[c]; if (pc != c) { double tmp = y[c]; y[c] = y[pc]; y[pc] = tmp; } }
+            for (int r = 1; r < nu; ++r) for (int q = 0; q < r; ++q) y[r] -= s_LU[r * nu + q] * y[q];
+            for (int r = nu - 1; r >= 0; --r) { for (int q = r + 1; q < nu; ++q) y[r] -= s_LU[r * nu + q] * y[q]; y[r] /= s_LU[r * nu + r]; }
+            for (int r = 0; r < nu; ++r) { if (col < nx) s_K[r * nx + col] = -y[r]; else s_k[r] = -y[r]; }
+          }
         }
         __syncwarp();
         if (lane == 0) {
@@ -373,7 +425,7 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
         }
         for (int e = lane; e < nx * nx + nx; e += 32) {   // value update (ilqr.py:186-187)
           if (e < nx * nx) {
-            const int a = e / nx, b = e - a * nx;
+            const int ab = s_tab_x[e], a = ab >> 16, b = ab & 0xffff;
             double acc = s_Qt[a * n + b];
             for (int r = 0; r < nu; ++r) acc += s_Qt[a * n + nx + r] * s_K[r * nx + b];
             for (int r = 0; r < nu; ++r) acc += s_K[r * nx + a] * s_Qt[(nx + r) * n + b];
@@ -415,27 +467,31 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
       const int bar = 1 + (grp % 15);
       double *h0 = s_h + (size_t)(grp % LS) * 2 * mw, *h1 = h0 + mw;
       double *xs = ls_states + (size_t)j * (H + 1) * nx, *us = ls_ctrls + (size_t)j * H * nu;
-      const double alpha = P.alphas[j];
+      const double alpha = c_alphas[j];
       for (int a = gl; a < nx; a += gthr) xs[a] = P.x0[a];
       group_sync(bar, gthr);
       for (int i = 0; i < H; ++i) {
-        const double *xi = xs + (size_t)i * nx;
-        for (int a = gl; a < nu; a += gthr) {
-          double fb = 0.0;
-          for (int b = 0; b < nx; ++b) fb += Ks[((size_t)i * nu + a) * nx + b] * (xi[b] - states[(size_t)i * nx + b]);
-          double u = alpha * ks[(size_t)i * nu + a] + ctrls[(size_t)i * nu + a] + fb;
-          if (P.bounded) u = fmin(fmax(u, P.umin[a]), P.umax[a]);     // np.clip, ilqr.py:203-204
-          us[(size_t)i * nu + a] = u;
-        }
-        group_sync(bar, gthr);
+        const double *xi = xs + (size_t)i * nx, *x_ref = states + (size_t)i * nx;
+        // z-scored input: the state columns, and the control columns computed in place (ilqr.py:201-204)
         for (int c = gl; c < n; c += gthr) {
-          const double v = c < nx ? xi[c] : us[(size_t)i * nu + (c - nx)];
-          h0[c] = (v - net.xu_mean[c]) / net.xu_std[c];
+          double v;
+          if (c < nx) {
+            v = xi[c];
+          } else {
+            const int a = c - nx;
+            const double *kr = Ks + ((size_t)i * nu + a) * nx;
+            double fb = 0.0;
+            for (int b = 0; b < nx; ++b) fb += kr[b] * (xi[b] - x_ref[b]);
+            double u = alpha * ks[(size_t)i * nu + a] + ctrls[(size_t)i * nu + a] + fb;
+            if (P.bounded) u = fmin(fmax(u, c_umin[a]), c_umax[a]);     // np.clip, ilqr.py:203-204
+            us[(size_t)i * nu + a] = u;
+            v = u;
+          }
+          h0[c] = (v - xu_mean[c]) / xu_std[c];
         }
         group_sync(bar, gthr);
-        const double *out = group_forward(net, h0, h1, gl, gthr, bar);
-        for (int a = gl; a < nx; a += gthr)
-          xs[(size_t)(i + 1) * nx + a] = xi[a] + (out[a] * net.dy_std[a] + net.dy_mean[a]);
+        const double *out = group_forward(net, nb, h0, h1, gl, gthr, bar);
+        for (int a = gl; a < nx; a += gthr) xs[(size_t)(i + 1) * nx + a] = xi[a] + (out[a] * dy_std[a] + dy_mean[a]);
         group_sync(bar, gthr);
       }
     }
@@ -444,11 +500,7 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
     // objective of every alpha: per-step costs in parallel, then a sequential sum per alpha
     for (int t = tid; t < LS * (H + 1); t += NT) {
       const int j = t / (H + 1), i = t - j * (H + 1);
-      const double *xs = ls_states + (size_t)j * (H + 1) * nx, *us = ls_ctrls + (size_t)j * H * nu;
-      double c;
-      if (i < H) c = P.dt * (quad_form(P.Q, xs + (size_t)i * nx, P.goal, nx) + quad_form(P.R, us + (size_t)i * nu, nullptr, nu));
-      else c = quad_form(P.F, xs + (size_t)H * nx, P.goalF, nx);
-      step_cost[(H + 1) + t] = c;
+      step_cost[(H + 1) + t] = step_cost_of(ls_states + (size_t)j * (H + 1) * nx, ls_ctrls + (size_t)j * H * nu, i);
     }
     __syncthreads();
     if (tid < LS) {
@@ -464,7 +516,7 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
       for (int l = 0; l < LS; ++l) {
         used = l;
         new_obj = s_obj[l];
-        const double alpha = P.alphas[l];
+        const double alpha = c_alphas[l];
         const double expect = alpha * lin_cost_reduce + alpha * alpha * quad_cost_reduce / 2;
         if ((obj - new_obj) / (-expect) > P.ls_cost_threshold) { best_obj = new_obj; best_idx = l; have_best = 1; break; }
         if (new_obj < best_obj) { best_obj = new_obj; best_idx = l; have_best = 1; }
@@ -486,7 +538,7 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
     if (s_flag[0]) { ls_fail = 1; break; }
     const int used = s_flag[1];
     const double *nxs = ls_states + (size_t)used * (H + 1) * nx, *nus = ls_ctrls + (size_t)used * H * nu;
-    if (s_flag[2]) jac_batch(P, net, nxs, nus, Jacs, jac_wk, warp, lane);   // ilqr.py:232 (stale Jacobians otherwise, as in the reference)
+    if (s_flag[2]) jac_batch(P, nb, nxs, nus, Jacs, jac_wk, warp, lane);   // ilqr.py:232 (stale Jacobians otherwise, as in the reference)
     lap(4);
     if (tid == 0) P.alpha_idx[itr] = used;
     double dsq = 0.0;
@@ -500,17 +552,15 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
     lap(3);
     if (converged) break;
   }
-  if (P.traj_smem) {                                     // outputs back to global memory
-    __syncthreads();
-    for (int t = tid; t < (H + 1) * nx; t += NT) P.states[t] = states[t];
-    for (int t = tid; t < H * nu; t += NT) { P.ctrls[t] = ctrls[t]; P.ks[t] = ks[t]; }
-    for (int t = tid; t < H * nu * nx; t += NT) P.Ks[t] = Ks[t];
-  }
+  __syncthreads();
+  for (int t = tid; t < (H + 1) * nx; t += NT) P.states[t] = states[t];
+  for (int t = tid; t < H * nu; t += NT) { P.ctrls[t] = ctrls[t]; P.ks[t] = ks[t]; }
+  for (int t = tid; t < H * nu * nx; t += NT) P.Ks[t] = Ks[t];
   if (tid == 0) {
     P.info[0] = converged; P.info[1] = n_iter; P.info[2] = ls_fail;
     lap(5);
     for (int q = 0; q < 6; ++q) P.prof[q] = cyc[q];
-    P.prof[6] = (unsigned long long)(clock64() - t_begin);
+    P.prof[6] = (unsigned long long)(clock64() - t_entry);
     P.prof[7] = (unsigned long long)n_iter;
   }
 }
@@ -521,7 +571,8 @@ struct ampc_ilqr {
   ampc_ilqr_cfg cfg;
   IlqrParams P;
   int device = 0;
-  double *d_blob = nullptr;   // MLP weights
+  bool resident = false;
+  double *d_net = nullptr;    // network blob (row-major padded weights, biases, normalisers)
   double *d_work = nullptr;   // everything else
   int *d_int = nullptr;
   unsigned long long *d_prof = nullptr;
@@ -529,91 +580,135 @@ struct ampc_ilqr {
   size_t o_x0 = 0, o_ug = 0;
 };
 
+static void launch_ilqr(const ampc_ilqr *h, const IlqrParams &P, cudaStream_t s) {
+  if (h->resident) ilqr_kernel<true><<<1, NT, h->smem, s>>>(P);
+  else ilqr_kernel<false><<<1, NT, h->smem, s>>>(P);
+  ampc_count_launch();
+}
+
 extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const ampc_mlp_desc *mlp,
                                 const ampc_quad_cost *cost) {
   AMPC_REQUIRE(out && cfg && mlp && cost, AMPC_ERR_INVALID, "null argument");
   *out = nullptr;
-  AMPC_REQUIRE(cfg->H >= 1 && cfg->nx >= 1 && cfg->nu >= 1 && cfg->nu <= MAX_NU, AMPC_ERR_INVALID,
-               "bad iLQR dims H=%d nx=%d nu=%d (nu <= %d)", cfg->H, cfg->nx, cfg->nu, MAX_NU);
+  AMPC_REQUIRE(cfg->H >= 1 && cfg->nx >= 1 && cfg->nu >= 1 && cfg->nu <= MAX_NU && cfg->nx + cfg->nu <= AMPC_MAX_WIDTH,
+               AMPC_ERR_INVALID, "bad iLQR dims H=%d nx=%d nu=%d (nu <= %d)", cfg->H, cfg->nx, cfg->nu, MAX_NU);
   AMPC_REQUIRE(cfg->max_iter >= 1 && cfg->ls_max_iter >= 1 && cfg->ls_max_iter <= MAX_LS, AMPC_ERR_INVALID,
                "bad iteration limits (1 <= ls_max_iter <= %d)", MAX_LS);
+  AMPC_REQUIRE(mlp->n_layers >= 2 && mlp->n_layers <= AMPC_MAX_LAYERS, AMPC_ERR_UNSUPPORTED,
+               "MLP must have 1..%d hidden layers", AMPC_MAX_LAYERS - 1);
+  AMPC_REQUIRE(mlp->dims[0] == cfg->nx + cfg->nu && mlp->dims[mlp->n_layers] == cfg->nx, AMPC_ERR_INVALID,
+               "MLP dims do not match nx+nu -> nx");
+  AMPC_REQUIRE(mlp->act >= 0 && mlp->act <= 3, AMPC_ERR_UNSUPPORTED, "unknown activation %d", mlp->act);
+  for (int l = 0; l <= mlp->n_layers; ++l)
+    AMPC_REQUIRE(mlp->dims[l] >= 1 && mlp->dims[l] <= AMPC_MAX_WIDTH, AMPC_ERR_UNSUPPORTED, "layer width %d", mlp->dims[l]);
+  for (int j = 0; j < cfg->nx + cfg->nu; ++j) AMPC_REQUIRE(mlp->xu_std[j] != 0.0, AMPC_ERR_INVALID, "xu_std[%d] == 0", j);
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   AMPC_REQUIRE(ce == cudaSuccess && ndev > 0, AMPC_ERR_CUDA, "no CUDA device: libampc_b200 has no CPU fallback (%s)",
                cudaGetErrorString(ce));
   AMPC_REQUIRE(cfg->device >= 0 && cfg->device < ndev, AMPC_ERR_INVALID, "device %d of %d", cfg->device, ndev);
   AMPC_CUDA_CHECK(cudaSetDevice(cfg->device));
+  const int H = cfg->H, nx = cfg->nx, nu = cfg->nu, n = nx + nu, LS = cfg->ls_max_iter;
   ampc_ilqr *h = new ampc_ilqr();
   h->cfg = *cfg;
   h->device = cfg->device;
   IlqrParams &P = h->P;
   memset(&P, 0, sizeof(P));
-  int rc = ampc_mlp_f64_upload(mlp, cfg->nx, cfg->nu, &P.net, &h->d_blob);
-  if (rc) { delete h; return rc; }
-  const int H = cfg->H, nx = cfg->nx, nu = cfg->nu, n = nx + nu, LS = cfg->ls_max_iter, mw = P.net.max_width;
+  // ---- network blob: W_l row-major (out, in) with an odd row stride, then b_l, then the normalisers
+  IlqrNet &net = P.net;
+  net.n_layers = mlp->n_layers;
+  net.act = mlp->act;
+  int off = 0;
+  for (int l = 0; l <= mlp->n_layers; ++l) {
+    net.dims[l] = mlp->dims[l];
+    if (mlp->dims[l] > net.max_width) net.max_width = mlp->dims[l];
+  }
+  for (int l = 0; l < mlp->n_layers; ++l) {
+    net.wstride[l] = mlp->dims[l] | 1;
+    net.woff[l] = off; off += net.wstride[l] * mlp->dims[l + 1]; off = (off + 1) & ~1;
+    net.boff[l] = off; off += mlp->dims[l + 1]; off = (off + 1) & ~1;
+  }
+  net.xu_mean = off; off += (n + 1) & ~1;
+  net.xu_std = off; off += (n + 1) & ~1;
+  net.dy_mean = off; off += (nx + 1) & ~1;
+  net.dy_std = off; off += (nx + 1) & ~1;
+  net.total = off;
+  std::vector<double> hb(off, 0.0);
+  for (int l = 0; l < mlp->n_layers; ++l) {
+    const int Kin = mlp->dims[l], N = mlp->dims[l + 1];
+    for (int j = 0; j < N; ++j) {
+      for (int k = 0; k < Kin; ++k) hb[net.woff[l] + (size_t)j * net.wstride[l] + k] = mlp->W[l][(size_t)j * Kin + k];
+      hb[net.boff[l] + j] = mlp->b[l][j];
+    }
+  }
+  for (int j = 0; j < n; ++j) { hb[net.xu_mean + j] = mlp->xu_mean[j]; hb[net.xu_std + j] = mlp->xu_std[j]; }
+  for (int j = 0; j < nx; ++j) { hb[net.dy_mean + j] = mlp->dy_mean[j]; hb[net.dy_std + j] = mlp->dy_std[j]; }
+  const int mw = net.max_width;
   P.H = H; P.nx = nx; P.nu = nu; P.bounded = cfg->bounded; P.max_iter = cfg->max_iter; P.ls_max_iter = LS;
   P.dt = cfg->dt; P.ls_discount = cfg->ls_discount; P.ls_cost_threshold = cfg->ls_cost_threshold;
   P.u_threshold = cfg->u_threshold;
-  size_t off = 0;
-  auto take = [&](size_t cnt) { size_t o = off; off += (cnt + 1) & ~(size_t)1; return o; };
-  const size_t oQ = take(nx * nx), oR = take(nu * nu), oF = take(nx * nx), og = take(nx), ogF = take(nx), oumin = take(nu), oumax = take(nu), oal = take(LS);
+  // ---- global work area: constants | x0 | uguess | outputs | trajectory block | Jacobian scratch
+  const TrajLayout tl(H, nx, nu, LS);
+  const size_t jpw = jac_per_warp(mw, n);
+  size_t woff = 0;
+  auto take = [&](size_t cnt) { size_t o = woff; woff += (cnt + 1) & ~(size_t)1; return o; };
+  const size_t o_cst = take(cst_doubles(nx, nu, LS));
   h->o_x0 = take(nx); h->o_ug = take((size_t)H * nu);
-  const size_t ost = take((size_t)(H + 1) * nx), oct = take((size_t)H * nu), oKs = take((size_t)H * nu * nx), oks = take((size_t)H * nu);
-  const size_t oJ = take((size_t)H * nx * n), ols = take((size_t)LS * (H + 1) * nx), olc = take((size_t)LS * H * nu);
-  const size_t osc = take((size_t)(LS + 1) * (H + 1));
-  const size_t jac_per_warp = 3 * (size_t)mw + 2 * (size_t)mw * n;
-  const size_t ohA = take((size_t)NWARPS * jac_per_warp);
-  cudaError_t e = cudaMalloc(&h->d_work, off * sizeof(double));
-  if (e == cudaSuccess) e = cudaMemset(h->d_work, 0, off * sizeof(double));
+  const size_t o_st = take((size_t)(H + 1) * nx), o_ct = take((size_t)H * nu), o_Ks = take((size_t)H * nu * nx), o_ks = take((size_t)H * nu);
+  const size_t o_traj = take(tl.total), o_jac = take((size_t)JAC_WARPS * jpw);
+  std::vector<double> hc(cst_doubles(nx, nu, LS), 0.0);
+  {
+    double *q = hc.data();
+    memcpy(q, cost->Q, sizeof(double) * nx * nx); q += nx * nx;
+    memcpy(q, cost->R, sizeof(double) * nu * nu); q += nu * nu;
+    memcpy(q, cost->F, sizeof(double) * nx * nx); q += nx * nx;
+    memcpy(q, cost->goal, sizeof(double) * nx); q += nx;
+    memcpy(q, cost->goal_term ? cost->goal_term : cost->goal, sizeof(double) * nx); q += nx;
+    memcpy(q, cost->umin, sizeof(double) * nu); q += nu;
+    memcpy(q, cost->umax, sizeof(double) * nu); q += nu;
+    for (int i = 0; i < LS; ++i) q[i] = pow(cfg->ls_discount, (double)i);   // ls_discount**i, ilqr.py:196
+  }
+  cudaError_t e = cudaMalloc(&h->d_net, hb.size() * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_net, hb.data(), hb.size() * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_work, woff * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(h->d_work, 0, woff * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_work + o_cst, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_int, (3 + cfg->max_iter) * sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&h->d_prof, 8 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(h->d_prof, 0, 8 * sizeof(unsigned long long));
-  std::vector<double> hc(h->o_x0, 0.0);
-  for (int i = 0; i < nx * nx; ++i) { hc[oQ + i] = cost->Q[i]; hc[oF + i] = cost->F[i]; }
-  for (int i = 0; i < nu * nu; ++i) hc[oR + i] = cost->R[i];
-  for (int i = 0; i < nx; ++i) { hc[og + i] = cost->goal[i]; hc[ogF + i] = cost->goal_term ? cost->goal_term[i] : cost->goal[i]; }
-  for (int i = 0; i < nu; ++i) { hc[oumin + i] = cost->umin[i]; hc[oumax + i] = cost->umax[i]; }
-  for (int i = 0; i < LS; ++i) hc[oal + i] = pow(cfg->ls_discount, (double)i);   // ls_discount**i, ilqr.py:196
-  if (e == cudaSuccess) e = cudaMemcpy(h->d_work, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice);
   double *w = h->d_work;
-  P.Q = w + oQ; P.R = w + oR; P.F = w + oF; P.goal = w + og; P.goalF = w + ogF; P.umin = w + oumin; P.umax = w + oumax; P.alphas = w + oal;
+  P.net_blob = h->d_net;
+  P.cst = w + o_cst;
   P.x0 = w + h->o_x0; P.uguess = nullptr;
-  P.states = w + ost; P.ctrls = w + oct; P.Ks = w + oKs; P.ks = w + oks; P.Jacs = w + oJ;
-  P.ls_states = w + ols; P.ls_ctrls = w + olc; P.step_cost = w + osc;
-  P.hA = w + ohA;
+  P.states = w + o_st; P.ctrls = w + o_ct; P.Ks = w + o_Ks; P.ks = w + o_ks;
+  P.traj = w + o_traj; P.jac_work = w + o_jac;
   P.info = h->d_int; P.alpha_idx = h->d_int + 3; P.prof = h->d_prof;
   {
-    // shared memory: the small matrices always; the network and the trajectories / gains / Jacobians / line-search
-    // rollouts when they fit next to them (the cartpole problem: 37 KB + 37 KB)
+    // shared memory: the small matrices, the cost constants, the per-group activations and the index tables always;
+    // network + trajectory block + Jacobian scratch when they all fit next to them
     size_t fixed = (size_t)n * n * 2 + (size_t)nx * nx * 3 + 2 * nx + (size_t)nx * n + n + (size_t)nu * nx + nu +
-                   (size_t)nu * nu + NWARPS + LS + 4 + (size_t)LS * 2 * mw;
-    size_t netd = 2 * (size_t)(nx + nu) + 2 * (size_t)nx;
-    for (int l = 0; l < mlp->n_layers; ++l) netd += (size_t)mlp->dims[l] * mlp->dims[l + 1] + mlp->dims[l + 1];
-    const size_t traj = (size_t)(H + 1) * nx + (size_t)H * nu * 2 + (size_t)H * nu * nx + (size_t)H * nx * n +
-                        (size_t)LS * (H + 1) * nx + (size_t)LS * H * nu + (size_t)(LS + 1) * (H + 1);
+                   (size_t)nu * nu + NWARPS + LS + 4 + ((cst_doubles(nx, nu, LS) + 1) & ~(size_t)1) + (size_t)LS * 2 * mw;
+    const size_t tabs = ((size_t)n * n + (size_t)nx * nx + 1) / 2 + 1;       // ints, in doubles
+    const size_t var = (((size_t)net.total + 1) & ~(size_t)1) + tl.total + (size_t)JAC_WARPS * jpw;
     int max_optin = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
     const size_t cap = (size_t)max_optin > 2048 ? ((size_t)max_optin - 2048) / sizeof(double) : 0;
-    P.net_doubles = netd;
-    P.net_blob = h->d_blob;
-    P.w_smem = (fixed + netd <= cap) ? 1 : 0;
-    if (P.w_smem) fixed += netd;
-    P.traj_smem = (fixed + traj <= cap) ? 1 : 0;
-    if (P.traj_smem) fixed += traj;
-    const size_t jacs = (size_t)NWARPS * jac_per_warp;
-    P.jac_smem = (fixed + jacs <= cap) ? 1 : 0;
-    if (P.jac_smem) fixed += jacs;
-    if (getenv("AMPC_ILQR_NO_SMEM")) {   // debugging / A-B: everything in global memory like the round-1 kernel
-      fixed -= (P.w_smem ? netd : 0) + (P.traj_smem ? traj : 0) + (P.jac_smem ? jacs : 0);
-      P.w_smem = P.traj_smem = P.jac_smem = 0;
+    h->resident = (fixed + tabs + var <= cap) && !getenv("AMPC_ILQR_NO_SMEM");
+    const size_t total = fixed + tabs + (h->resident ? var : 0);
+    h->smem = total * sizeof(double);
+    if (e == cudaSuccess && total > cap) {
+      ampc_set_error("iLQR: %zu B of shared memory needed", h->smem);
+      cudaFree(h->d_net); cudaFree(h->d_work); cudaFree(h->d_int); cudaFree(h->d_prof);
+      delete h;
+      return AMPC_ERR_UNSUPPORTED;
     }
-    h->smem = fixed * sizeof(double);
-    AMPC_REQUIRE(fixed <= cap || e != cudaSuccess, AMPC_ERR_UNSUPPORTED, "iLQR: %zu B of shared memory needed", h->smem);
   }
-  if (e == cudaSuccess) e = ampc_raise_smem_limit((const void *)ilqr_kernel, h->smem);
+  if (e == cudaSuccess)
+    e = h->resident ? ampc_raise_smem_limit((const void *)ilqr_kernel<true>, h->smem)
+                    : ampc_raise_smem_limit((const void *)ilqr_kernel<false>, h->smem);
   if (e != cudaSuccess) {
     ampc_set_error("iLQR create: %s", cudaGetErrorString(e));
-    cudaFree(h->d_blob); cudaFree(h->d_work); cudaFree(h->d_int); cudaFree(h->d_prof);
+    cudaFree(h->d_net); cudaFree(h->d_work); cudaFree(h->d_int); cudaFree(h->d_prof);
     delete h;
     return AMPC_ERR_CUDA;
   }
@@ -624,7 +719,7 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
 extern "C" int ampc_ilqr_destroy(ampc_ilqr *h) {
   if (!h) return AMPC_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_blob); cudaFree(h->d_work); cudaFree(h->d_int); cudaFree(h->d_prof);
+  cudaFree(h->d_net); cudaFree(h->d_work); cudaFree(h->d_int); cudaFree(h->d_prof);
   delete h;
   return AMPC_OK;
 }
@@ -643,8 +738,7 @@ extern "C" int ampc_ilqr_debug_profile(ampc_ilqr *h, unsigned long long *out8) {
 extern "C" int ampc_ilqr_launch(ampc_ilqr *h, void *stream) {
   AMPC_REQUIRE(h, AMPC_ERR_INVALID, "null handle");
   AMPC_CUDA_CHECK(cudaSetDevice(h->device));
-  ilqr_kernel<<<1, NT, h->smem, (cudaStream_t)stream>>>(h->P);
-  ampc_count_launch();
+  launch_ilqr(h, h->P, (cudaStream_t)stream);
   AMPC_CUDA_CHECK(cudaGetLastError());
   return AMPC_OK;
 }
@@ -660,8 +754,7 @@ extern "C" int ampc_ilqr_solve_host(ampc_ilqr *h, const double *x0, const double
     AMPC_CUDA_CHECK(cudaMemcpy(h->d_work + h->o_ug, uguess, (size_t)H * nu * sizeof(double), cudaMemcpyHostToDevice));
     P.uguess = h->d_work + h->o_ug;
   }
-  ilqr_kernel<<<1, NT, h->smem>>>(P);
-  ampc_count_launch();
+  launch_ilqr(h, P, nullptr);
   AMPC_CUDA_CHECK(cudaGetLastError());
   AMPC_CUDA_CHECK(cudaMemcpy(states, P.states, (size_t)(H + 1) * nx * sizeof(double), cudaMemcpyDeviceToHost));
   AMPC_CUDA_CHECK(cudaMemcpy(ctrls, P.ctrls, (size_t)H * nu * sizeof(double), cudaMemcpyDeviceToHost));

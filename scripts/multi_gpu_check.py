@@ -38,7 +38,7 @@ if rank == 0:
         print("%-6s (used %s): max|u - single GPU| per solve = %s, %.4f ms/solve"
               % (ex, used, np.array2string(np.abs(us - uf).max(axis=1), precision=2), ms), flush=True)
     # first solve: only the merge order of the partial records differs (fp32 rounding); later solves start from
-    # action sequences that differ by that rounding, which bf16 activations amplify (stated bf16 tolerance)
+    # action sequences that differ by that rounding, which the 16-bit activations amplify (stated tolerance)
     for ex in ("nvlink", "nccl"):
         d = np.abs(res[ex][1] - uf).max(axis=1)
         assert d[0] < 1e-5 and d.max() < 5e-2, (ex, d)
