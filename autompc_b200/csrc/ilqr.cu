@@ -13,25 +13,28 @@
 // Work decomposition inside the CTA (20 warps):
 //   * backward pass: ONE warp, warp barriers only -- the matrices are (nx+nu)^2; (row, column) of every element comes
 //     from small index tables instead of integer divisions;
-//   * line search: alpha j is rolled out by its own group of 1-2 warps for all H steps with group barriers only (the
-//     reference batches the alphas per step, ilqr.py:197-205: same numbers, no block-wide barrier per step);
+//   * line search: all step sizes batched per horizon step like the reference (ilqr.py:197-205) by 8 warps = 64 output
+//     slots x 4 K-quarters; a weight is read from shared memory once for all alphas (ls_rollouts);
 //   * Jacobian refresh (mlp.py:281-305 in closed form): one warp per horizon step, forward-mode propagation of the
-//     [width x (nx+nu)] panel with a strip of each row held in registers.
+//     [width x (nx+nu)] panel with a strip of two rows held in registers (jac_batch).
 // Data placement (template RES): when the network (row-major, rows padded to an odd stride so that lane j reading row j
 // is bank-conflict free), the trajectories / gains / Jacobians / line-search rollouts and the per-warp Jacobian scratch
-// all fit in shared memory (the cartpole problem: 38 + 37 + 66 KB) they live there and every pointer is derived from
+// all fit in shared memory (the cartpole problem: 40 + 37 + 123 KB) they live there and every pointer is derived from
 // the shared array, so the compiler emits LDS/STS with immediate offsets; otherwise the same code runs on global
-// scratch.  (ncu on the round-2 first cut, which passed shared and global pointers through one struct: 111 M warp
-// instructions per solve of which 10 M were DFMA -- 64-bit generic address arithmetic was the kernel.)
+// scratch.  What the profiles said on the way (profiles/r02_ilqr_*): the round-1 kernel and the first round-2 cut spent
+// 111 M warp instructions per solve of which 10 M were DFMA -- 64-bit generic address arithmetic; with that gone, rolling
+// every alpha out on its own was bound by the shared-memory pipe (the whole network per alpha per step), and the
+// one-warp Riccati recursion by its instruction count (a lone warp retires a dependent instruction every ~10 cycles).
 #include <vector>
 
 #include "ampc_common.cuh"
 
 namespace {
 
-constexpr int NT = 640;            // 20 warps
+constexpr int NT = 512;            // 16 warps (<= 128 registers per thread)
 constexpr int NWARPS = NT / 32;
-constexpr int JAC_WARPS = 10;      // warps that take part in the Jacobian refresh (bounds its shared-memory scratch)
+constexpr int JAC_WARPS = 16;      // warps that take part in the Jacobian refresh (bounds its shared-memory scratch)
+constexpr int LS_WARPS = 16;       // warps of the line-search phase (4 or 8 of them run the main loops)
 constexpr int MAX_NU = 16;
 constexpr int MAX_LS = 20;
 constexpr int MAXL = AMPC_MAX_LAYERS;
@@ -39,7 +42,8 @@ constexpr int MAXL = AMPC_MAX_LAYERS;
 struct IlqrNet {                   // offsets in doubles from the base of the network blob
   int n_layers, act, max_width, total;
   int dims[MAXL + 1];
-  int woff[MAXL], wstride[MAXL], boff[MAXL];   // W_l row-major (out, in) with row stride wstride (odd)
+  int woff[MAXL], wstride[MAXL], boff[MAXL];   // W_l row-major (out, in) with an odd row stride: lane j reading row j is conflict free
+  int w0s;                                     // W_0[j][c] / xu_std[c], row stride dims[0]: first Jacobian panel (mlp.py:298)
   int xu_mean, xu_std, dy_mean, dy_std;
 };
 
@@ -72,7 +76,12 @@ struct TrajLayout {
   }
 };
 
-__host__ __device__ inline size_t jac_per_warp(int mw, int n) { return 3 * (size_t)mw + 2 * (size_t)mw * n + 2; }
+__host__ __device__ inline int jac_cols(int n) { return (n + 1) & ~1; }           // panel row stride: even, rows 16-byte aligned
+__host__ __device__ inline size_t jac_per_warp(int mw, int n) {
+  return 4 * (size_t)((mw + 1) & ~1) + 2 * (size_t)mw * jac_cols(n);
+}
+__host__ __device__ inline int ls_cols(int LS) { return LS <= 10 ? 10 : 20; }   // activation columns of ls_rollouts (AG x LAP)
+__host__ __device__ inline size_t ls_scratch(int mw, int LS) { return (size_t)6 * mw * ls_cols(LS); }   // hT x 2 + partials x 4
 __host__ __device__ inline size_t cst_doubles(int nx, int nu, int LS) {
   return 2 * (size_t)nx * nx + (size_t)nu * nu + 2 * (size_t)nx + 2 * (size_t)nu + LS;
 }
@@ -152,15 +161,17 @@ __device__ __forceinline__ const double *group_forward(const IlqrNet &net, const
 
 // Jacobians of x' = x + dy(x,u) at (xs[i], us[i]) for i < H  ->  Jacs (H, nx, nx+nu)   (mlp.py:281-305)
 // One WARP per sample (samples warp, warp + JAC_WARPS, ...), warp barriers only.  Forward-mode propagation of the
-// [width x nin] panel through the layer stack; per layer a lane owns output rows j = lane, lane + 32, ... and keeps a
-// CB-column strip of its row in registers while it walks k: its weights are a contiguous row, the previous panel's row
-// k is a broadcast load.  `wk` = this warp's scratch: h0, h1, g (mw each) and two panels (mw * nin each).
-constexpr int JAC_CB = 8;
-__device__ void jac_batch(const IlqrParams &P, const double *nb, const double *xs, const double *us, double *Jacs, double *wk,
+// [width x nin] panel through the layer stack.  Per layer a lane owns the output rows j = lane and lane + 32 (then
+// lane + 64, ...) TOGETHER and keeps a CB-column strip of both in registers while it walks k: its weights are two
+// contiguous rows, row k of the previous panel is a broadcast 16-byte load shared by both rows.
+// `wk` = this warp's scratch: h0, h1, g (mw each, 16-byte aligned) and two panels (mw x jac_cols(nin) each).
+constexpr int JAC_CB = 6;
+__device__ __forceinline__ void jac_batch(const IlqrParams &P, const double *nb, const double *xs, const double *us, double *Jacs, double *wk,
                           int warp, int lane) {
   const IlqrNet &net = P.net;
-  const int nx = P.nx, nu = P.nu, nin = nx + nu, H = P.H, mw = net.max_width;
-  double *h0 = wk, *h1 = h0 + mw, *g = h1 + mw, *J0 = g + mw, *J1 = J0 + (size_t)mw * nin;
+  const int nx = P.nx, nu = P.nu, nin = nx + nu, H = P.H, mw = net.max_width, np = jac_cols(nin);
+  const int mwp = (mw + 1) & ~1;                        // keeps the panels 16-byte aligned
+  double *h0 = wk, *h1 = h0 + mwp, *g = h1 + mwp, *J0 = g + 2 * mwp, *J1 = J0 + (size_t)mw * np;
   const double *xu_mean = nb + net.xu_mean, *xu_std = nb + net.xu_std, *dy_std = nb + net.dy_std;
   if (warp < JAC_WARPS) {
     for (int s = warp; s < H; s += JAC_WARPS) {
@@ -181,43 +192,61 @@ __device__ void jac_batch(const IlqrParams &P, const double *nb, const double *x
           g[j] = last ? 1.0 : ampc_act_grad<double>(net.act, y);
         }
         __syncwarp();
-        for (int j = lane; j < N; j += 32) {
-          const double gj = g[j];
-          const double *wr = W + (size_t)j * ws;
-          double *out = Jn + (size_t)j * nin;
-          if (l == 0) {
-            for (int c = 0; c < nin; ++c) out[c] = wr[c] / xu_std[c] * gj;
-          } else {
-            for (int c0 = 0; c0 < nin; c0 += JAC_CB) {
-              double acc0[JAC_CB], acc1[JAC_CB];        // even / odd k
+        if (l == 0) {
+          const double *W0s = nb + net.w0s;
+          for (int e = lane; e < N * nin; e += 32) {
+            const int j = e / nin, c = e - j * nin;
+            Jn[(size_t)j * np + c] = W0s[e] * g[j];
+          }
+          if (np != nin) for (int j = lane; j < N; j += 32) Jn[(size_t)j * np + nin] = 0.0;
+        } else if (N * np <= 256) {
+          // narrow layer (the output layer): one (row, column) element per lane and pass instead of a whole row pair
+          for (int e = lane; e < N * np; e += 32) {
+            const int j = e / np, c = e - j * np;
+            const double *wr = W + (size_t)j * ws, *r0 = Jp + c;
+            double a0 = 0.0, a1 = 0.0;                   // even / odd k
+            int k = 0;
+            for (; k + 2 <= Kin; k += 2) { a0 = fma(wr[k], r0[(size_t)k * np], a0); a1 = fma(wr[k + 1], r0[(size_t)(k + 1) * np], a1); }
+            if (k < Kin) a0 = fma(wr[k], r0[(size_t)k * np], a0);
+            Jn[e] = (a0 + a1) * g[j];
+          }
+        } else {
+          for (int j0 = lane; j0 < N; j0 += 64) {
+            const int j1 = j0 + 32;
+            const bool two = j1 < N;
+            const double *wr0 = W + (size_t)j0 * ws, *wr1 = W + (size_t)(two ? j1 : j0) * ws;
+            const double g0 = g[j0], g1 = two ? g[j1] : 0.0;
+            for (int c0 = 0; c0 < np; c0 += JAC_CB) {
+              // strips are JAC_CB wide; the last one may hang over the panel's row by up to JAC_CB - 2 columns: those
+              // columns read the next row's leading entries (inside the panel except for its very last row, which has
+              // mw - N rows of slack or the neighbouring buffer behind it) and are never stored
+              double a00[JAC_CB], a01[JAC_CB], a10[JAC_CB], a11[JAC_CB];   // [row][k parity]
 #pragma unroll
-              for (int q = 0; q < JAC_CB; ++q) { acc0[q] = 0.0; acc1[q] = 0.0; }
+              for (int q = 0; q < JAC_CB; ++q) { a00[q] = 0.0; a01[q] = 0.0; a10[q] = 0.0; a11[q] = 0.0; }
               const double *r0 = Jp + c0;
-              const int cw = nin - c0;                  // live columns of this strip (>= 1)
               int k = 0;
-              if (cw >= JAC_CB) {
-                for (; k + 2 <= Kin; k += 2, r0 += 2 * nin) {
-                  const double w0 = wr[k], w1 = wr[k + 1];
+              for (; k + 2 <= Kin; k += 2, r0 += 2 * np) {
+                const double w00 = wr0[k], w01 = wr0[k + 1], w10 = wr1[k], w11 = wr1[k + 1];
 #pragma unroll
-                  for (int q = 0; q < JAC_CB; ++q) { acc0[q] = fma(w0, r0[q], acc0[q]); acc1[q] = fma(w1, r0[nin + q], acc1[q]); }
-                }
-              } else {
-                for (; k + 2 <= Kin; k += 2, r0 += 2 * nin) {
-                  const double w0 = wr[k], w1 = wr[k + 1];
-#pragma unroll
-                  for (int q = 0; q < JAC_CB; ++q)
-                    if (q < cw) { acc0[q] = fma(w0, r0[q], acc0[q]); acc1[q] = fma(w1, r0[nin + q], acc1[q]); }
+                for (int q = 0; q < JAC_CB; q += 2) {
+                  const double2 e = *reinterpret_cast<const double2 *>(r0 + q), o = *reinterpret_cast<const double2 *>(r0 + np + q);
+                  a00[q] = fma(w00, e.x, a00[q]); a00[q + 1] = fma(w00, e.y, a00[q + 1]);
+                  a01[q] = fma(w01, o.x, a01[q]); a01[q + 1] = fma(w01, o.y, a01[q + 1]);
+                  a10[q] = fma(w10, e.x, a10[q]); a10[q + 1] = fma(w10, e.y, a10[q + 1]);
+                  a11[q] = fma(w11, o.x, a11[q]); a11[q + 1] = fma(w11, o.y, a11[q + 1]);
                 }
               }
               if (k < Kin) {
-                const double w0 = wr[k];
+                const double w00 = wr0[k], w10 = wr1[k];
 #pragma unroll
-                for (int q = 0; q < JAC_CB; ++q)
-                  if (q < cw) acc0[q] = fma(w0, r0[q], acc0[q]);
+                for (int q = 0; q < JAC_CB; ++q) { a00[q] = fma(w00, r0[q], a00[q]); a10[q] = fma(w10, r0[q], a10[q]); }
               }
 #pragma unroll
               for (int q = 0; q < JAC_CB; ++q)
-                if (q < cw) out[c0 + q] = (acc0[q] + acc1[q]) * gj;
+                if (c0 + q < np) {
+                  Jn[(size_t)j0 * np + c0 + q] = (a00[q] + a01[q]) * g0;
+                  if (two) Jn[(size_t)j1 * np + c0 + q] = (a10[q] + a11[q]) * g1;
+                }
             }
           }
         }
@@ -226,17 +255,305 @@ __device__ void jac_batch(const IlqrParams &P, const double *nb, const double *x
         double *t3 = Jp; Jp = Jn; Jn = t3;
       }
       double *dst = Jacs + (size_t)s * nx * nin;
-      for (int a = 0; a < nx; ++a)
-        for (int c = lane; c < nin; c += 32) dst[a * nin + c] = Jp[a * nin + c] * dy_std[a] + ((c == a) ? 1.0 : 0.0);
+      for (int e = lane; e < nx * nin; e += 32) {
+        const int a = e / nin, c = e - a * nin;
+        dst[e] = Jp[(size_t)a * np + c] * dy_std[a] + ((c == a) ? 1.0 : 0.0);
+      }
       __syncwarp();
     }
   }
   __syncthreads();
 }
 
+// Line-search rollouts (ilqr.py:190-205) for all LS step sizes at once, like the reference's batched pred_batch, as a
+// register-tiled product  out[alpha][j] = sum_k h[alpha][k] W[j][k].
+//   main loop: 8 * AG warps = (alpha group ag) x (row half rh) x (K-quarter kq in 0..3); lane = output row j = 32 rh +
+//     lane (+ 64, ...).  A thread accumulates, for its LA alphas, the partial sum over k == kq (mod 4) of its row --
+//     exactly the four partial sums of dot_row.  Per k it loads its weight (conflict free with the odd row stride) and
+//     its alphas' activations (stored [k][alpha]: the address is uniform across the warp) for LA multiply-adds.  With
+//     AG = 1 (LS <= 10) every weight crosses the shared-memory pipe ONCE per layer and step;
+//   combine / controls / state update: all LS_WARPS warps, one (alpha, output) element per thread, (alpha, j) per layer
+//     computed once per call; the four K-quarters meet in shared memory and are combined in dot_row's order
+//     (p0 + p1) + (p2 + p3).
+// What the in-kernel phase counters said on the way (cycles per horizon step, 10 alphas, 5-64-64-4 network): one group
+// of warps per alpha 8.8 k -- the whole network through the 128 B/clk shared-memory pipe ten times per step; a
+// lane-level K split 12.4 k -- 16-byte activation loads with four addresses per warp; 16 main-loop warps in 4 alpha
+// groups 10 k (main loops 5.8 k: the weights still cross the pipe four times; combine 2.5 k: a division per element).
+template <int LA, int AG>
+__device__ __forceinline__ void ls_rollouts(const IlqrParams &P, const double *nb, double *hT /* 2 x mw x LSP */,
+                            double *part /* 4 x LSP x mw */, const double *states, const double *ctrls, const double *Ks,
+                            const double *ks, double *ls_states, double *ls_ctrls, const double *c_alphas,
+                            const double *c_umin, const double *c_umax, int tid) {
+  const IlqrNet &net = P.net;
+  const int nx = P.nx, nu = P.nu, n = nx + nu, H = P.H, LS = P.ls_max_iter, mw = net.max_width;
+  constexpr int NTH = LS_WARPS * 32, LAP = (LA + 1) & ~1, LSP = AG * LAP;
+  static_assert(8 * AG <= LS_WARPS, "main-loop warps");
+  const int lane = tid & 31, wp = tid >> 5, kq = wp & 3, rh = (wp >> 2) & 1, ag = wp >> 3;
+  const bool main_warp = wp < 8 * AG;
+  const double *xu_mean = nb + net.xu_mean, *xu_std = nb + net.xu_std, *dy_mean = nb + net.dy_mean, *dy_std = nb + net.dy_std;
+  double *hA = hT, *hB = hT + (size_t)mw * LSP;
+  auto sync_ls = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NTH) : "memory"); };
+  auto col_of = [&](int alpha) { const int g = alpha / LA; return g * LAP + (alpha - g * LA); };
+  long long tm = clock64();
+  unsigned long long lc[6] = {0, 0, 0, 0, 0, 0};         // thread 0: controls, main loops, barrier after main, combine, barrier after combine, update
+  auto lapl = [&](int q) { const long long now = clock64(); lc[q] += (unsigned long long)(now - tm); tm = now; };
+  // the (alpha, column) this thread prepares in the controls phase and the (alpha, state) it integrates
+  const int cj = tid < LS * n ? tid / n : -1, cc = tid - (tid / n) * n;
+  const int uj = tid < LS * nx ? tid / nx : -1, ua = tid - (tid / nx) * nx;
+  for (int t = tid; t < LS * nx; t += NTH) {
+    const int j = t / nx, a = t - j * nx;
+    ls_states[(size_t)j * (H + 1) * nx + a] = P.x0[a];
+  }
+  for (int t = tid; t < 2 * mw * LSP; t += NTH) hT[t] = 0.0;       // padding alphas stay zero
+  sync_ls();
+#pragma unroll 1
+  for (int i = 0; i < H; ++i) {
+    // controls (ilqr.py:201-204) and the z-scored input, one thread per (alpha, input column)
+    auto prep = [&](int j, int c) {
+      const double *xi = ls_states + ((size_t)j * (H + 1) + i) * nx;
+      double v;
+      if (c < nx) {
+        v = xi[c];
+      } else {
+        const int a = c - nx;
+        const double *kr = Ks + ((size_t)i * nu + a) * nx, *x_ref = states + (size_t)i * nx;
+        double fb = 0.0;
+        for (int b = 0; b < nx; ++b) fb += kr[b] * (xi[b] - x_ref[b]);
+        double u = c_alphas[j] * ks[(size_t)i * nu + a] + ctrls[(size_t)i * nu + a] + fb;
+        if (P.bounded) u = fmin(fmax(u, c_umin[a]), c_umax[a]);     // np.clip, ilqr.py:203-204
+        ls_ctrls[((size_t)j * H + i) * nu + a] = u;
+        v = u;
+      }
+      hA[(size_t)c * LSP + col_of(j)] = (v - xu_mean[c]) / xu_std[c];
+    };
+    if (cj >= 0) prep(cj, cc);
+    for (int t = tid + NTH; t < LS * n; t += NTH) prep(t / n, t % n);
+    sync_ls();
+    lapl(0);
+    double *hin = hA, *hout = hB;
+#pragma unroll 1
+    for (int l = 0; l < net.n_layers; ++l) {
+      const int Kin = net.dims[l], N = net.dims[l + 1], ws = net.wstride[l], Kin4 = Kin & ~3;
+      const bool last = (l == net.n_layers - 1);
+      const double *W = nb + net.woff[l], *B = nb + net.boff[l];
+      if (main_warp) {
+#pragma unroll 1
+        for (int j0 = rh * 32; j0 < N; j0 += 64) {
+          const int r0 = j0 + lane;
+          const bool live = r0 < N;
+          const double *wp0 = W + (size_t)(live ? r0 : 0) * ws;
+          const double *hp = hin + ag * LAP;
+          double p0[LA];
+#pragma unroll
+          for (int q = 0; q < LA; ++q) p0[q] = 0.0;
+          auto step = [&](int k) {
+            const double w = wp0[k];
+            const double2 *hv = reinterpret_cast<const double2 *>(hp + (size_t)k * LSP);
+#pragma unroll
+            for (int q = 0; q < LAP / 2; ++q) {
+              const double2 v = hv[q];
+              p0[2 * q] = fma(w, v.x, p0[2 * q]);
+              if (2 * q + 1 < LA) p0[2 * q + 1] = fma(w, v.y, p0[2 * q + 1]);
+            }
+          };
+#pragma unroll 2
+          for (int k = kq; k < Kin4; k += 4) step(k);
+          if (kq == 0) for (int k = Kin4; k < Kin; ++k) step(k);     // dot_row's tail goes into the first partial sum
+          if (live) {
+            double *pp = part + ((size_t)kq * LSP + ag * LAP) * mw + r0;
+#pragma unroll
+            for (int q = 0; q < LA; ++q) pp[(size_t)q * mw] = p0[q];
+          }
+        }
+      }
+      lapl(1);
+      sync_ls();
+      lapl(2);
+      {                                                             // (p0 + p1) + (p2 + p3), bias, activation
+        const size_t qs = (size_t)LSP * mw;
+        for (int jb = 0; jb < N; jb += 64) {
+          const int j = jb + (tid & 63);
+          if (j < N) {
+            const double bj = B[j];
+            for (int a = tid >> 6; a < LS; a += NTH / 64) {
+              const int col = col_of(a);
+              const double *q0 = part + (size_t)col * mw + j;
+              const double y = bj + ((q0[0] + q0[qs]) + (q0[2 * qs] + q0[3 * qs]));
+              hout[(size_t)j * LSP + col] = last ? y : ampc_act<double>(net.act, y);
+            }
+          }
+        }
+      }
+      lapl(3);
+      sync_ls();
+      lapl(4);
+      double *t2 = hin; hin = hout; hout = t2;
+    }
+    if (uj >= 0) {                                                   // mlp.py:235-236
+      const double *xi = ls_states + ((size_t)uj * (H + 1) + i) * nx;
+      ls_states[((size_t)uj * (H + 1) + i + 1) * nx + ua] = xi[ua] + (hin[(size_t)ua * LSP + col_of(uj)] * dy_std[ua] + dy_mean[ua]);
+    }
+    for (int t = tid + NTH; t < LS * nx; t += NTH) {
+      const int j = t / nx, a = t - j * nx;
+      const double *xi = ls_states + ((size_t)j * (H + 1) + i) * nx;
+      ls_states[((size_t)j * (H + 1) + i + 1) * nx + a] = xi[a] + (hin[(size_t)a * LSP + col_of(j)] * dy_std[a] + dy_mean[a]);
+    }
+    sync_ls();
+    lapl(5);
+  }
+  if (tid == 0) for (int q = 0; q < 6; ++q) P.prof[8 + q] += lc[q];
+}
+
+// Backward Riccati pass (ilqr.py:159-187) by ONE warp with warp barriers only.  A lone warp retires a dependent
+// instruction every ~7-10 cycles, so the recursion costs what it executes: NX / NU > 0 fix the dimensions at compile time
+// (loops unroll, index arithmetic folds; the cartpole shape 4 / 1 is instantiated), 0 = run-time dimensions.  Each
+// lane's (row, column) per phase is fixed over the horizon and is looked up once (when a phase has more than 32 elements
+// the lane strides over the rest).
+struct BackwardSmem {
+  double *Ct, *Fs, *V0, *V1, *v0, *v1, *T, *Qt, *qt, *K, *k, *LU;
+  int *tab_n, *tab_x, *piv;
+};
+template <int NX, int NU>
+__device__ __forceinline__ void backward_pass(const IlqrParams &P, const BackwardSmem &B, const double *states,
+                                              const double *ctrls, const double *Jacs, double *Ks, double *ks,
+                                              const double *c_goal, double *lin_out, double *quad_out, int lane) {
+  const int nx = NX ? NX : P.nx, nu = NU ? NU : P.nu, n = nx + nu, H = P.H;
+  double *const s_Ct = B.Ct, *const s_Fs = B.Fs, *const s_V0 = B.V0, *const s_V1 = B.V1, *const s_v0 = B.v0, *const s_v1 = B.v1,
+         *const s_T = B.T, *const s_Qt = B.Qt, *const s_qt = B.qt, *const s_K = B.K, *const s_k = B.k, *const s_LU = B.LU;
+  int *const s_tab_n = B.tab_n, *const s_tab_x = B.tab_x, *const s_piv = B.piv;
+  double s_lin = 0.0, s_quad = 0.0;
+  double *Vn = s_V0, *Vnn = s_V1, *vn = s_v0, *vnn = s_v1;
+  for (int t = lane; t < nx * nx; t += 32) Vn[t] = s_Fs[t];
+  for (int a = lane; a < nx; a += 32) {
+    double acc = 0.0;
+    for (int b = 0; b < nx; ++b) acc += s_Fs[a * nx + b] * states[(size_t)H * nx + b];   // no goal: cost.py:208
+    vn[a] = acc;
+  }
+  double lin_acc = 0.0, quad_acc = 0.0;               // lane 0's running sums (ilqr.py:178-179)
+  // element e of T (nx x n): T[a][c] = Vn[a,:] . J[:,c]
+  auto do_T = [&](int e, int rc, const double *Vc, const double *J) {
+    const int a = rc >> 16, c = rc & 0xffff;
+    const double *vr = Vc + a * nx, *jc = J + c;
+    double acc = 0.0;
+    for (int b = 0; b < nx; ++b) acc += vr[b] * jc[b * n];
+    s_T[e] = acc;
+  };
+  // element e of [Qt (n x n) | qt (n)]: Qt = Ct + J^T T ; qt = ct + J^T vn
+  auto do_Q = [&](int e, int rc, const double *J, const double *vc, const double *xt, const double *ut) {
+    if (e < n * n) {
+      const int r = rc >> 16, c = rc & 0xffff;
+      const double *jr = J + r, *tc = s_T + c;
+      double acc = 0.0;
+      for (int a = 0; a < nx; ++a) acc += jr[a * n] * tc[a * n];
+      s_Qt[e] = s_Ct[e] + acc;
+    } else {
+      const int r = e - n * n;
+      const double *cr = s_Ct + r * n;
+      double ct = 0.0;
+      if (r < nx) { for (int b = 0; b < nx; ++b) ct += cr[b] * (xt[b] - c_goal[b]); }
+      else { for (int b = 0; b < nu; ++b) ct += cr[nx + b] * ut[b]; }
+      double acc = 0.0;
+      for (int a = 0; a < nx; ++a) acc += J[a * n + r] * vc[a];
+      s_qt[r] = ct + acc;
+    }
+  };
+  // element e of [V' (nx x nx) | v' (nx)]  (ilqr.py:186-187)
+  auto do_V = [&](int e, int ab, double *Vo, double *vo) {
+    if (e < nx * nx) {
+      const int a = ab >> 16, b = ab & 0xffff;
+      double acc = s_Qt[a * n + b];
+      for (int r = 0; r < nu; ++r) acc += s_Qt[a * n + nx + r] * s_K[r * nx + b];
+      for (int r = 0; r < nu; ++r) acc += s_K[r * nx + a] * s_Qt[(nx + r) * n + b];
+      for (int r = 0; r < nu; ++r) {
+        double row = 0.0;
+        for (int c = 0; c < nu; ++c) row += s_Qt[(nx + r) * n + nx + c] * s_K[c * nx + b];
+        acc += s_K[r * nx + a] * row;
+      }
+      Vo[e] = acc;
+    } else {
+      const int a = e - nx * nx;
+      double acc = s_qt[a];
+      for (int r = 0; r < nu; ++r) acc += s_Qt[a * n + nx + r] * s_k[r];
+      for (int r = 0; r < nu; ++r) {
+        double inner = s_qt[nx + r];
+        for (int c = 0; c < nu; ++c) inner += s_Qt[(nx + r) * n + nx + c] * s_k[c];
+        acc += s_K[r * nx + a] * inner;
+      }
+      vo[a] = acc;
+    }
+  };
+  const int nT = nx * n, nQ = n * n + n, nV = nx * nx + nx;
+  const int rcT = lane < nT ? s_tab_n[lane] : 0;
+  const int rcQ = lane < n * n ? s_tab_n[lane] : 0;
+  const int abV = lane < nx * nx ? s_tab_x[lane] : 0;
+  __syncwarp();
+  for (int t = H; t >= 1; --t) {
+    const double *J = Jacs + (size_t)(t - 1) * nx * n;
+    const double *xt = states + (size_t)(t - 1) * nx, *ut = ctrls + (size_t)(t - 1) * nu;
+    if (lane < nT) do_T(lane, rcT, Vn, J);
+    for (int e = lane + 32; e < nT; e += 32) do_T(e, s_tab_n[e], Vn, J);
+    __syncwarp();
+    if (lane < nQ) do_Q(lane, rcQ, J, vn, xt, ut);
+    for (int e = lane + 32; e < nQ; e += 32) do_Q(e, e < n * n ? s_tab_n[e] : 0, J, vn, xt, ut);
+    __syncwarp();
+    if (nu == 1) {                                    // scalar Quu: K = -Qux / Quu, k = -qu / Quu (what gesv does for 1 x 1)
+      const double quu = s_Qt[nx * n + nx];
+      for (int col = lane; col <= nx; col += 32) {
+        const double y = ((col < nx) ? s_Qt[nx * n + col] : s_qt[nx]) / quu;
+        if (col < nx) s_K[col] = -y; else s_k[0] = -y;
+      }
+    } else {
+      if (lane == 0) {                                // LU of Quu with partial pivoting (LAPACK gesv)
+        for (int r = 0; r < nu; ++r) for (int c = 0; c < nu; ++c) s_LU[r * nu + c] = s_Qt[(nx + r) * n + nx + c];
+        for (int c = 0; c < nu; ++c) {
+          int pr = c; double best = fabs(s_LU[c * nu + c]);
+          for (int r = c + 1; r < nu; ++r) if (fabs(s_LU[r * nu + c]) > best) { best = fabs(s_LU[r * nu + c]); pr = r; }
+          s_piv[c] = pr;
+          if (pr != c) for (int q = 0; q < nu; ++q) { double tmp = s_LU[c * nu + q]; s_LU[c * nu + q] = s_LU[pr * nu + q]; s_LU[pr * nu + q] = tmp; }
+          for (int r = c + 1; r < nu; ++r) {
+            s_LU[r * nu + c] /= s_LU[c * nu + c];
+            for (int q = c + 1; q < nu; ++q) s_LU[r * nu + q] -= s_LU[r * nu + c] * s_LU[c * nu + q];
+          }
+        }
+      }
+      __syncwarp();
+      for (int col = lane; col <= nx; col += 32) {    // K = -Quu^-1 Qux, k = -Quu^-1 qu: one right-hand side per lane
+        double y[MAX_NU];
+        for (int r = 0; r < nu; ++r) y[r] = (col < nx) ? s_Qt[(nx + r) * n + col] : s_qt[nx + r];
+        for (int c = 0; c < nu; ++c) { const int pc = s_piv[c]; if (pc != c) { double tmp = y[c]; y[c] = y[pc]; y[pc] = tmp; } }
+        for (int r = 1; r < nu; ++r) for (int q = 0; q < r; ++q) y[r] -= s_LU[r * nu + q] * y[q];
+        for (int r = nu - 1; r >= 0; --r) { for (int q = r + 1; q < nu; ++q) y[r] -= s_LU[r * nu + q] * y[q]; y[r] /= s_LU[r * nu + r]; }
+        for (int r = 0; r < nu; ++r) { if (col < nx) s_K[r * nx + col] = -y[r]; else s_k[r] = -y[r]; }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      double lin = 0.0, quad = 0.0;
+      for (int r = 0; r < nu; ++r) {
+        lin += s_qt[nx + r] * s_k[r];
+        double row = 0.0;
+        for (int c = 0; c < nu; ++c) row += s_Qt[(nx + r) * n + nx + c] * s_k[c];
+        quad += s_k[r] * row;
+      }
+      lin_acc += lin; quad_acc += quad;
+    }
+    for (int e = lane; e < nu * nx + nu; e += 32) {
+      if (e < nu * nx) Ks[(size_t)(t - 1) * nu * nx + e] = s_K[e];
+      else ks[(size_t)(t - 1) * nu + (e - nu * nx)] = s_k[e - nu * nx];
+    }
+    if (lane < nV) do_V(lane, abV, Vnn, vnn);
+    for (int e = lane + 32; e < nV; e += 32) do_V(e, e < nx * nx ? s_tab_x[e] : 0, Vnn, vnn);
+    __syncwarp();
+    double *tp = Vn; Vn = Vnn; Vnn = tp;
+    tp = vn; vn = vnn; vnn = tp;
+  }
+  s_lin = lin_acc; s_quad = quad_acc;
+  if (lane == 0) { *lin_out = s_lin; *quad_out = s_quad; }
+}
+
 template <bool RES>
 __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const long long t_entry = clock64();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const IlqrNet &net = P.net;
@@ -260,17 +577,20 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
   double *s_LU = s_k + nu;           // nu*nu  LU factors of Quu
   double *s_red = s_LU + nu * nu;    // NWARPS
   double *s_obj = s_red + NWARPS;    // LS + 4
-  double *s_cst = s_obj + LS + 4;    // Q | R | F | goal | goalF | umin | umax | alphas
-  double *s_h = s_cst + ((cst_doubles(nx, nu, LS) + 1) & ~(size_t)1);   // LS * 2 * mw: per-group activation ping-pong
-  double *s_var = s_h + (size_t)LS * 2 * mw;
+  double *s_cst = sm + (((size_t)(s_obj + LS + 4 - sm) + 1) & ~(size_t)1);   // Q | R | F | goal | goalF | umin | umax | alphas (16-byte aligned from here on)
+  double *s_var = s_cst + ((cst_doubles(nx, nu, LS) + 1) & ~(size_t)1);
   const TrajLayout tl(H, nx, nu, LS);
   const size_t jpw = jac_per_warp(mw, n);
   const size_t net_d = ((size_t)net.total + 1) & ~(size_t)1;
-  // resident: network | trajectory block | Jacobian scratch, all derived from the shared array
+  // resident: network | trajectory block, then (both modes) the phase scratch: the line search's activations and
+  // K-quarter partials, which the Jacobian refresh's per-warp panels overlay when resident (the phases never overlap);
+  // all derived from the shared array
   const double *nb = RES ? s_var : P.net_blob;
   double *traj = RES ? s_var + net_d : P.traj;
-  double *jac_wk = (RES ? s_var + net_d + tl.total : P.jac_work) + (size_t)(warp < JAC_WARPS ? warp : 0) * jpw;
-  int *s_tab_n = reinterpret_cast<int *>(s_var + (RES ? net_d + tl.total + JAC_WARPS * jpw : 0));   // e -> (e / n) << 16 | e % n
+  double *s_h = s_var + (RES ? net_d + tl.total : 0);
+  const size_t phase_d = RES ? (ls_scratch(mw, LS) > JAC_WARPS * jpw ? ls_scratch(mw, LS) : JAC_WARPS * jpw) : ls_scratch(mw, LS);
+  double *jac_wk = (RES ? s_h : P.jac_work) + (size_t)(warp < JAC_WARPS ? warp : 0) * jpw;
+  int *s_tab_n = reinterpret_cast<int *>(s_h + phase_d);                          // e -> (e / n) << 16 | e % n
   int *s_tab_x = s_tab_n + n * n;                                                                    // e -> (e / nx) << 16 | e % nx
   __shared__ int s_flag[4];          // [0]=line search failed, [1]=used idx, [2]=refresh jac
   __shared__ int s_piv[MAX_NU];
@@ -305,6 +625,7 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
   for (int t = tid; t < nx; t += NT) states[t] = P.x0[t];
   for (int t = tid; t < H * nu; t += NT) ctrls[t] = P.uguess ? P.uguess[t] : 0.0;
   for (int t = tid; t < P.max_iter; t += NT) P.alpha_idx[t] = -1;
+  if (tid < 8) P.prof[8 + tid] = 0ull;
   __syncthreads();
 
   // per-step cost table for trajectory (xs (H+1,nx), us (H,nu)): c[i] = dt*(obs+ctrl), c[H] = terminal   (ilqr.py:124-129)
@@ -343,115 +664,11 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
   int converged = 0, n_iter = 0, ls_fail = 0;
   for (int itr = 0; itr < P.max_iter; ++itr) {
     n_iter = itr + 1;
-    // ---- backward pass (ilqr.py:159-187): ONE warp, warp barriers only
+    // ---- backward pass (ilqr.py:159-187): one warp (backward_pass)
     if (warp == 0) {
-      double *Vn = s_V0, *Vnn = s_V1, *vn = s_v0, *vnn = s_v1;
-      for (int t = lane; t < nx * nx; t += 32) Vn[t] = s_Fs[t];
-      for (int a = lane; a < nx; a += 32) {
-        double acc = 0.0;
-        for (int b = 0; b < nx; ++b) acc += s_Fs[a * nx + b] * states[(size_t)H * nx + b];   // no goal: cost.py:208
-        vn[a] = acc;
-      }
-      double lin_acc = 0.0, quad_acc = 0.0;               // lane 0's running sums (ilqr.py:178-179)
-      __syncwarp();
-      for (int t = H; t >= 1; --t) {
-        const double *J = Jacs + (size_t)(t - 1) * nx * n;
-        const double *xt = states + (size_t)(t - 1) * nx, *ut = ctrls + (size_t)(t - 1) * nu;
-        for (int e = lane; e < nx * n; e += 32) {         // T = Vn @ J
-          const int rc = s_tab_n[e], a = rc >> 16, c = rc & 0xffff;
-          const double *vr = Vn + a * nx, *jc = J + c;
-          double acc = 0.0;
-          for (int b = 0; b < nx; ++b) acc += vr[b] * jc[b * n];
-          s_T[e] = acc;
-        }
-        __syncwarp();
-        for (int e = lane; e < n * n + n; e += 32) {      // Qt = Ct + J^T T ; qt = ct + J^T vn
-          if (e < n * n) {
-            const int rc = s_tab_n[e], r = rc >> 16, c = rc & 0xffff;
-            const double *jr = J + r, *tc = s_T + c;
-            double acc = 0.0;
-            for (int a = 0; a < nx; ++a) acc += jr[a * n] * tc[a * n];
-            s_Qt[e] = s_Ct[e] + acc;
-          } else {
-            const int r = e - n * n;
-            const double *cr = s_Ct + r * n;
-            double ct = 0.0;
-            if (r < nx) { for (int b = 0; b < nx; ++b) ct += cr[b] * (xt[b] - c_goal[b]); }
-            else { for (int b = 0; b < nu; ++b) ct += cr[nx + b] * ut[b]; }
-            double acc = 0.0;
-            for (int a = 0; a < nx; ++a) acc += J[a * n + r] * vn[a];
-            s_qt[r] = ct + acc;
-          }
-        }
-        __syncwarp();
-        {
-          if (lane == 0) {                                // LU of Quu with partial pivoting (LAPACK gesv)
-            for (int r = 0; r < nu; ++r) for (int c = 0; c < nu; ++c) s_LU[r * nu + c] = s_Qt[(nx + r) * n + nx + c];
-            for (int c = 0; c < nu; ++c) {
-              int pr = c; double best = fabs(s_LU[c * nu + c]);
-              for (int r = c + 1; r < nu; ++r) if (fabs(s_LU[r * nu + c]) > best) { best = fabs(s_LU[r * nu + c]); pr = r; }
-              s_piv[c] = pr;
-              if (pr != c) for (int q = 0; q < nu; ++q) { double tmp = s_LU[c * nu + q]; s_LU[c * nu + q] = s_LU[pr * nu + q]; s_LU[pr * nu + q] = tmp; }
-              for (int r = c + 1; r < nu; ++r) {
-                s_LU[r * nu + c] /= s_LU[c * nu + c];
-                for (int q = c + 1; q < nu; ++q) s_LU[r * nu + q] -= s_LU[r * nu + c] * s_LU[c * nu + q];
-              }
-            }
-          }
-          __syncwarp();
-          for (int col = lane; col <= nx; col += 32) {    // K = -Quu^-1 Qux, k = -Quu^-1 qu: one right-hand side per lane
-            double y[MAX_NU];
-            for (int r = 0; r < nu; ++r) y[r] = (col < nx) ? s_Qt[(nx + r) * n + col] : s_qt[nx + r];
-            for (int c = 0; c < nu; ++c) { const int pc = s_piv[c]; if (pc != c) { double tmp = y[c]; y[c] = y[pc]; y[pc] = tmp; } }
-            for (int r = 1; r < nu; ++r) for (int q = 0; q < r; ++q) y[r] -= s_LU[r * nu + q] * y[q];
-            for (int r = nu - 1; r >= 0; --r) { for (int q = r + 1; q < nu; ++q) y[r] -= s_LU[r * nu + q] * y[q]; y[r] /= s_LU[r * nu + r]; }
-            for (int r = 0; r < nu; ++r) { if (col < nx) s_K[r * nx + col] = -y[r]; else s_k[r] = -y[r]; }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) {
-          double lin = 0.0, quad = 0.0;
-          for (int r = 0; r < nu; ++r) {
-            lin += s_qt[nx + r] * s_k[r];
-            double row = 0.0;
-            for (int c = 0; c < nu; ++c) row += s_Qt[(nx + r) * n + nx + c] * s_k[c];
-            quad += s_k[r] * row;
-          }
-          lin_acc += lin; quad_acc += quad;
-        }
-        for (int e = lane; e < nu * nx + nu; e += 32) {
-          if (e < nu * nx) Ks[(size_t)(t - 1) * nu * nx + e] = s_K[e];
-          else ks[(size_t)(t - 1) * nu + (e - nu * nx)] = s_k[e - nu * nx];
-        }
-        for (int e = lane; e < nx * nx + nx; e += 32) {   // value update (ilqr.py:186-187)
-          if (e < nx * nx) {
-            const int ab = s_tab_x[e], a = ab >> 16, b = ab & 0xffff;
-            double acc = s_Qt[a * n + b];
-            for (int r = 0; r < nu; ++r) acc += s_Qt[a * n + nx + r] * s_K[r * nx + b];
-            for (int r = 0; r < nu; ++r) acc += s_K[r * nx + a] * s_Qt[(nx + r) * n + b];
-            for (int r = 0; r < nu; ++r) {
-              double row = 0.0;
-              for (int c = 0; c < nu; ++c) row += s_Qt[(nx + r) * n + nx + c] * s_K[c * nx + b];
-              acc += s_K[r * nx + a] * row;
-            }
-            Vnn[e] = acc;
-          } else {
-            const int a = e - nx * nx;
-            double acc = s_qt[a];
-            for (int r = 0; r < nu; ++r) acc += s_Qt[a * n + nx + r] * s_k[r];
-            for (int r = 0; r < nu; ++r) {
-              double inner = s_qt[nx + r];
-              for (int c = 0; c < nu; ++c) inner += s_Qt[(nx + r) * n + nx + c] * s_k[c];
-              acc += s_K[r * nx + a] * inner;
-            }
-            vnn[a] = acc;
-          }
-        }
-        __syncwarp();
-        double *tp = Vn; Vn = Vnn; Vnn = tp;
-        tp = vn; vn = vnn; vnn = tp;
-      }
-      if (lane == 0) { s_lin = lin_acc; s_quad = quad_acc; }
+      BackwardSmem bs{s_Ct, s_Fs, s_V0, s_V1, s_v0, s_v1, s_T, s_Qt, s_qt, s_K, s_k, s_LU, s_tab_n, s_tab_x, s_piv};
+      if (nx == 4 && nu == 1) backward_pass<4, 1>(P, bs, states, ctrls, Jacs, Ks, ks, c_goal, &s_lin, &s_quad, lane);
+      else backward_pass<0, 0>(P, bs, states, ctrls, Jacs, Ks, ks, c_goal, &s_lin, &s_quad, lane);
     }
     __syncthreads();
     lap(1);
@@ -460,40 +677,11 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
     for (int t = tid; t < H * nu; t += NT) ksq += ks[t] * ks[t];
     const double ks_norm = sqrt(block_sum(ksq, s_red, tid));
 
-    // ---- line-search rollouts (ilqr.py:190-205): alpha j is rolled out by group j on its own, H sequential steps with
-    //      group barriers only; alphas beyond the number of groups are taken in further rounds
-    const int n_groups = NWARPS / G;
-    for (int j = grp; j < LS; j += n_groups) {
-      const int bar = 1 + (grp % 15);
-      double *h0 = s_h + (size_t)(grp % LS) * 2 * mw, *h1 = h0 + mw;
-      double *xs = ls_states + (size_t)j * (H + 1) * nx, *us = ls_ctrls + (size_t)j * H * nu;
-      const double alpha = c_alphas[j];
-      for (int a = gl; a < nx; a += gthr) xs[a] = P.x0[a];
-      group_sync(bar, gthr);
-      for (int i = 0; i < H; ++i) {
-        const double *xi = xs + (size_t)i * nx, *x_ref = states + (size_t)i * nx;
-        // z-scored input: the state columns, and the control columns computed in place (ilqr.py:201-204)
-        for (int c = gl; c < n; c += gthr) {
-          double v;
-          if (c < nx) {
-            v = xi[c];
-          } else {
-            const int a = c - nx;
-            const double *kr = Ks + ((size_t)i * nu + a) * nx;
-            double fb = 0.0;
-            for (int b = 0; b < nx; ++b) fb += kr[b] * (xi[b] - x_ref[b]);
-            double u = alpha * ks[(size_t)i * nu + a] + ctrls[(size_t)i * nu + a] + fb;
-            if (P.bounded) u = fmin(fmax(u, c_umin[a]), c_umax[a]);     // np.clip, ilqr.py:203-204
-            us[(size_t)i * nu + a] = u;
-            v = u;
-          }
-          h0[c] = (v - xu_mean[c]) / xu_std[c];
-        }
-        group_sync(bar, gthr);
-        const double *out = group_forward(net, nb, h0, h1, gl, gthr, bar);
-        for (int a = gl; a < nx; a += gthr) xs[(size_t)(i + 1) * nx + a] = xi[a] + (out[a] * dy_std[a] + dy_mean[a]);
-        group_sync(bar, gthr);
-      }
+    // ---- line-search rollouts (ilqr.py:190-205)
+    if (warp < LS_WARPS) {
+      double *part = s_h + (size_t)2 * mw * ls_cols(LS);
+      if (LS <= 10) ls_rollouts<10, 1>(P, nb, s_h, part, states, ctrls, Ks, ks, ls_states, ls_ctrls, c_alphas, c_umin, c_umax, tid);
+      else ls_rollouts<10, 2>(P, nb, s_h, part, states, ctrls, Ks, ks, ls_states, ls_ctrls, c_alphas, c_umin, c_umax, tid);
     }
     __syncthreads();
     lap(2);
@@ -628,6 +816,7 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
     net.woff[l] = off; off += net.wstride[l] * mlp->dims[l + 1]; off = (off + 1) & ~1;
     net.boff[l] = off; off += mlp->dims[l + 1]; off = (off + 1) & ~1;
   }
+  net.w0s = off; off += (mlp->dims[0] * mlp->dims[1] + 1) & ~1;
   net.xu_mean = off; off += (n + 1) & ~1;
   net.xu_std = off; off += (n + 1) & ~1;
   net.dy_mean = off; off += (nx + 1) & ~1;
@@ -641,6 +830,8 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
       hb[net.boff[l] + j] = mlp->b[l][j];
     }
   }
+  for (int j = 0; j < mlp->dims[1]; ++j)
+    for (int c = 0; c < n; ++c) hb[net.w0s + (size_t)j * n + c] = mlp->W[0][(size_t)j * n + c] / mlp->xu_std[c];
   for (int j = 0; j < n; ++j) { hb[net.xu_mean + j] = mlp->xu_mean[j]; hb[net.xu_std + j] = mlp->xu_std[j]; }
   for (int j = 0; j < nx; ++j) { hb[net.dy_mean + j] = mlp->dy_mean[j]; hb[net.dy_std + j] = mlp->dy_std[j]; }
   const int mw = net.max_width;
@@ -655,7 +846,7 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
   const size_t o_cst = take(cst_doubles(nx, nu, LS));
   h->o_x0 = take(nx); h->o_ug = take((size_t)H * nu);
   const size_t o_st = take((size_t)(H + 1) * nx), o_ct = take((size_t)H * nu), o_Ks = take((size_t)H * nu * nx), o_ks = take((size_t)H * nu);
-  const size_t o_traj = take(tl.total), o_jac = take((size_t)JAC_WARPS * jpw);
+  const size_t o_traj = take(tl.total), o_jac = take((size_t)JAC_WARPS * jpw + 8);   // + slack: the last column strip may read past a panel
   std::vector<double> hc(cst_doubles(nx, nu, LS), 0.0);
   {
     double *q = hc.data();
@@ -674,8 +865,8 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
   if (e == cudaSuccess) e = cudaMemset(h->d_work, 0, woff * sizeof(double));
   if (e == cudaSuccess) e = cudaMemcpy(h->d_work + o_cst, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_int, (3 + cfg->max_iter) * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&h->d_prof, 8 * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMemset(h->d_prof, 0, 8 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_prof, 16 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->d_prof, 0, 16 * sizeof(unsigned long long));
   double *w = h->d_work;
   P.net_blob = h->d_net;
   P.cst = w + o_cst;
@@ -687,14 +878,16 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
     // shared memory: the small matrices, the cost constants, the per-group activations and the index tables always;
     // network + trajectory block + Jacobian scratch when they all fit next to them
     size_t fixed = (size_t)n * n * 2 + (size_t)nx * nx * 3 + 2 * nx + (size_t)nx * n + n + (size_t)nu * nx + nu +
-                   (size_t)nu * nu + NWARPS + LS + 4 + ((cst_doubles(nx, nu, LS) + 1) & ~(size_t)1) + (size_t)LS * 2 * mw;
+                   (size_t)nu * nu + NWARPS + LS + 4 + 1 + ((cst_doubles(nx, nu, LS) + 1) & ~(size_t)1);
     const size_t tabs = ((size_t)n * n + (size_t)nx * nx + 1) / 2 + 1;       // ints, in doubles
-    const size_t var = (((size_t)net.total + 1) & ~(size_t)1) + tl.total + (size_t)JAC_WARPS * jpw;
+    const size_t jacs = (size_t)JAC_WARPS * jpw, lss = ls_scratch(mw, LS);
+    const size_t var = (((size_t)net.total + 1) & ~(size_t)1) + tl.total + (jacs > lss ? jacs : lss);
+    fixed += tabs;
     int max_optin = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
     const size_t cap = (size_t)max_optin > 2048 ? ((size_t)max_optin - 2048) / sizeof(double) : 0;
-    h->resident = (fixed + tabs + var <= cap) && !getenv("AMPC_ILQR_NO_SMEM");
-    const size_t total = fixed + tabs + (h->resident ? var : 0);
+    h->resident = (fixed + var <= cap) && !getenv("AMPC_ILQR_NO_SMEM");
+    const size_t total = fixed + (h->resident ? var : lss);
     h->smem = total * sizeof(double);
     if (e == cudaSuccess && total > cap) {
       ampc_set_error("iLQR: %zu B of shared memory needed", h->smem);
@@ -729,6 +922,12 @@ extern "C" int ampc_ilqr_debug_profile(ampc_ilqr *h, unsigned long long *out8) {
   AMPC_REQUIRE(h && out8, AMPC_ERR_INVALID, "null argument");
   AMPC_CUDA_CHECK(cudaSetDevice(h->device));
   AMPC_CUDA_CHECK(cudaDeviceSynchronize());
+  if (getenv("AMPC_ILQR_LS_PROFILE")) {   // the line-search phase split (thread 0): controls, main loops, barrier, combine, barrier, update
+    unsigned long long v[16];
+    AMPC_CUDA_CHECK(cudaMemcpy(v, h->d_prof, sizeof(v), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "ilqr line search (cycles): controls %llu, main loops %llu, barrier %llu, combine %llu, barrier %llu, update %llu\n",
+            v[8], v[9], v[10], v[11], v[12], v[13]);
+  }
   AMPC_CUDA_CHECK(cudaMemcpy(out8, h->d_prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return AMPC_OK;
 }

@@ -470,6 +470,13 @@ def gpu_arm_mppi(args, wl, d):
         peaks = measured_peaks()
         ms_per_step = total_ms / args.steps
         value = args.steps / (total_ms * 1e-3)
+        value_note = "solves per second"
+        if args.scaling == "weak" and world > 1:
+            # weak scaling: every solve rolls out N x the base problem's samples; the whole-job aggregate is counted in
+            # units of the base problem (K per GPU), so that it is comparable across N
+            value *= world
+            value_note = ("weak scaling: %d x solves per second = solves of the base problem (K=%d) per second; one solve of "
+                          "K=%d samples takes ms_per_step" % (world, wl["K"] // world, wl["K"]))
         flops = mlp_flops_per_solve(w, wl["K"], wl["H"])
         traffic, traffic_src = ncu_traffic(wl["name"], ctl.precision, world)
         fused = world > 1 and ctl.exchange == "nvlink"
@@ -481,7 +488,8 @@ def gpu_arm_mppi(args, wl, d):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None,
             "dtype": {"bf16": "bf16", "fp16": "fp16"}.get(ctl.precision, "f32"), "data": "synthetic",
-            "config": {"workload": wl["label"], "noise": "in-kernel Philox4x32-10", "precision": ctl.precision,
+            "config": {"workload": wl["label"], "value_is": value_note, "noise": "in-kernel Philox4x32-10",
+                       "precision": ctl.precision,
                        "precision_note": {"fp16": "tcgen05 kind::f16 with IEEE-half operands (11-bit significands = the "
                                                   "operand precision of tf32), fp32 accumulate/state/cost; deviation of "
                                                   "the updated action sequence from the float64 oracle at this size: "
@@ -499,7 +507,8 @@ def gpu_arm_mppi(args, wl, d):
                        "ms_per_step_min_median_max": [float(per_step_ms.min()), float(np.median(per_step_ms)),
                                                       float(per_step_ms.max())]},
             "clocks": clk.summary(),
-            "e2e": {"value": args.steps / e2e_s, "unit": unit, "h2d_bytes_per_step": 4 * nx,
+            "e2e": {"value": args.steps / e2e_s * (world if (args.scaling == "weak" and world > 1) else 1), "unit": unit,
+                    "h2d_bytes_per_step": 4 * nx,
                     "d2h_bytes_per_step": 4 * nu, "api": "autompc_b200.MPPI.run(state, new_obs) with NumPy float64 buffers",
                     "transfer": "host observation -> pinned float32 -> kernel parameters (H2D with the launch); control "
                                 "written by the kernel's last CTA into mapped pinned host memory (D2H), one stream "
