@@ -105,8 +105,13 @@ def evaluate_candidates(controllers, init_obs, max_steps, sim_model, group=None,
     mine = [i for i in range(len(controllers)) if i % world == rank]
     T = int(max_steps)
     sims = {}
-    for i in mine:
-        c = controllers[i]
+    for i, c in enumerate(controllers):
+        if i % world != rank:
+            # the reference evaluates candidates one after the other and every reset() draws a new nominal sequence from
+            # the global NumPy stream (mppi.py:99, :107-108): consume the draws of the candidates other ranks own, so that
+            # ranks seeded alike give every candidate the sequence the sequential loop would have given it
+            np.random.normal(scale=np.sqrt(c.sigma), size=(c.H, c.dim_ctrl))
+            continue
         _check(c, None, None, sim_model)
         if c.device not in sims:
             sims[c.device] = _sim_handle(c, sim_model)
