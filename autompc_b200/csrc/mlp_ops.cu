@@ -25,6 +25,7 @@ struct ampc_mlp {
 namespace {
 
 constexpr int NT = 128;
+constexpr int NTJ = 512;   // Jacobian kernels: a [width x (nx+nu)] panel per layer is 5 888 dot products at 3x256
 
 // threshold terms of a trajectory cost (thresh_cost.py:27-32, :73-77): n_box x [lo (nx) | hi (nx) | weight]
 __device__ __forceinline__ double ampc_box_cost_f64(const double *box, int n_box, int nx, const double *x) {
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(NT) pred_batch_kernel(const AmpcMlpF64 net, in
     Xn[(size_t)s * nx + j] = X[(size_t)s * nx + j] + (out[j] * net.dy_std[j] + net.dy_mean[j]);
 }
 
-__global__ void __launch_bounds__(NT) pred_diff_kernel(const AmpcMlpF64 net, int batch, const double *X,
+__global__ void __launch_bounds__(NTJ) pred_diff_kernel(const AmpcMlpF64 net, int batch, const double *X,
                                                        const double *U, double *Xn, double *Jx, double *Ju) {
   extern __shared__ double sm_d[];
   const int s = blockIdx.x;
@@ -63,16 +64,16 @@ __global__ void __launch_bounds__(NT) pred_diff_kernel(const AmpcMlpF64 net, int
   const int nx = net.nx, nu = net.nu, nin = nx + nu;
   double *h0 = sm_d, *h1 = h0 + net.max_width, *g = h1 + net.max_width;
   double *J0 = g + net.max_width, *J1 = J0 + (size_t)net.max_width * nin;
-  for (int j = threadIdx.x; j < nin; j += NT) {
+  for (int j = threadIdx.x; j < nin; j += NTJ) {
     const double v = j < nx ? X[(size_t)s * nx + j] : U[(size_t)s * nu + (j - nx)];
     h0[j] = (v - net.xu_mean[j]) / net.xu_std[j];
   }
   __syncthreads();
   const double *J;
-  const double *out = ampc_mlp_f64_forward_jac(net, h0, h1, g, J0, J1, &J, threadIdx.x, NT);
-  for (int j = threadIdx.x; j < nx; j += NT)
+  const double *out = ampc_mlp_f64_forward_jac(net, h0, h1, g, J0, J1, &J, threadIdx.x, NTJ);
+  for (int j = threadIdx.x; j < nx; j += NTJ)
     Xn[(size_t)s * nx + j] = X[(size_t)s * nx + j] + (out[j] * net.dy_std[j] + net.dy_mean[j]);
-  for (int t = threadIdx.x; t < nx * nin; t += NT) {
+  for (int t = threadIdx.x; t < nx * nin; t += NTJ) {
     const int r = t / nin, c = t - r * nin;
     const double v = J[t] * net.dy_std[r];                     // mlp.py:298
     if (c < nx) Jx[((size_t)s * nx + r) * nx + c] = v + (r == c ? 1.0 : 0.0);   // mlp.py:303
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(NT) pred_diff_kernel(const AmpcMlpF64 net, int
 // (get_constraint).  WANT_JAC = true: the values of get_jacobian(x, False) in the reference's order, per knot
 // [ d pred / d state (nx*nx, row-major) | d pred / d ctrl (nx*nu) | -1 x nx ].
 template <bool WANT_JAC>
-__global__ void __launch_bounds__(NT) nmpc_knot_kernel(const AmpcMlpF64 net, int H, const double *xvec, double *out) {
+__global__ void __launch_bounds__(NTJ) nmpc_knot_kernel(const AmpcMlpF64 net, int H, const double *xvec, double *out) {
   extern __shared__ double sm_d[];
   const int i = blockIdx.x;
   if (i >= H) return;
@@ -93,27 +94,27 @@ __global__ void __launch_bounds__(NT) nmpc_knot_kernel(const AmpcMlpF64 net, int
   const double *xs = xvec + (size_t)i * nx, *xn = xvec + (size_t)(i + 1) * nx;
   const double *us = xvec + (size_t)(H + 1) * nx + (size_t)i * nu;
   double *h0 = sm_d, *h1 = h0 + net.max_width, *g = h1 + net.max_width;
-  for (int j = threadIdx.x; j < nin; j += NT) {
+  for (int j = threadIdx.x; j < nin; j += NTJ) {
     const double v = j < nx ? xs[j] : us[j - nx];
     h0[j] = (v - net.xu_mean[j]) / net.xu_std[j];
   }
   __syncthreads();
   if constexpr (!WANT_JAC) {
-    const double *o = ampc_mlp_f64_forward(net, h0, h1, nullptr, threadIdx.x, NT);
-    for (int j = threadIdx.x; j < nx; j += NT)
+    const double *o = ampc_mlp_f64_forward(net, h0, h1, nullptr, threadIdx.x, NTJ);
+    for (int j = threadIdx.x; j < nx; j += NTJ)
       out[(size_t)i * nx + j] = -xn[j] + (xs[j] + (o[j] * net.dy_std[j] + net.dy_mean[j]));     // nmpc.py:109
   } else {
     double *J0 = g + net.max_width, *J1 = J0 + (size_t)net.max_width * nin;
     const double *J;
-    ampc_mlp_f64_forward_jac(net, h0, h1, g, J0, J1, &J, threadIdx.x, NT);
+    ampc_mlp_f64_forward_jac(net, h0, h1, g, J0, J1, &J, threadIdx.x, NTJ);
     double *o = out + (size_t)i * (nx * nx + nx * nu + nx);
-    for (int t = threadIdx.x; t < nx * nin; t += NT) {
+    for (int t = threadIdx.x; t < nx * nin; t += NTJ) {
       const int r = t / nin, c = t - r * nin;
       const double v = J[t] * net.dy_std[r];                                                  // mlp.py:298
       if (c < nx) o[r * nx + c] = v + (r == c ? 1.0 : 0.0);                                   // nmpc.py:180-181
       else o[nx * nx + r * nu + (c - nx)] = v;                                                // nmpc.py:182-183
     }
-    for (int j = threadIdx.x; j < nx; j += NT) o[nx * nx + nx * nu + j] = -1.0;               // nmpc.py:184-185
+    for (int j = threadIdx.x; j < nx; j += NTJ) o[nx * nx + nx * nu + j] = -1.0;               // nmpc.py:184-185
   }
 }
 
@@ -321,7 +322,7 @@ static int run_mlp(ampc_mlp *m, int batch, const double *X, const double *U, dou
   cudaError_t e = cudaMemcpy(dX, X, nX * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(dU, U, nU * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    if (Jx) pred_diff_kernel<<<batch, NT, m->smem_diff>>>(m->net, batch, dX, dU, dXn, dJx, dJu);
+    if (Jx) pred_diff_kernel<<<batch, NTJ, m->smem_diff>>>(m->net, batch, dX, dU, dXn, dJx, dJu);
     else pred_batch_kernel<<<batch, NT, m->smem_pred>>>(m->net, batch, dX, dU, dXn);
     ampc_count_launch();
     e = cudaGetLastError();
@@ -377,8 +378,8 @@ static int run_nmpc(ampc_mlp *m, int32_t H, const double *x, double *out, bool j
   AMPC_CUDA_CHECK(cudaMalloc(&d, (n_in + n_out) * sizeof(double)));
   cudaError_t e = cudaMemcpy(d, x, n_in * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    if (jac) nmpc_knot_kernel<true><<<H, NT, m->smem_diff>>>(m->net, H, d, d + n_in);
-    else nmpc_knot_kernel<false><<<H, NT, m->smem_diff>>>(m->net, H, d, d + n_in);
+    if (jac) nmpc_knot_kernel<true><<<H, NTJ, m->smem_diff>>>(m->net, H, d, d + n_in);
+    else nmpc_knot_kernel<false><<<H, NTJ, m->smem_diff>>>(m->net, H, d, d + n_in);
     ampc_count_launch();
     e = cudaGetLastError();
   }

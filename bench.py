@@ -425,11 +425,11 @@ def gpu_arm_mppi(args, wl, d):
         da = float(np.abs(act_sharded - single.act_sequence).max())
         single.close()
         (du, da), _ = d.reduce([du, da], [0.0])
-        parity = {"max_abs_du_vs_single_gpu": du, "max_abs_dact_vs_single_gpu": da, "atol": 5e-6,
+        parity = {"max_abs_du_vs_single_gpu": du, "max_abs_dact_vs_single_gpu": da, "atol": 2e-5,
                   "what": "first sharded solve vs one GPU rolling out all K samples from the same action sequence, seed "
                           "and counter (normalised controls); the only difference is the fp32 summation order of the "
                           "softmax merge; max over ranks"}
-        assert du < 5e-6 and da < 5e-6, "sharded solve differs from the single-GPU solve: %g / %g" % (du, da)
+        assert du < 2e-5 and da < 2e-5, "sharded solve differs from the single-GPU solve: %g / %g" % (du, da)
 
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
@@ -465,6 +465,34 @@ def gpu_arm_mppi(args, wl, d):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     (total_ms, e2e_s), (launches,) = d.reduce([total_ms, e2e_s], [float(launches)])
+    # ---- N>1, default (strong) scaling: the same machine on the weak-scaled problem (K per GPU fixed), as an extra key;
+    #      its launches are outside the timed region above and are not counted in gpu_launches
+    weak = None
+    if world > 1 and args.scaling == "strong" and not args.no_weak_probe:
+        Kw = wl["K"] * world
+        np.random.seed(0)
+        ctl_w = MPPI(system, task, model, horizon=wl["H"], num_path=Kw, sigma=wl["sigma"], lmda=wl["lmda"], seed=0,
+                     noise="philox", precision=ctl.precision, device=local_rank, group=d.group, exchange=ctl.exchange)
+        n_w = min(args.steps, 50)
+        for _ in range(5):
+            flush.zero_()
+            ctl_w.solve_device(x0_dev, u_dev, stream=stream.cuda_stream)
+        d.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_w)]
+        for a, b in ev:
+            flush.zero_()
+            a.record(stream)
+            ctl_w.solve_device(x0_dev, u_dev, stream=stream.cuda_stream)
+            b.record(stream)
+        d.barrier()
+        ms_w = float(sum(a.elapsed_time(b) for a, b in ev))
+        (ms_w,), _ = d.reduce([ms_w], [0.0])
+        ctl_w.close()
+        weak = {"K_total": Kw, "K_per_gpu": wl["K"], "steps": n_w, "ms_per_step": ms_w / n_w,
+                "base_problem_solves_per_s": world * n_w / (ms_w * 1e-3),
+                "what": "the same run on the weak-scaled problem (K=%d per GPU, one solve of K=%d): solves of the base "
+                        "problem per second = N x solves/s; `python bench.py --scaling weak` reports it as the line's value"
+                        % (wl["K"], Kw)}
     if rank == 0:
         metric, unit = METRICS[wl["name"]]
         peaks = measured_peaks()
@@ -523,6 +551,8 @@ def gpu_arm_mppi(args, wl, d):
         }
         if parity is not None:
             line["parity"] = parity
+        if weak is not None:
+            line["weak_scaling"] = weak
         if world == 1 and not args.no_cpu:
             budget = float(os.environ.get("AMPC_CPU_BUDGET_S", "24"))
             rows = cpu_rows(wl, budget)
@@ -680,6 +710,7 @@ def main():
     ap.add_argument("--exchange", default="nvlink", choices=["nvlink", "nccl"],
                     help="N>1: how the ranks' softmax records meet (fused NVLink peer stores, or NCCL all-gather)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-weak-probe", action="store_true", help="N>1, strong scaling: skip the extra weak-scaling timing")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
