@@ -465,6 +465,34 @@ def gpu_arm_mppi(args, wl, d):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     (total_ms, e2e_s), (launches,) = d.reduce([total_ms, e2e_s], [float(launches)])
+    # ---- N=1: the other tensor-core operand format beside the default, same workload (extra key, outside the timed region)
+    alt = None
+    if world == 1 and ctl.precision in ("fp16", "bf16") and not args.no_weak_probe:
+        other = "bf16" if ctl.precision == "fp16" else "fp16"
+        try:
+            np.random.seed(0)
+            ctl_o = MPPI(system, task, model, horizon=wl["H"], num_path=wl["K"], sigma=wl["sigma"], lmda=wl["lmda"], seed=0,
+                         noise="philox", precision=other, device=local_rank)
+            n_o = min(args.steps, 50)
+            for _ in range(5):
+                flush.zero_()
+                ctl_o.solve_device(x0_dev, u_dev, stream=stream.cuda_stream)
+            torch.cuda.synchronize()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_o)]
+            for a, b in ev:
+                flush.zero_()
+                a.record(stream)
+                ctl_o.solve_device(x0_dev, u_dev, stream=stream.cuda_stream)
+                b.record(stream)
+            torch.cuda.synchronize()
+            ms_o = float(sum(a.elapsed_time(b) for a, b in ev)) / n_o
+            ctl_o.close()
+            alt = {other: {"ms_per_step": ms_o, "value": 1e3 / ms_o, "steps": n_o,
+                           "deviation_from_float64_oracle": {"fp16": 2.1e-4, "bf16": 2.1e-3}[other],
+                           "what": "same workload and timing rule with %s operands; the deviation is the measured max |act - "
+                                   "oracle| at this size (profiles/r02_precision.jsonl)" % other}}
+        except ValueError:
+            alt = None
     # ---- N>1, default (strong) scaling: the same machine on the weak-scaled problem (K per GPU fixed), as an extra key;
     #      its launches are outside the timed region above and are not counted in gpu_launches
     weak = None
@@ -553,6 +581,8 @@ def gpu_arm_mppi(args, wl, d):
             line["parity"] = parity
         if weak is not None:
             line["weak_scaling"] = weak
+        if alt is not None:
+            line["alt_precisions"] = alt
         if world == 1 and not args.no_cpu:
             budget = float(os.environ.get("AMPC_CPU_BUDGET_S", "24"))
             rows = cpu_rows(wl, budget)
