@@ -740,7 +740,7 @@ def main():
     ap.add_argument("--exchange", default="nvlink", choices=["nvlink", "nccl"],
                     help="N>1: how the ranks' softmax records meet (fused NVLink peer stores, or NCCL all-gather)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-weak-probe", action="store_true", help="N>1, strong scaling: skip the extra weak-scaling timing")
+    ap.add_argument("--no-weak-probe", action="store_true", help="skip the extra probes outside the timed region (weak-scaled problem at N>1, other operand format at N=1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
