@@ -284,6 +284,104 @@ __device__ __forceinline__ void ampc_merge_records(const float *recs, int n_recs
   }
 }
 
+// The same merge for the in-kernel tail of the tensor-core kernel, where it is on the critical path of every solve
+// (one CTA, ~1 % of the kernel per 5 k cycles) and a large scratch is free (the weight image is dead by then):
+//   * (m_b, s_b) of every record are fetched ONCE (one float2 each) and kept in shared memory -- the generic routine
+//     walks the records three times, each walk a dependent L2 round trip of lines other SMs have just written;
+//   * the first MU records of every thread's share of W are requested BEFORE that, so their latency hides under the
+//     min / sum passes; MU = 32 loads in flight per thread leave one more round trip for 128 records.
+// Needs HN and rec_stride even and 64 + 3 n_recs + G HN floats of scratch; returns false (nothing done) otherwise.
+template <int MU>
+__device__ __forceinline__ bool ampc_merge_records_tail(const float *recs, int n_recs, int rec_stride, int HN, int nu,
+                                                        float inv_lmda, const float *s_act_shift, const float *scale,
+                                                        float *act_seq, float *u_out, float *record_out, float *s_scratch,
+                                                        int scratch_floats) {
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  const int E2 = HN >> 1;
+  int G = E2 > 0 ? nthr / E2 : 0;
+  if (G > 8) G = 8;
+  if (G > n_recs) G = n_recs;
+  if (G < 1 || (HN & 1) || (rec_stride & 1) || 64 + 3 * n_recs + G * HN > scratch_floats) return false;   // uniform
+  float *s_m = s_scratch + 64, *s_s = s_m + n_recs, *s_rs = s_s + n_recs, *s_part = s_rs + n_recs;        // [G][HN]
+  const int g = tid / E2, pe = tid - g * E2;
+  const bool active = g < G;
+  const float *base = recs + 2 + 2 * pe;
+  float2 v[MU];
+  if (active) {
+#pragma unroll
+    for (int u = 0; u < MU; ++u) {
+      const int b = g + u * G;
+      v[u] = b < n_recs ? __ldcg(reinterpret_cast<const float2 *>(base + (size_t)b * rec_stride)) : make_float2(0.f, 0.f);
+    }
+  }
+  float m = INFINITY;
+  for (int b = tid; b < n_recs; b += nthr) {
+    const float2 ms = __ldcg(reinterpret_cast<const float2 *>(recs + (size_t)b * rec_stride));
+    s_m[b] = ms.x;
+    s_s[b] = ms.y;
+    m = fminf(m, ms.x);
+  }
+  m = ampc_warp_min(m);
+  if (lane == 0) s_scratch[warp] = m;
+  __syncthreads();
+  m = s_scratch[0];
+  for (int w = 1; w < nwarp; ++w) m = fminf(m, s_scratch[w]);
+  float s = 0.f;
+  for (int b = tid; b < n_recs; b += nthr) {
+    const float rs = expf(-(s_m[b] - m) * inv_lmda);
+    s_rs[b] = rs;
+    s += s_s[b] * rs;
+  }
+  s = ampc_warp_sum(s);
+  if (lane == 0) s_scratch[32 + warp] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int w = 0; w < nwarp; ++w) s += s_scratch[32 + w];
+  if (active) {
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < MU; ++u) {
+      const int b = g + u * G;
+      const float r = b < n_recs ? s_rs[b] : 0.f;
+      acc.x = fmaf(v[u].x, r, acc.x);
+      acc.y = fmaf(v[u].y, r, acc.y);
+    }
+    for (int b0 = g + MU * G; b0 < n_recs; b0 += G * MU) {
+#pragma unroll
+      for (int u = 0; u < MU; ++u) {
+        const int b = b0 + u * G;
+        v[u] = b < n_recs ? __ldcg(reinterpret_cast<const float2 *>(base + (size_t)b * rec_stride)) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < MU; ++u) {
+        const int b = b0 + u * G;
+        const float r = b < n_recs ? s_rs[b] : 0.f;
+        acc.x = fmaf(v[u].x, r, acc.x);
+        acc.y = fmaf(v[u].y, r, acc.y);
+      }
+    }
+    s_part[g * HN + 2 * pe] = acc.x;
+    s_part[g * HN + 2 * pe + 1] = acc.y;
+  }
+  __syncthreads();
+  for (int e = tid; e < HN; e += nthr) {
+    float acc = 0.f;
+    for (int gg = 0; gg < G; ++gg) acc += s_part[gg * HN + e];
+    if (record_out) {
+      record_out[2 + e] = acc;
+    } else {
+      const float val = s_act_shift[e] + acc / s;
+      act_seq[e] = val;
+      if (e < nu) u_out[e] = val * scale[e];
+    }
+  }
+  if (record_out && tid == 0) {
+    record_out[0] = m;
+    record_out[1] = s;
+  }
+  return true;
+}
+
 // ------------------------------------------------------- NVLink peer exchange ---
 // Mailbox of a rank (in its own HBM, mapped into every peer): 2 slots x [ world records of `rec` floats ]
 // followed by 2 x world 32-bit flags.  Called by ONE CTA per GPU (the last to finish) once the shard's record

@@ -796,8 +796,11 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   if (s_last) {
     __threadfence();
     const uint32_t t_merge = (uint32_t)clock();
-    ampc_merge_records(p.partials, (int)gridDim.x, 2 + HN, HN, nu, p.inv_lmda, s_act, c_scale, p.act_seq, p.u_out,
-                       p.record_out, s_misc);
+    // the weight image is dead (every MMA of the pair has completed): its shared memory is the merge's scratch
+    if (!ampc_merge_records_tail<32>(p.partials, (int)gridDim.x, 2 + HN, HN, nu, p.inv_lmda, s_act, c_scale, p.act_seq,
+                                     p.u_out, p.record_out, reinterpret_cast<float *>(s_w), (int)(a.w_bytes >> 2)))
+      ampc_merge_records(p.partials, (int)gridDim.x, 2 + HN, HN, nu, p.inv_lmda, s_act, c_scale, p.act_seq, p.u_out,
+                         p.record_out, s_misc);
     if constexpr (TRACE) {
       __syncthreads();
       if (tid == 0)

@@ -23,7 +23,7 @@ pytestmark = pytest.mark.gpu
 # operand rounding along the rollout; with bf16 operands (2.5 % of the cost scale on the round-1 fixtures,
 # profiles/r02_precision.jsonl) most samples that hover near a limit are counted differently at some step, so the
 # fixtures are run in fp32 and fp16 only; bf16 is checked on a stable synthetic model below.
-COST_RTOL = {"fp32": 2e-5, "fp16": 1e-3, "bf16": 2e-3}
+COST_RTOL = {"fp32": 2e-5, "fp16": 2e-3, "bf16": 4e-3}
 ACT_ATOL = {"fp32": 2e-3, "fp16": 1e-2, "bf16": 5e-2}
 MAX_FLIP_FRAC = {"fp32": 0.005, "fp16": 0.03, "bf16": 0.05}
 
