@@ -66,6 +66,7 @@ EXPORTS = {
     "ampc_mppi_closed_loop_start": [C.c_void_p, C.c_void_p, _dp, C.c_int32, C.c_uint64, C.c_uint64],
     "ampc_mppi_closed_loop_finish": [C.c_void_p, C.c_int32, _dp, _dp, _dp],
     "ampc_mppi_debug_trace": [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32],
+    "ampc_mppi_debug_tc_mode": [C.c_void_p],
     "ampc_mlp_create": [C.POINTER(C.c_void_p), C.POINTER(MlpDesc), C.c_int32, C.c_int32, C.c_int32],
     "ampc_mlp_destroy": [C.c_void_p],
     "ampc_mlp_pred_batch": [C.c_void_p, C.c_int32, _dp, _dp, _dp],

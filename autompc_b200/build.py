@@ -11,8 +11,9 @@ LIB = os.path.join(LIB_DIR, "libampc_b200.so")
 SOURCES = ["mppi_api.cu", "mppi_fp32.cu", "mppi_tc.cu", "mlp_ops.cu", "ilqr.cu", "linear.cu"]
 # the tcgen05 kernel template is instantiated once per (cta_group, NXP, ReLU, trace) combination, each as its own
 # compilation of mppi_tc_inst.cu, so that the matrix builds in parallel
-TC_INSTANCES = [(cg, nxp, relu, f16, 0) for f16 in (0, 1) for cg in (1, 2) for relu in (0, 1)
-                for nxp in (4, 8, 16, 24, 32)] + [(2, 24, 1, 0, 1)]
+# ... and, for ReLU networks, in "dz" mode (see mppi_tc_kernel.cuh); the last two are the timeline builds
+TC_INSTANCES = [(cg, nxp, relu, f16, 0, dz) for dz in (0, 1) for f16 in (0, 1) for cg in (1, 2) for relu in (0, 1)
+                for nxp in (4, 8, 16, 24, 32) if relu or not dz] + [(2, 24, 1, 0, 1, 0), (2, 24, 1, 0, 1, 1)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -45,7 +46,7 @@ def _fresh(obj, src):
     if not os.path.exists(obj):
         return False
     t = os.path.getmtime(obj)
-    deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
     deps += [os.path.join(os.path.dirname(HERE), "include", "ampc_b200.h"), os.path.abspath(__file__)]
     return all(os.path.getmtime(d) <= t for d in deps)
 
@@ -57,14 +58,19 @@ def build(force=False, verbose=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     odir = _obj_dir()
     jobs = [(src, os.path.join(odir, src.replace(".cu", ".o")), []) for src in SOURCES]
-    for cg, nxp, relu, f16, tr in TC_INSTANCES:
-        obj = os.path.join(odir, "mppi_tc_inst_cg%d_nxp%d_relu%d_f16%d_trace%d.o" % (cg, nxp, relu, f16, tr))
+    for cg, nxp, relu, f16, tr, dz in TC_INSTANCES:
+        obj = os.path.join(odir, "mppi_tc_inst_cg%d_nxp%d_relu%d_f16%d_trace%d_dz%d.o" % (cg, nxp, relu, f16, tr, dz))
         jobs.append(("mppi_tc_inst.cu", obj, ["-DAMPC_TC_INST_CG=%d" % cg, "-DAMPC_TC_INST_NXP=%d" % nxp,
                                               "-DAMPC_TC_INST_RELU=%d" % relu, "-DAMPC_TC_INST_F16=%d" % f16,
-                                              "-DAMPC_TC_INST_TRACE=%d" % tr]))
+                                              "-DAMPC_TC_INST_TRACE=%d" % tr, "-DAMPC_TC_INST_DZ=%d" % dz]))
     max_par = max(1, min(len(jobs), int(os.environ.get("AMPC_BUILD_JOBS", os.cpu_count() or 4))))
     objs = [obj for _, obj, _ in jobs]
     pending, running = [j for j in jobs if force or not _fresh(j[1], j[0])], []
+    # development knob: AMPC_TC_DEV_ONLY="cg2_nxp24_relu1" rebuilds only the matching kernel instantiations and links
+    # the others from their (stale) cached objects -- never for a build that is tested or shipped
+    dev = os.environ.get("AMPC_TC_DEV_ONLY")
+    if dev:
+        pending = [j for j in pending if j[0] != "mppi_tc_inst.cu" or dev in j[1] or not os.path.exists(j[1])]
 
     def reap(src, pr):
         out, _ = pr.communicate()

@@ -50,6 +50,8 @@ int ampc_mppi_tc_supported(const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp, c
 int ampc_mppi_tc_create(AmpcTcPlan **plan, const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp);
 void ampc_mppi_tc_destroy(AmpcTcPlan *plan);
 int ampc_mppi_tc_grid(const AmpcTcPlan *plan);
+int ampc_mppi_tc_cta_group(const AmpcTcPlan *plan);
+int ampc_mppi_tc_dz(const AmpcTcPlan *plan);
 int ampc_mppi_tc_launch(AmpcTcPlan *plan, const AmpcMppiParams &p, cudaStream_t stream);
 int ampc_mppi_tc_trace(AmpcTcPlan *plan, unsigned long long *host, int max_words);
 
@@ -606,6 +608,13 @@ extern "C" int ampc_mppi_debug_trace(ampc_mppi *h, unsigned long long *host, int
   if (!h || !h->tc || !host) return 0;
   DeviceGuard g(h->device);
   return ampc_mppi_tc_trace(h->tc, host, max_words);
+}
+
+// Debug tap: which build of the tcgen05 kernel the handle runs.  0 = not the tensor-core path; otherwise
+// cta_group (1 | 2) + 16 if the "dz" build (input layer fed by the output layer's accumulator through kind::tf32).
+extern "C" int ampc_mppi_debug_tc_mode(ampc_mppi *h) {
+  if (!h || !h->tc) return 0;
+  return ampc_mppi_tc_cta_group(h->tc) + (ampc_mppi_tc_dz(h->tc) ? 16 : 0);
 }
 
 // ------------------------------------------------------------ NVLink peer exchange ---

@@ -66,7 +66,7 @@ size_t tc_smem_bytes(const TcArgs &a, int nx, int nu, int H) {
   const AmpcConstLayout cl(nx, nu);
   const size_t floats = (size_t)cl.total + ((H * nu + 3) & ~3) + (size_t)nx * TM +
                         (size_t)2 * nu * TM + 2 * 64 + 2 * 2 * 32 + 4 * 32 + 2 * TM + 32 + 64 + AMPC_MERGE_CACHE;
-  return 1024 + a.w_bytes + floats * sizeof(float) + (2 * MAXG + 1) * sizeof(uint64_t) + 16 +
+  return 1024 + a.w_bytes + floats * sizeof(float) + (2 * MAXG + 2) * sizeof(uint64_t) + 16 +
          (getenv("AMPC_TC_TRACE") ? (NTHR / 32) * TRACE_EV * sizeof(uint32_t) + 16 : 0);
 }
 
@@ -78,7 +78,17 @@ int chunk_width(int npad, bool last) {
   return npad / 2;                    // hidden GEMMs of width >= 128 are issued as two N-halves
 }
 
-void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg, bool f16) {
+// fp32 -> tf32 (10 explicit mantissa bits), round to nearest even; the tensor core ignores the low 13 bits
+float f32_to_tf32(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) != 0x7F800000u) u += 0xFFFu + ((u >> 13) & 1u);
+  u &= ~0x1FFFu;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg, bool f16, bool dz) {
   memset(&a, 0, sizeof(a));
   a.n_layers = mlp->n_layers;
   {
@@ -99,11 +109,14 @@ void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg, bool f16) {
     a.ones[l] = (l <= mlp->n_layers - 2) ? 1 : 0;  // ... written by the epilogue of the layer before them
     const int rows = a.npad[l] / cg, kblk = (a.kpad[l] + 63) / 64 + (bias_k ? 1 : 0);
     a.w_off[l] = off;
-    off += (uint32_t)kblk * rows * 128;
+    // input layer with K <= 32 and two N-halves: a row of the 64-wide K block is half empty, so N-half 1 is stored in
+    // bytes [64,128) of N-half 0's rows (its descriptor starts 64 bytes further, like K-steps 2 and 3 would)
+    a.cw[l] = chunk_width(a.npad[l], l == mlp->n_layers - 1);
+    if (l == 0 && a.kpad[0] <= 32 && a.cw[0] * 2 == a.npad[0]) a.l0_packed = 1;
+    off += (uint32_t)kblk * rows * 128 / ((l == 0 && a.l0_packed) ? 2 : 1);
     a.b_off[l] = boff;
     boff += a.npad[l];
     // kind::f16: c=f32 (bit 4), a/b format at bits 7 / 10 (0 = f16, 1 = bf16), both K-major, N>>3 at 17, M>>4 at 24
-    a.cw[l] = chunk_width(a.npad[l], l == mlp->n_layers - 1);
     a.nch[l] = a.npad[l] / a.cw[l];
     a.nh[l] = a.nch[l];
     a.hwid[l] = a.cw[l];
@@ -111,6 +124,17 @@ void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg, bool f16) {
     a.awid[l] = (l == 0) ? 64 : a.hwid[l - 1];
     a.idesc[l] = (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(a.cw[l] >> 3) << 17) |
                  ((uint32_t)((TM * cg) >> 4) << 24);
+  }
+  // dz mode: fp32 (tf32-rounded) image of the input layer's state columns, one 128-byte row (32 K elements) per neuron
+  a.nkx = (a.nxp + 7) / 8;
+  a.idesc_x = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cw[0] >> 3) << 17) | ((uint32_t)((TM * cg) >> 4) << 24);
+  // (needs a hidden GEMM between the input layer's reads of its operand and the next stores to it, and the ReLU build)
+  if (dz && mlp->n_layers >= 3 && mlp->act == AMPC_ACT_RELU) {
+    a.dz = 1;
+    // the early 16-bit input block goes where the last hidden GEMM's A buffer has 32 columns its MMAs never read
+    a.ecol = (a.npad[mlp->n_layers - 3] == 256) ? 160 : 128;
+    a.wx_off = off;
+    off += (uint32_t)(a.npad[0] / cg) * 128;
   }
   a.w_bytes = off;
   a.bias_floats = boff;
@@ -120,23 +144,28 @@ void fill_args(TcArgs &a, const ampc_mlp_desc *mlp, int cg, bool f16) {
 
 // the timeline build (AMPC_TC_TRACE=1) exists for the headline shape only: CTA pairs, NXP = 24, ReLU
 static bool tc_trace_available(int cg, int nxp, int act) { return cg == 2 && nxp == 24 && act == AMPC_ACT_RELU; }
-static TcKernel tc_kernel_ptr(int cg, int nxp, int act, bool f16, bool traced) {
-  if (traced && !f16 && tc_trace_available(cg, nxp, act)) return ampc_tc_kernel_cg2_nxp24_relu1_f160_trace1();
+static TcKernel tc_kernel_ptr(int cg, int nxp, int act, bool f16, bool traced, bool dz) {
+  if (traced && !f16 && tc_trace_available(cg, nxp, act))
+    return dz ? ampc_tc_kernel_cg2_nxp24_relu1_f160_trace1_dz1() : ampc_tc_kernel_cg2_nxp24_relu1_f160_trace1_dz0();
   const bool relu = act == AMPC_ACT_RELU;
-#define AMPC_TC_PICK_F(N, F)                                                                                                  \
-  return cg == 1 ? (relu ? ampc_tc_kernel_cg1_nxp##N##_relu1_f16##F##_trace0() : ampc_tc_kernel_cg1_nxp##N##_relu0_f16##F##_trace0()) \
-                 : (relu ? ampc_tc_kernel_cg2_nxp##N##_relu1_f16##F##_trace0() : ampc_tc_kernel_cg2_nxp##N##_relu0_f16##F##_trace0())
+#define AMPC_TC_PICK_CG(N, F, D, R) \
+  return cg == 1 ? ampc_tc_kernel_cg1_nxp##N##_relu##R##_f16##F##_trace0_dz##D() : ampc_tc_kernel_cg2_nxp##N##_relu##R##_f16##F##_trace0_dz##D()
+#define AMPC_TC_PICK_F(N, F)                      \
+  if (!relu) { AMPC_TC_PICK_CG(N, F, 0, 0); }     \
+  else if (dz) { AMPC_TC_PICK_CG(N, F, 1, 1); }   \
+  else { AMPC_TC_PICK_CG(N, F, 0, 1); }
 #define AMPC_TC_PICK(N) \
-  if (f16) { AMPC_TC_PICK_F(N, 1); } else { AMPC_TC_PICK_F(N, 0); }
+  if (f16) { AMPC_TC_PICK_F(N, 1) } else { AMPC_TC_PICK_F(N, 0) }
   switch (nxp) {
-    case 4: AMPC_TC_PICK(4);
-    case 8: AMPC_TC_PICK(8);
-    case 16: AMPC_TC_PICK(16);
-    case 24: AMPC_TC_PICK(24);
-    default: AMPC_TC_PICK(32);
+    case 4: AMPC_TC_PICK(4)
+    case 8: AMPC_TC_PICK(8)
+    case 16: AMPC_TC_PICK(16)
+    case 24: AMPC_TC_PICK(24)
+    default: AMPC_TC_PICK(32)
   }
 #undef AMPC_TC_PICK
 #undef AMPC_TC_PICK_F
+#undef AMPC_TC_PICK_CG
 }
 
 struct AmpcTcPlan {
@@ -180,17 +209,23 @@ static bool tc_shape_ok(const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp, cons
 }
 
 // picks CG=1 when the whole bf16 weight image fits next to the working set, else CG=2 (half per CTA)
+static bool tc_dz_wanted() {
+  const char *e = getenv("AMPC_TC_DZ");                // A/B knob: AMPC_TC_DZ=0 keeps the owner hop between the output and the input layer
+  return !(e && e[0] == '0');
+}
+
 static int tc_pick_cg(const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp, size_t cap, TcArgs *out, size_t *smem_out) {
-  for (int cg = 1; cg <= 2; ++cg) {
-    TcArgs a;
-    fill_args(a, mlp, cg, cfg->precision == AMPC_PREC_FP16);
-    const size_t need = tc_smem_bytes(a, cfg->nx, cfg->nu, cfg->H);
-    if (need <= cap) {
-      *out = a;
-      *smem_out = need;
-      return cg;
+  for (int cg = 1; cg <= 2; ++cg)
+    for (int dz = tc_dz_wanted() ? 1 : 0; dz >= 0; --dz) {   // dz mode needs room for one more image: without it otherwise
+      TcArgs a;
+      fill_args(a, mlp, cg, cfg->precision == AMPC_PREC_FP16, dz != 0);
+      const size_t need = tc_smem_bytes(a, cfg->nx, cfg->nu, cfg->H);
+      if (need <= cap) {
+        *out = a;
+        *smem_out = need;
+        return cg;
+      }
     }
-  }
   return 0;
 }
 
@@ -230,9 +265,12 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
   const char *force = getenv("AMPC_TC_FORCE_CG");
   if (force && (force[0] == '1' || force[0] == '2')) {
     const int f = force[0] - '0';
-    fill_args(pl->args, mlp, f, cfg->precision == AMPC_PREC_FP16);
-    pl->smem = tc_smem_bytes(pl->args, cfg->nx, cfg->nu, cfg->H);
-    cg = (pl->smem <= (size_t)max_optin) ? f : 0;
+    cg = 0;
+    for (int dz = tc_dz_wanted() ? 1 : 0; dz >= 0 && !cg; --dz) {
+      fill_args(pl->args, mlp, f, cfg->precision == AMPC_PREC_FP16, dz != 0);
+      pl->smem = tc_smem_bytes(pl->args, cfg->nx, cfg->nu, cfg->H);
+      cg = (pl->smem <= (size_t)max_optin) ? f : 0;
+    }
   }
   if (!cg) {
     delete pl;
@@ -256,13 +294,16 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
     const bool outl = (l == mlp->n_layers - 1);
     const int kdata = (a.kpad[l] + 63) / 64;      // K blocks of data; the bias block (if any) follows
     const int rows = a.npad[l] / cg, kblk = kdata + (bias_k ? 1 : 0);
+    const bool packed = (l == 0 && a.l0_packed);
     for (int r = 0; r < cg; ++r)
       for (int kb = 0; kb < kblk; ++kb)
         for (int n = 0; n < rows; ++n)
-          for (int ch = 0; ch < 8; ++ch) {
-            const size_t byte = (size_t)r * a.w_bytes + a.w_off[l] + (size_t)kb * rows * 128 + (size_t)n * 128 +
-                                (size_t)((ch ^ (n & 7)) * 16);
+          for (int ch = 0; ch < (packed ? 4 : 8); ++ch) {
             const int crow = a.cw[l] / cg;      // rows of one chunk held by each CTA
+            // packed input layer: local row n of N-half n / crow lives in physical row n % crow, 16-byte chunks 4..7 for half 1
+            const int prow = packed ? n % crow : n, pch = packed ? ch + 4 * (n / crow) : ch;
+            const size_t byte = (size_t)r * a.w_bytes + a.w_off[l] + (size_t)kb * rows * 128 + (size_t)prow * 128 +
+                                (size_t)((pch ^ (prow & 7)) * 16);
             const int ng = (n / crow) * a.cw[l] + r * crow + (n % crow);   // D column (= neuron) of local row n
             for (int e = 0; e < 8; ++e) {
               const int k = kb * 64 + ch * 8 + e;
@@ -290,13 +331,27 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
           }
     for (int j = 0; j < Nl; ++j) bias[a.b_off[l] + j] = (float)mlp->b[l][j];
   }
+  if (a.dz) {
+    // tf32 image of W0's state columns (the A operand is the increment of the NORMALISED state, which is what W0 eats)
+    const int Kl = mlp->dims[0], Nl = mlp->dims[1], nx = mlp->dims[mlp->n_layers];
+    const int rows = a.npad[0] / cg, crow = a.cw[0] / cg;
+    for (int r = 0; r < cg; ++r)
+      for (int n = 0; n < rows; ++n) {
+        const int ng = (n / crow) * a.cw[0] + r * crow + (n % crow);
+        for (int k = 0; k < 32; ++k) {
+          const float v = (ng < Nl && k < nx) ? f32_to_tf32((float)mlp->W[0][(size_t)ng * Kl + k]) : 0.f;
+          const size_t byte = (size_t)r * a.w_bytes + a.wx_off + (size_t)n * 128 + (size_t)(((k >> 2) ^ (n & 7)) * 16) + (size_t)(k & 3) * 4;
+          memcpy(reinterpret_cast<uint8_t *>(img.data()) + byte, &v, 4);
+        }
+      }
+  }
   cudaError_t e = cudaMalloc(&pl->d_wimg, img.size() * 2);
   if (e == cudaSuccess) e = cudaMemcpy(pl->d_wimg, img.data(), img.size() * 2, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_bias, bias.size() * sizeof(float));
   if (e == cudaSuccess) e = cudaMemcpy(pl->d_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_epsc, (size_t)cfg->H * cfg->nu * a.Kc * sizeof(float));
   if (e == cudaSuccess)
-    e = ampc_raise_smem_limit((const void *)tc_kernel_ptr(cg, a.nxp, mlp->act, f16, false), pl->smem);
+    e = ampc_raise_smem_limit((const void *)tc_kernel_ptr(cg, a.nxp, mlp->act, f16, false, a.dz != 0), pl->smem);
   if (e != cudaSuccess) {
     ampc_set_error("tcgen05 MPPI path create: %s", cudaGetErrorString(e));
     ampc_mppi_tc_destroy(pl);
@@ -306,13 +361,14 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
   a.bias = pl->d_bias;
   a.epsc = pl->d_epsc;
   a.trace = nullptr;
+  if (a.dz && getenv("AMPC_TC_DZ") && getenv("AMPC_TC_DZ")[0] == '2') a.dz = 2;   // measurement knob, see the issuer
   a.defer_j = DEFER_J;
   if (const char *dj = getenv("AMPC_TC_DEFER")) {   // tuning knob
     const int v = atoi(dj);
     if (v == 2 || v == 4 || v == 6 || v == 8) a.defer_j = v;
   }
   if (getenv("AMPC_TC_TRACE") && !f16 && tc_trace_available(cg, a.nxp, mlp->act)) {
-    ampc_raise_smem_limit((const void *)tc_kernel_ptr(cg, a.nxp, mlp->act, f16, true), pl->smem);
+    ampc_raise_smem_limit((const void *)tc_kernel_ptr(cg, a.nxp, mlp->act, f16, true, a.dz != 0), pl->smem);
     if (cudaMalloc(&pl->d_trace, (NTHR / 32) * TRACE_EV * sizeof(unsigned long long)) == cudaSuccess) {
       cudaMemset(pl->d_trace, 0, (NTHR / 32) * TRACE_EV * sizeof(unsigned long long));
       a.trace = pl->d_trace;
@@ -324,6 +380,7 @@ int ampc_mppi_tc_create(AmpcTcPlan **out, const ampc_mppi_cfg *cfg, const ampc_m
 
 int ampc_mppi_tc_grid(const AmpcTcPlan *plan) { return plan->grid; }
 int ampc_mppi_tc_cta_group(const AmpcTcPlan *plan) { return plan->cg; }
+int ampc_mppi_tc_dz(const AmpcTcPlan *plan) { return plan->args.dz; }
 
 int ampc_mppi_tc_launch(AmpcTcPlan *plan, const AmpcMppiParams &p, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
@@ -338,7 +395,7 @@ int ampc_mppi_tc_launch(AmpcTcPlan *plan, const AmpcMppiParams &p, cudaStream_t 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_kernel_ptr(plan->cg, plan->args.nxp, plan->act, plan->f16, plan->args.trace != nullptr), p, plan->args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_kernel_ptr(plan->cg, plan->args.nxp, plan->act, plan->f16, plan->args.trace != nullptr, plan->args.dz != 0), p, plan->args);
   ampc_count_launch();
   AMPC_CUDA_CHECK(e);
   return AMPC_OK;

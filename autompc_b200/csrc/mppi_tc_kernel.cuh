@@ -38,6 +38,8 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "ampc_common.cuh"
 
 // Kernel template + device helpers.  Included by mppi_tc.cu (host side: plans, weight images, launch) and by the
@@ -56,7 +58,7 @@ constexpr int BAR_X = 5;             // owners -> helpers: the shared copy of th
 constexpr int TMEM_COLS = 512;
 constexpr int TMEM_BUF = 256;        // two accumulator / activation buffers: columns [0,256) and [256,512)
 constexpr int MAXL = AMPC_MAX_LAYERS;
-constexpr int TRACE_EV = 128;
+constexpr int TRACE_EV = 120;           // (120: the headline shape in dz mode + the timeline ring just fit in 227 KB)
 // upper word of the K-major SWIZZLE_128B descriptor: SBO = 1024 B (bits 32-45), version 1 (bit 46), layout 2 (bits 61-63)
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 constexpr int DEFER_J = 4;           // K-steps of (half 1, K-pair 0) issued in the first phase; the other 8 - DEFER_J follow commit0
@@ -81,6 +83,14 @@ struct TcArgs {
   int nxp;                           // padded state width (kernel template): input K columns [0,nxp) = state
   int ones[MAXL];                    // layer l's epilogue also writes the constant-one K-step of layer l+1 (bias fold)
   int defer_j;                       // K-steps of (half 1, K-pair 0) issued before the wait for K-pair 1 (2 | 4 | 6; 8 = no deferral)
+  // "dz" mode (see the kernel header): layer 0 of step i+1 = 16-bit GEMM on [z_i | u_{i+1} | 1] issued EARLY
+  //   + kind::tf32 GEMM whose A operand is the output layer's fp32 accumulator (the increment of z) read in place
+  int dz;                            // != 0: on
+  uint32_t wx_off;                   // byte offset of the tf32 image of the input layer's state columns (rows x 128 B)
+  uint32_t idesc_x;                  // kind::tf32 instruction descriptor (N = hwid[0])
+  int nkx;                           // tf32 K-steps (8 states each) = ceil(nxp / 8)
+  int ecol;                          // dz mode: TMEM column (inside the buffer) of the early 16-bit input block
+  int l0_packed;                     // input layer's image: N-half 1 sits in bytes [64,128) of N-half 0's rows (kpad[0] <= 32)
   unsigned long long *trace;         // debug timeline (AMPC_TC_TRACE=1), else null: [warp][event] = clock<<8 | tag
 };
 
@@ -115,6 +125,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {   // non-suspending probe
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -170,6 +191,24 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// same with kind::tf32: A = 8 fp32 TMEM columns per K-step (an fp32 accumulator read in place), B = fp32 K-major image
+template <int CG>
+__device__ __forceinline__ void umma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_desc_lo, uint32_t idesc,
+                                             uint32_t accumulate) {
+  const uint64_t b_desc = ((uint64_t)DESC_HI << 32) | (uint64_t)b_desc_lo;
+  if constexpr (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -281,7 +320,7 @@ __device__ __forceinline__ void issue_pair(uint32_t dh, uint32_t a_pair, uint32_
 // instantiation with a runtime switch.  Keeping their code out of the ReLU kernel matters: inlined, it put 43 KB
 // of cold instructions between the LDTM, the packs and the STTM of every epilogue (instruction-cache misses on
 // the critical path).
-template <int CG, int NXP, bool RELU, bool F16, bool TRACE>
+template <int CG, int NXP, bool RELU, bool F16, bool TRACE, bool DZ>
 __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppiParams p, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -306,7 +345,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
   float *s_red = s_cc + TM;                            // 32
   float *s_misc = s_red + 32;                          // 64 + AMPC_MERGE_CACHE
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_misc + 64 + AMPC_MERGE_CACHE);   // [0..1]=bar_d[h], [2..3]=bar_a[kp]
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2 * MAXG + 1);   // s_bar[2*MAXG] = bar_w (weight image landed)
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2 * MAXG + 2);   // s_bar[2*MAXG] = bar_w (weight image landed), [2*MAXG+1] = bar_y
   __shared__ int s_last;
 
   // Weight image (this CTA's half): TMA bulk copies global -> shared, completion counted in bytes on bar_w.  One
@@ -364,7 +403,10 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
     s_qc[j] = qc;
   }
   const uint32_t bar_d0 = smem_u32(&s_bar[0]), bar_a0 = smem_u32(&s_bar[MAXG]);
+  const uint32_t bar_y = smem_u32(&s_bar[2 * MAXG + 1]);   // dz mode: "output-layer accumulator complete"
+  constexpr bool dz = DZ;
   if (tid == 0) {
+    mbar_init(bar_y, 1);
     for (int g = 0; g < MAXG; ++g) mbar_init(bar_d0 + 8u * g, 1);
     for (int g = 0; g < MAXG; ++g) mbar_init(bar_a0 + 8u * g, (NEPI / 32) * CG);
     fence_mbar_init();
@@ -423,6 +465,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
         lo_l[l] = (((w_addr + a.w_off[l]) >> 4) & 0x3FFFu) | (1u << 16);
         kbs_l[l] = (uint32_t)(rows * 128) >> 4;
         hro_l[l] = (uint32_t)((a.hwid[l] / CG) * 128) >> 4;   // B rows of one N-half (descriptor units)
+        if (l == 0 && a.l0_packed) hro_l[l] = 64u >> 4;       // ... or the second 64 bytes of the same rows
         id_l[l] = a.idesc[l];
         nh_l[l] = a.nh[l];
         nkp_l[l] = a.nkp[l];
@@ -432,10 +475,20 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
       }
       const int nks0 = a.kpad[0] >> 4;
       const int defer_j = a.defer_j;
+      // dz mode: descriptor words of the input layer's two N-halves, 16-bit image (E) and tf32 image of the state columns (T)
+      constexpr int NKX = (NXP + 7) / 8;
+      const uint32_t xlo = (((w_addr + a.wx_off) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t xhro = (uint32_t)((a.hwid[0] / CG) * 128) >> 4;
+      const uint32_t e_lo[MAXG] = {lo_l[0], lo_l[0] + hro_l[0]}, x_lo[MAXG] = {xlo, xlo + xhro};
+      const uint32_t hw0 = (uint32_t)hw_l[0], idx = a.idesc_x, ecol = (uint32_t)a.ecol;
+      const int nh0 = nh_l[0];
       for (int i = 0; i < H; ++i) {
 #pragma unroll
         for (int l = 0; l < MAXL; ++l) {
           if (l >= L) break;
+          if constexpr (dz) {
+            if (l == 0 && i > 0) continue;              // issued at the end of the previous step (below)
+          }
           const int nh = nh_l[l], nkp = nkp_l[l];
           const uint32_t idesc = id_l[l], kb_stride = kbs_l[l];
           const uint32_t d_addr = (n & 1u) * TMEM_BUF + (l == L - 1 ? (uint32_t)YCOL : 0u);
@@ -481,7 +534,46 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
               }
               if (l > 0 && kp == 0)                   // constant-one K-step: the layer's bias (extra K block of the image)
                 umma_ts<CG>(dh, a_addr + (uint32_t)(aw_l[l] >> 2), hb0 + (uint32_t)(a.kpad[l] >> 6) * kb_stride, idesc, 1u);
-              if (kp == nkp - 1) { umma_commit<CG>(bar_d0 + 8u * h); trace(i, 0x20 + l * 2 + h); }   // half h committed
+              if (kp == nkp - 1) {                     // half h committed (dz mode: the output layer reports on bar_y)
+                umma_commit<CG>((dz && l == L - 1) ? bar_y : bar_d0 + 8u * h);
+                trace(i, 0x20 + l * 2 + h);
+              }
+            }
+          }
+          ++n;
+        }
+        if constexpr (dz) if (i + 1 < H) {
+          // ---- input layer of step i+1 (GEMM n), dz mode.  z_{i+1} = z_i + dz_i, so
+          //   W0 [z_{i+1} | u_{i+1} | 1] = W0 [z_i | u_{i+1} | 1]  (16-bit operands; the owners stored them at TMEM columns
+          //                                                         [ecol, ecol + 8 nks0) of this buffer -- columns the last
+          //                                                         hidden GEMM does not read -- before their first release
+          //                                                         of that layer's epilogue: "early" part E)
+          //                              + W0x dz_i               (kind::tf32; A = the output layer's fp32 accumulator, read
+          //                                                         in place at YCOL of the same buffer, no epilogue hop: T).
+          // Order  E(h0) | wait bar_y | T(h0) commit0  E(h1) T(h1) commit1 :  E(h0) executes while this thread waits for
+          // the output layer's commit (T reads what other MMAs wrote: not a pair the tensor pipe orders by itself).
+          const uint32_t d_addr = (n & 1u) * TMEM_BUF, a_addr = ((n + 1u) & 1u) * TMEM_BUF;
+#pragma unroll
+          for (int h = 0; h < MAXG; ++h) {
+            if (h < nh0) {
+              const uint32_t dh = d_addr + (uint32_t)h * hw0;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                if (ks < nks0)
+                  umma_ts<CG>(dh, a_addr + ecol + (uint32_t)(ks * 8), e_lo[h] + (uint32_t)(ks * 2), id_l[0], ks > 0 ? 1u : 0u);
+              if (h == 0) {
+                trace(i, 0x61);                         // E(h0) issued
+                if (a.dz != 2) {                        // (dz == 2: measurement only -- rely on the pipe's issue order)
+                  if (!mbar_test_wait(bar_y, (uint32_t)i & 1u)) mbar_wait(bar_y, (uint32_t)i & 1u);
+                  tc_fence_after();
+                }
+                trace(i, 0x60);                         // output-layer accumulator of step i complete (issuer)
+              }
+#pragma unroll
+              for (int ks = 0; ks < NKX; ++ks)
+                umma_ts_tf32<CG>(dh, a_addr + (uint32_t)(YCOL + ks * 8), x_lo[h] + (uint32_t)(ks * 2), idx, 1u);
+              umma_commit<CG>(bar_d0 + 8u * h);
+              trace(i + 1, 0x20 + h);
             }
           }
           ++n;
@@ -578,10 +670,14 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
       const float2 zc = s_zc[k];
       return fmaf((k - NXP < nu) ? su[(k - NXP) * TM + t] : 0.f, zc.x, zc.y);
     };
-    auto pack_controls = [&](int step, uint32_t buf) {
+    // controls of `step`: acquire = wait until the control warps have them (named barrier, also a rendezvous of the four
+    // owner warps: kept out of critical sections); pack = z-score, pack and store the K-steps that hold no state
+    auto acquire_controls = [&](int step) {
+      asm volatile("bar.sync %0, %1;" ::"r"(BAR_FULL + (step & 1)), "n"(NEPI / 2 + NCTL) : "memory");
+    };
+    auto pack_acquired_controls = [&](int step, uint32_t buf) {
       const int b = step & 1;
       const float *su = s_u + b * nu * TM;
-      asm volatile("bar.sync %0, %1;" ::"r"(BAR_FULL + b), "n"(NEPI / 2 + NCTL) : "memory");   // controls of `step` are ready
       if constexpr (NXP % 16 != 0) {
 #pragma unroll
         for (int q = 0; q < NMIX; ++q) cpk[q] = pack_16<F16>(zctl(su, NXP + 2 * q), zctl(su, NXP + 2 * q + 1));
@@ -593,6 +689,32 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
 #pragma unroll
           for (int q = 0; q < 8; ++q) pk[q] = pack_16<F16>(zctl(su, g * 16 + 2 * q), zctl(su, g * 16 + 2 * q + 1));
           tmem_st8(lane_base + buf * TMEM_BUF + (uint32_t)((g >> 1) * 32 + (g & 1) * 8), pk);
+        }
+      }
+      if (step + 2 < H) asm volatile("bar.arrive %0, %1;" ::"r"(BAR_EMPTY + b), "n"(NEPI / 2 + NCTL) : "memory");
+    };
+    auto pack_controls = [&](int step, uint32_t buf) {
+      acquire_controls(step);
+      pack_acquired_controls(step, buf);
+    };
+    // dz mode: the 16-bit operand of the NEXT step's input layer, [z_i | z-scored u_{i+1} | ones], K-step g at TMEM columns
+    // ecol + 8 g of buffer `buf` (columns of the last hidden GEMM's A buffer that its MMAs never read: the 32 columns an
+    // owner warp freed when it packed 64 accumulator columns into 32, or columns beyond a narrower layer)
+    auto early_input = [&](int step, uint32_t buf) {
+      const int b = step & 1;
+      const float *su = s_u + b * nu * TM;
+      asm volatile("bar.sync %0, %1;" ::"r"(BAR_FULL + b), "n"(NEPI / 2 + NCTL) : "memory");   // controls of `step` are ready
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (g * 16 < kpad0) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int k = g * 16 + q * 2;               // NXP is even: a pair is all state or all control
+            if (k < NXP) pk[q] = pack_16<F16>(z[k < NXP ? k : 0], z[k + 1 < NXP ? k + 1 : 0]);
+            else pk[q] = pack_16<F16>(zctl(su, k), zctl(su, k + 1));
+          }
+          tmem_st8(lane_base + buf * TMEM_BUF + (uint32_t)a.ecol + (uint32_t)(g * 8), pk);
         }
       }
       if (step + 2 < H) asm volatile("bar.arrive %0, %1;" ::"r"(BAR_EMPTY + b), "n"(NEPI / 2 + NCTL) : "memory");
@@ -625,105 +747,54 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
     signal_a(0);
 
     for (int i = 0; i < H; ++i) {
-      // ---- hidden layers: D (buffer n&1) -> activation -> bf16, written IN PLACE over the consumed accumulator
-      //      columns; each N-half is one K-pair of the next GEMM
+      // ---- hidden layers: D (buffer n&1) -> activation -> 16 bit, written IN PLACE over the consumed accumulator
+      //      columns; each N-half is one K-pair of the next GEMM.  The dz build keeps ONE copy of this loop body (no
+      //      unrolling over layers: a third of the instruction footprint, and early_input is not replicated per layer).
+      if constexpr (!dz) {
 #pragma unroll
-      for (int l = 0; l < MAXL - 1; ++l) {
-        if (l >= L - 1) break;
-        const int nh = a.nh[l], hwid = a.hwid[l];
-        const uint32_t dbuf = lane_base + (n & 1u) * TMEM_BUF;
-#pragma unroll
-        for (int h = 0; h < MAXG; ++h) {
-          if (h >= nh) break;
-          wait_d(h);
-          trace(i, 0x30 + l * 2 + h);                   // bar_d[h] of layer l observed
-          uint32_t ra[32], pk[16];
-          if (hwid == 128) {                            // this warp's 64 columns of the half
-            const uint32_t c0 = dbuf + (uint32_t)(h * 128 + hf * 64);
-            uint32_t rb[32];
-            tmem_ld32(c0, ra);
-            tmem_ld32(c0 + 32, rb);
-            tc_wait_ld();
-            epi_pack<32, RELU, F16>(ra, p.act, pk);
-            tmem_st16(c0, pk);
-            epi_pack<32, RELU, F16>(rb, p.act, pk);
-            tmem_st16(c0 + 16, pk);
-          } else {                                      // hwid == 64: 32 columns
-            const uint32_t c0 = dbuf + (uint32_t)(h * 64 + hf * 32);
-            tmem_ld32(c0, ra);
-            tc_wait_ld();
-            epi_pack<32, RELU, F16>(ra, p.act, pk);
-            tmem_st16(c0, pk);
-          }
-          if (h == 0 && hf == 0 && a.ones[l]) {         // constant-one K-step of the next GEMM (its bias), in free columns
-            uint32_t one[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) one[q] = q == 0 ? (F16 ? 0x3C003C00u : 0x3F803F80u) : 0u;
-            tmem_st8(dbuf + (uint32_t)(hwid >> 2), one);
-          }
-          signal_a(h);
-          trace(i, 0x40 + l * 2 + h);                   // half h packed and released
+        for (int l = 0; l < MAXL - 1; ++l) {
+          if (l >= L - 1) break;
+#include "mppi_tc_hidden_layer.inc"
         }
-        if (l == 0) {                                   // off the critical path: the next GEMM's MMAs are running
-          if (owner) {                                  // hand the (normalised) state to the helper: plain stores
-#pragma unroll
-            for (int j = 0; j < NXP; ++j)
-              if (j < nx) s_x[j * TM + t] = z[j];
-            asm volatile("bar.arrive %0, %1;" ::"n"(BAR_X), "n"(NEPI) : "memory");
-            trace(i, 0xB0);                             // state copy stored
-          } else {                                      // stage cost (x_i - g)^T Q (x_i - g), x_i = z * std + mean   (mppi.py:142)
-            asm volatile("bar.sync %0, %1;" ::"n"(BAR_X), "n"(NEPI) : "memory");
-            trace(i, 0xB1);                             // state copy visible
-            if (p.n_box > 0) {                          // threshold terms (thresh_cost.py:27-32, :73-77), x = z * std + mean
-              for (int b = 0; b < p.n_box; ++b) {
-                const float *bx = p.box + (size_t)b * (2 * nx + 1);
-                bool out = false;
-                for (int j = 0; j < nx; ++j) {
-                  const float2 xc = s_xc[j];
-                  const float x = fmaf(s_x[j * TM + t], xc.x, xc.y);
-                  out = out || (x < __ldg(bx + j)) || (x > __ldg(bx + nx + j));
-                }
-                if (out) cost_acc += __ldg(bx + 2 * nx);
-              }
-            }
-            if (p.q_diag) {
-              float c = 0.f;
-#pragma unroll 8
-              for (int j = 0; j < nx; ++j) {
-                const float4 qc = s_qc[j];
-                const float d = fmaf(s_x[j * TM + t], qc.x, qc.y);
-                c = fmaf(qc.z * d, d, c);
-              }
-              cost_acc += c;
-            } else {                                    // dense Q: x - g in place (column t is this sample's own), then the full form
-#pragma unroll 8
-              for (int j = 0; j < nx; ++j) {
-                const float4 qc = s_qc[j];
-                s_x[j * TM + t] = fmaf(s_x[j * TM + t], qc.x, qc.y);
-              }
-              cost_acc += quad_full(c_Q, s_x, nullptr, nx, false, t);
-            }
-            trace(i, 0xB2);                             // stage cost done
-          }
+      } else {
+#pragma unroll 1
+        for (int l = 0; l < L - 1; ++l) {
+#include "mppi_tc_hidden_layer.inc"
         }
-        ++n;
       }
       // ---- output layer: integrate in z space (mlp.py:235-236), then the next step's input in place.
       //      The control columns of that input are packed while the output-layer MMAs run.
-      if (owner && i + 1 < H) pack_controls(i + 1, n & 1u);
-      wait_d(0);
-      trace(i, 0x30 + (L - 1) * 2);
-      if (owner) {
-        const uint32_t dbuf = lane_base + (n & 1u) * TMEM_BUF;
-        uint32_t r[32];
-        tmem_ld32(dbuf + YCOL, r);
-        tc_wait_ld();
+      if constexpr (dz) {
+        // dz mode: the 16-bit part of the next input was built from z_i before the last hidden epilogue (above); the
+        // increment the output layer is computing reaches the next input layer through the tensor pipe (kind::tf32 on
+        // the accumulator), so integrating z is off the critical path.
+        if (owner) {
+          mbar_wait(bar_y, (uint32_t)i & 1u);
+          tc_fence_after();
+          trace(i, 0x30 + (L - 1) * 2);
+          uint32_t r[32];
+          tmem_ld32(lane_base + (n & 1u) * TMEM_BUF + YCOL, r);
+          tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < NXP; ++j) z[j] += __uint_as_float(r[j]);   // the image carries dy_std / std and the constants
-        if (i + 1 < H) store_input(n & 1u);             // GEMM n+1 reads A from buffer n&1
+          for (int j = 0; j < NXP; ++j) z[j] += __uint_as_float(r[j]);
+          trace(i, 0x91);
+        }
+      } else {
+        if (owner && i + 1 < H) pack_controls(i + 1, n & 1u);
+        wait_d(0);
+        trace(i, 0x30 + (L - 1) * 2);
+        if (owner) {
+          const uint32_t dbuf = lane_base + (n & 1u) * TMEM_BUF;
+          uint32_t r[32];
+          tmem_ld32(dbuf + YCOL, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < NXP; ++j) z[j] += __uint_as_float(r[j]);   // the image carries dy_std / std and the constants
+          if (i + 1 < H) store_input(n & 1u);           // GEMM n+1 reads A from buffer n&1
+        }
+        if (i + 1 < H) signal_a(0);
+        trace(i, 0x50);                                 // next input released
       }
-      if (i + 1 < H) signal_a(0);
-      trace(i, 0x50);                                   // next input released
       ++n;
     }
     // x_H for the terminal cost goes into the same shared array the helpers read the last stage cost from: nothing
@@ -832,12 +903,15 @@ typedef void (*TcKernel)(const AmpcMppiParams, const TcArgs);
 }  // namespace ampc_tc
 
 // one getter per instantiation (mppi_tc_inst.cu compiled once per combination)
-#define AMPC_TC_DECL(cg, nxp, relu, f16, tr) ampc_tc::TcKernel ampc_tc_kernel_cg##cg##_nxp##nxp##_relu##relu##_f16##f16##_trace##tr();
-#define AMPC_TC_DECL_NXP(cg, relu, f16) \
-  AMPC_TC_DECL(cg, 4, relu, f16, 0) AMPC_TC_DECL(cg, 8, relu, f16, 0) AMPC_TC_DECL(cg, 16, relu, f16, 0) \
-  AMPC_TC_DECL(cg, 24, relu, f16, 0) AMPC_TC_DECL(cg, 32, relu, f16, 0)
-AMPC_TC_DECL_NXP(1, 0, 0) AMPC_TC_DECL_NXP(1, 1, 0) AMPC_TC_DECL_NXP(2, 0, 0) AMPC_TC_DECL_NXP(2, 1, 0)
-AMPC_TC_DECL_NXP(1, 0, 1) AMPC_TC_DECL_NXP(1, 1, 1) AMPC_TC_DECL_NXP(2, 0, 1) AMPC_TC_DECL_NXP(2, 1, 1)
-AMPC_TC_DECL(2, 24, 1, 0, 1)   // the timeline build: headline shape only
+#define AMPC_TC_DECL(cg, nxp, relu, f16, tr, dz) \
+  ampc_tc::TcKernel ampc_tc_kernel_cg##cg##_nxp##nxp##_relu##relu##_f16##f16##_trace##tr##_dz##dz();
+#define AMPC_TC_DECL_NXP(cg, relu, f16, dz) \
+  AMPC_TC_DECL(cg, 4, relu, f16, 0, dz) AMPC_TC_DECL(cg, 8, relu, f16, 0, dz) AMPC_TC_DECL(cg, 16, relu, f16, 0, dz) \
+  AMPC_TC_DECL(cg, 24, relu, f16, 0, dz) AMPC_TC_DECL(cg, 32, relu, f16, 0, dz)
+AMPC_TC_DECL_NXP(1, 0, 0, 0) AMPC_TC_DECL_NXP(1, 1, 0, 0) AMPC_TC_DECL_NXP(2, 0, 0, 0) AMPC_TC_DECL_NXP(2, 1, 0, 0)
+AMPC_TC_DECL_NXP(1, 0, 1, 0) AMPC_TC_DECL_NXP(1, 1, 1, 0) AMPC_TC_DECL_NXP(2, 0, 1, 0) AMPC_TC_DECL_NXP(2, 1, 1, 0)
+// dz mode (ReLU networks only)
+AMPC_TC_DECL_NXP(1, 1, 0, 1) AMPC_TC_DECL_NXP(2, 1, 0, 1) AMPC_TC_DECL_NXP(1, 1, 1, 1) AMPC_TC_DECL_NXP(2, 1, 1, 1)
+AMPC_TC_DECL(2, 24, 1, 0, 1, 0) AMPC_TC_DECL(2, 24, 1, 0, 1, 1)   // the timeline builds: headline shape only
 #undef AMPC_TC_DECL_NXP
 #undef AMPC_TC_DECL

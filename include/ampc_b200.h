@@ -171,6 +171,8 @@ int ampc_mppi_solve_fused_host(ampc_mppi *h, const double *host_x0, const double
 /* Debug tap, no reference counterpart: when the handle was created with AMPC_TC_TRACE=1 in the environment,
  * copies the tcgen05 kernel's timeline of CTA 0 ([warp][64] words = clock64 << 8 | tag) to host.       */
 int ampc_mppi_debug_trace(ampc_mppi *h, unsigned long long *host, int32_t max_words);
+/* Debug tap: 0 = the handle does not run the tcgen05 kernel; else cta_group (1 | 2) + 16 for the "dz" build. */
+int ampc_mppi_debug_tc_mode(ampc_mppi *h);
 
 /* ------------------------------------------------------- MLP model ops --- */
 /* Replaces autompc.sysid.mlp.MLP.pred / pred_batch (mlp.py:219-236) and

@@ -8,18 +8,19 @@ from autompc_b200.problems import halfcheetah_dim_problem
 system, task, w, x0 = halfcheetah_dim_problem()
 ctl = MPPI(system, task, B200MLP(system, w), horizon=50, num_path=16384, precision="bf16")
 for _ in range(3): ctl.solve(x0)
-buf = np.zeros(13 * 128, dtype=np.uint64)
+EV = 120   # TRACE_EV in mppi_tc_kernel.cuh
+buf = np.zeros(13 * EV, dtype=np.uint64)
 n = _abi.lib().ampc_mppi_debug_trace(ctl._h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), buf.size)
 ev = []
 for wp in range(13):
-    for e in buf[wp * 128:(wp + 1) * 128]:
+    for e in buf[wp * EV:(wp + 1) * EV]:
         if e: ev.append((int(e) >> 8, wp, int(e) & 255))
 ev.sort()
 t0 = 0   # cycles since kernel entry (CTA 0)
 phase = {1: "setup done", 2: "left the horizon loop", 3: "CTA softmax record written", 4: "ticket / merge done", 5: "kernel end"}
 names = {1: "MMA  saw bar_a", 2: "MMA  commit   ", 3: "EPI  saw bar_d", 4: "EPI  released ", 5: "EPI  next input",
          6: "EPI    ld#1 done (half = idx)", 7: "EPI    ld#2 done (half = idx)", 8: "EPI    stores issued (half = idx)",
-         9: "OWN    y loaded(0) / integrated(1) / input stored(2): idx ="}
+         6: "MMA  saw bar_y (output layer complete), idx =", 9: "OWN    y loaded(0) / integrated(1) / input stored(2): idx ="}
 for t, wp, tag in ev:
     if wp in (4, 8, 12):
         k, idx = tag >> 4, tag & 15

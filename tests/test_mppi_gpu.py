@@ -720,3 +720,50 @@ def test_tensor_core_kernel_matches_unmodified_reference_fixture(name, precision
         np.testing.assert_allclose(ctl.act_sequence, z["act_%d" % s_], rtol=0, atol=tol["act"])
         np.testing.assert_allclose(u, z["u_%d" % s_], rtol=0, atol=tol["act"] * 20.0)
     ctl.close()
+
+
+# "dz" build of the tensor-core kernel (ReLU networks with >= 2 hidden layers, when the extra tf32 image fits in shared
+# memory): the next step's input layer is fed by the output layer's fp32 accumulator through kind::tf32 MMAs plus a
+# 16-bit part built from the previous state.  Both builds must meet the same tolerance on the same cases.
+@pytest.mark.parametrize("dz", ["1", "0"])
+@pytest.mark.parametrize("ci", [0, 1, 2, 7, 9])
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_tensor_core_builds_with_and_without_dz(ci, dz, precision, monkeypatch):
+    from autompc_b200 import _abi
+    nx, nu, hidden, act, K, H, sigma, lmda, force_cg = TC_CASES[ci][:9]
+    monkeypatch.setenv("AMPC_TC_DZ", dz)
+    if force_cg:
+        monkeypatch.setenv("AMPC_TC_FORCE_CG", force_cg)
+    else:
+        monkeypatch.delenv("AMPC_TC_FORCE_CG", raising=False)
+    rng = np.random.default_rng(5)
+    p = synthetic_mlp(nx, nu, hidden, act=act, seed=3)
+    cost = QuadCostParams(np.eye(nx), 0.01 * np.eye(nu), 10 * np.eye(nx), goal=0.05 * rng.normal(size=nx))
+    umax = rng.uniform(0.5, 2.0, size=nu)
+    umin = -umax * rng.uniform(0.5, 1.0, size=nu)
+    np.random.seed(1)
+    ctl = _engine(p, cost, umin, umax, horizon=H, num_path=K, sigma=sigma, lmda=lmda, noise="numpy", precision=precision)
+    mode = _abi.lib().ampc_mppi_debug_tc_mode(ctl._h)
+    assert mode != 0 and (not force_cg or (mode & 3) == int(force_cg))
+    assert bool(mode & 16) == (dz == "1"), "dz build expected for a ReLU network with two or more hidden layers"
+    np.random.seed(1)
+    o = MPPIOracle(p, cost, umin, umax, horizon=H, num_path=K, sigma=sigma, lmda=lmda)
+    x0 = rng.normal(size=nx)
+    for _ in range(3):
+        eps = o.sample_eps()
+        u, _ = _check_solve(ctl, o, x0, eps, TOL[precision], check_argmin=False)
+        x0 = mlp_pred_batch(p, x0[None], u[None])[0]
+    ctl.close()
+
+
+def test_dz_build_not_taken_for_one_hidden_layer_or_other_activations():
+    from autompc_b200 import _abi
+    for ci in (3, 6, 8):                                  # tanh; one hidden layer (twice)
+        nx, nu, hidden, act, K, H, sigma, lmda, _ = TC_CASES[ci][:9]
+        p = synthetic_mlp(nx, nu, hidden, act=act, seed=3)
+        cost = QuadCostParams(np.eye(nx), 0.01 * np.eye(nu), 10 * np.eye(nx))
+        ctl = _engine(p, cost, -np.ones(nu), np.ones(nu), horizon=H, num_path=K, precision="fp16")
+        mode = _abi.lib().ampc_mppi_debug_tc_mode(ctl._h)
+        assert mode in (1, 2)
+        ctl.solve(np.zeros(nx))
+        ctl.close()
