@@ -25,6 +25,7 @@
 // 111 M warp instructions per solve of which 10 M were DFMA -- 64-bit generic address arithmetic; with that gone, rolling
 // every alpha out on its own was bound by the shared-memory pipe (the whole network per alpha per step), and the
 // one-warp Riccati recursion by its instruction count (a lone warp retires a dependent instruction every ~10 cycles).
+#include <algorithm>
 #include <vector>
 
 #include "ampc_common.cuh"
@@ -58,6 +59,10 @@ struct IlqrParams {
   double *jac_work;                // global per-warp scratch of the Jacobian refresh (ditto)
   double *states, *ctrls, *Ks, *ks;   // outputs (global)
   int *info, *alpha_idx;
+  // line search on FP64 tensor-core fragments (ls_rollouts_mma): on when the fragment-ordered weight image fits
+  int ls_profile;                  // != 0: ls_rollouts_mma reads the clock at its phase boundaries (AMPC_ILQR_LS_PROFILE)
+  int ls_mma, ls_S, ls_mwp, ls_doubles;   // activation row stride (doubles), padded activation rows, phase scratch in doubles
+  int ls_wf[MAXL], ls_kp[MAXL], ls_mt[MAXL];   // per layer: offset of its image inside the Wf region, padded K, 8-row tiles
   unsigned long long *prof;        // [0..5] cycles of thread 0 in: setup+init rollout, backward passes, line-search rollouts,
                                    // objective + acceptance, Jacobian refreshes, copy-out; [6] = total, [7] = iterations
 };
@@ -404,6 +409,230 @@ __device__ __forceinline__ void ls_rollouts(const IlqrParams &P, const double *n
   if (tid == 0) for (int q = 0; q < 6; ++q) P.prof[8 + q] += lc[q];
 }
 
+// D (8x8) += A (8x4, row-major) . B (4x8, column-major), float64, one warp.  Fragments (lane = 4 g + t): a = A[g][t],
+// b = B[t][g], c0 / c1 = C[g][2 t] / C[g][2 t + 1].
+__device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Activations other than ReLU out of line: the horizon loop of ls_rollouts_mma is latency bound, and the inlined
+// float64 tanh / exp / expm1 bodies (twice per call site) were most of its instruction footprint.
+__device__ __noinline__ double ilqr_act_other(int act, double y) { return ampc_act<double>(act, y); }
+__device__ __forceinline__ double ilqr_act(int act, double y) {
+  if (act == AMPC_ACT_RELU) return y > 0.0 ? y : 0.0;
+  return ilqr_act_other(act, y);
+}
+
+// 32-bit shared-memory addressing for ls_rollouts_mma: every array it touches is shared-memory resident (the caller only
+// takes this path in resident mode), and the horizon loop is a latency-bound chain -- with generic double pointers the
+// compiler rebuilt 64-bit addresses (and the shared window base from SR_CgaCtaId) in front of almost every load.
+__device__ __forceinline__ uint32_t sh32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+
+// Everything ls_rollouts_mma needs, in shared memory (filled once per solve by the kernel): the routine is compiled OUT
+// OF LINE so that it gets a register allocation of its own -- inlined into the solve kernel it competed with the other
+// phases for the 128 registers, the compiler re-derived its loop-invariant addresses from special registers and the
+// constant bank in front of the loads of every layer, and the other phases spilled more.
+struct LsArgs {
+  int nx, nu, H, S, mwp, L, act, bounded, profile;
+  int KS[MAXL], MT[MAXL], N[MAXL], Kin[MAXL], ws[MAXL];      // per layer: k-steps, row tiles, outputs, inputs, row stride of W
+  uint32_t a_W[MAXL], a_B[MAXL], a_Wf[MAXL];                 // shared addresses: row-major weights, biases, fragment image
+  uint32_t a_xu_mean, a_xu_std, a_dy_mean, a_dy_std;
+  uint32_t a_scr, a_states, a_ctrls, a_Ks, a_ks, a_ls_states, a_ls_ctrls, a_alphas, a_umin, a_umax;
+  const double *x0;                                          // global
+  unsigned long long *prof;                                  // global
+};
+
+// Line-search rollouts on the FP64 tensor-core path: same contract as ls_rollouts for the `na` (<= 8) step sizes
+// a0 .. a0 + na - 1, which occupy the 8 columns of one alpha tile.  (The caller evaluates the step sizes eight at a time
+// and stops as soon as the acceptance rule of ilqr.py:208-225, which walks them in order, has made its choice: the
+// outputs are those of the reference's all-at-once batch, the rollouts nobody reads are not computed.)
+// Per horizon step and layer the product  out[j][alpha] = sum_k W[j][k] h[alpha][k]  is tiled as
+// (8 output rows) x (8 alphas) x (4 k)  mma.m8n8k4: warp w of the 8 main warps owns the row tiles w, w + 8, ...; the
+// weights come from a FRAGMENT-ORDERED image built once per call in the phase scratch (tile, k-step, lane -> one
+// double: a conflict-free 256-byte load per warp), the activations sit as [k][S] with S = 4 (mod 16) doubles so that the
+// (4 k) x (8 alphas) operand of a warp is conflict free as well.  That removes what bounded ls_rollouts (one
+// shared-memory operand per multiply-add per lane: the register write-back of warp-wide loads) -- here one operand pair
+// feeds 256 multiply-adds -- and the K-quarter partials with their combine pass: four accumulators per tile take the
+// k-steps 0..3 (mod 4) and are summed as (p0 + p1) + (p2 + p3).  The input z-score's division is folded into the image
+// of the first layer (columns scaled by 1 / xu_std), the mean is subtracted when the input is staged.  An output layer of
+// one or two row tiles (nx <= 16) is split over K instead: warp 4 tile + q takes the k-steps q (mod 4), i.e. one of the
+// four partial sums, and the state update combines them.  Padding alphas / rows / k carry finite garbage times zero.
+// Every array is shared-memory resident (the caller takes this path in resident mode only) and addressed with 32-bit
+// shared addresses; per-thread roles (which (alpha, column) a thread stages, which (alpha, state) it integrates), their
+// addresses and the per-layer constants are fixed before the horizon loop, inside it addresses advance by constants.
+// NXT = nx at compile time (0: run time).
+// (scripts/dmma_microbench.cu, profiles/r02b_dmma_microbench.txt: 26 cycles latency, one mma per 16 cycles and SM
+// sub-partition = 64 multiply-adds per clock and SM, the DFMA rate -- the gain is in the operand traffic.)
+template <int NXT>
+__device__ __noinline__ void ls_rollouts_mma(const LsArgs *A, int a0, int na) {
+  const int tid = threadIdx.x;
+  const int nx = NXT ? NXT : A->nx, nu = A->nu, n = nx + nu, H = A->H, S = A->S, L = A->L;
+  constexpr int NTH = LS_WARPS * 32, NMAIN = 8;
+  const int lane = tid & 31, wp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+  const uint32_t S8 = (uint32_t)S * 8u;
+  const uint32_t a_hA = A->a_scr, a_hB = a_hA + (uint32_t)A->mwp * S8, a_part = a_hB + (uint32_t)A->mwp * S8;
+  auto sync_ls = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NTH) : "memory"); };
+  auto sync_main = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(NMAIN * 32) : "memory"); };
+  const bool prof = A->profile != 0;
+  long long tm = prof ? clock64() : 0;
+  unsigned long long lc[6] = {0, 0, 0, 0, 0, 0};         // thread 0: controls, layer 0, output layer, other layers, barrier, update
+  auto lapl = [&](int q) { if (prof) { const long long now = clock64(); lc[q] += (unsigned long long)(now - tm); tm = now; } };
+  // fragment-ordered weight image: Wf_l[(tile * KS + ks) * 32 + lane] = W_l[8 tile + lane / 4][4 ks + lane % 4], zero padded
+  for (int l = 0; l < L; ++l) {
+    const int Kin = A->Kin[l], N = A->N[l], ws = A->ws[l], KS = A->KS[l], cnt = A->MT[l] * KS * 32;
+    const uint32_t W = A->a_W[l], dst = A->a_Wf[l];
+    for (int e = tid; e < cnt; e += NTH) {
+      const int ln = e & 31, ks = (e >> 5) % KS, mt = (e >> 5) / KS, j = 8 * mt + (ln >> 2), k = 4 * ks + (ln & 3);
+      double w = (j < N && k < Kin) ? lds64(W + (uint32_t)(j * ws + k) * 8u) : 0.0;
+      if (l == 0 && k < Kin) w /= lds64(A->a_xu_std + (uint32_t)k * 8u);   // z = (v - mean) / std  ->  (v - mean) . (W / std)
+      sts64(dst + (uint32_t)e * 8u, w);
+    }
+  }
+  for (int t = tid; t < na * nx; t += NTH) {
+    const int j = t / nx, a = t - j * nx;
+    sts64(A->a_ls_states + (uint32_t)((a0 + j) * (H + 1) * nx + a) * 8u, A->x0[a]);
+  }
+  for (int t = tid; t < 2 * A->mwp * S; t += NTH) sts64(a_hA + (uint32_t)t * 8u, 0.0);
+  // ---- roles and addresses (the host takes this path only when 8 (nx + nu) <= NTH)
+  const bool stager = tid < na * n;
+  const int pj = stager ? tid / n : 0, pc = stager ? tid - pj * n : 0;
+  const bool is_ctl = stager && pc >= nx;
+  const int pa = is_ctl ? pc - nx : 0;
+  const double p_mean = lds64(A->a_xu_mean + (uint32_t)pc * 8u);
+  const uint32_t p_dst = a_hA + (uint32_t)(pc * S + pj) * 8u;
+  uint32_t p_row = A->a_ls_states + (uint32_t)((a0 + pj) * (H + 1) * nx) * 8u;       // this alpha's state at step i
+  uint32_t p_ref = A->a_states, p_kr = A->a_Ks + (uint32_t)(pa * nx) * 8u, p_ks = A->a_ks + (uint32_t)pa * 8u,
+           p_ct = A->a_ctrls + (uint32_t)pa * 8u, p_lsc = A->a_ls_ctrls + (uint32_t)((a0 + pj) * H * nu + pa) * 8u;
+  const double p_alpha = lds64(A->a_alphas + (uint32_t)(a0 + pj) * 8u), p_umin = lds64(A->a_umin + (uint32_t)pa * 8u),
+               p_umax = lds64(A->a_umax + (uint32_t)pa * 8u);
+  const bool bounded = A->bounded != 0;
+  const bool integrator = tid < na * nx;
+  const int uj = integrator ? tid / nx : 0, ua = integrator ? tid - uj * nx : 0;
+  const double u_std = lds64(A->a_dy_std + (uint32_t)ua * 8u), u_mean = lds64(A->a_dy_mean + (uint32_t)ua * 8u),
+               u_bias = lds64(A->a_B[L - 1] + (uint32_t)ua * 8u);
+  uint32_t u_x = A->a_ls_states + (uint32_t)((a0 + uj) * (H + 1) * nx + ua) * 8u;
+  const bool ksplit = A->MT[L - 1] * 4 <= NMAIN;         // output layer split over K (see above)
+  const uint32_t u_part = a_part + (uint32_t)(((ua >> 3) * 4) * 64 + (ua & 7) * 8 + uj) * 8u;
+  const uint32_t u_y = (((L & 1) ? a_hB : a_hA)) + (uint32_t)(ua * S + uj) * 8u;    // where the last layer's output lands
+  const uint32_t nx8 = (uint32_t)nx * 8u, nu8 = (uint32_t)nu * 8u, knx8 = (uint32_t)(nu * nx) * 8u;
+  const int act = A->act;
+  const uint32_t hb_off = (uint32_t)(t4 * S + g) * 8u, out_off = (uint32_t)(g * S + 2 * t4) * 8u, lane8 = (uint32_t)lane * 8u;
+  sync_ls();
+#pragma unroll 1
+  for (int i = 0; i < H; ++i) {
+    // controls (ilqr.py:201-204) and the centred input, one thread per (alpha, input column)
+    if (stager) {
+      double v;
+      if (!is_ctl) {
+        v = lds64(p_row + (uint32_t)pc * 8u);
+      } else {
+        double fb = 0.0;
+        if constexpr (NXT > 0) {
+          double kr[NXT], xi[NXT], xr[NXT];
+#pragma unroll
+          for (int b = 0; b < NXT; ++b) { kr[b] = lds64(p_kr + b * 8u); xi[b] = lds64(p_row + b * 8u); xr[b] = lds64(p_ref + b * 8u); }
+#pragma unroll
+          for (int b = 0; b < NXT; ++b) fb = fma(kr[b], xi[b] - xr[b], fb);
+        } else {
+          for (int b = 0; b < nx; ++b) fb = fma(lds64(p_kr + b * 8u), lds64(p_row + b * 8u) - lds64(p_ref + b * 8u), fb);
+        }
+        double u = fma(p_alpha, lds64(p_ks), lds64(p_ct)) + fb;
+        if (bounded) u = fmin(fmax(u, p_umin), p_umax);               // np.clip, ilqr.py:203-204
+        sts64(p_lsc, u);
+        v = u;
+        p_kr += knx8; p_ks += nu8; p_ct += nu8; p_lsc += nu8;
+      }
+      sts64(p_dst, v - p_mean);
+      p_row += nx8; p_ref += nx8;
+    }
+    sync_ls();
+    lapl(0);
+    if (wp < NMAIN) {
+      uint32_t hin = a_hA, hout = a_hB;
+#pragma unroll 1
+      for (int l = 0; l < L; ++l) {
+        const int KS = A->KS[l], MT = A->MT[l];
+        const bool last = (l == L - 1);
+        const uint32_t hb = hin + hb_off, wl = A->a_Wf[l] + lane8;
+        if (last && ksplit) {
+          // output layer, K split: this warp = (row tile, partial q); a chain of KS / 4 dependent mma
+          const int mt = wp >> 2, q = wp & 3;
+          if (mt < MT) {
+            double c0 = 0.0, c1 = 0.0;
+            const uint32_t wa = wl + (uint32_t)(mt * KS) * 256u;
+#pragma unroll 4
+            for (int ks = q; ks < KS; ks += 4) dmma_884(c0, c1, lds64(wa + (uint32_t)ks * 256u), lds64(hb + (uint32_t)ks * 4u * S8));
+            sts128(a_part + (uint32_t)((mt * 4 + q) * 64 + g * 8 + 2 * t4) * 8u, c0, c1);
+          }
+          lapl(2);
+          break;                                                    // the state update combines the partials behind sync_ls
+        }
+        const int N = A->N[l];
+        const uint32_t a_B = A->a_B[l];
+#pragma unroll 1
+        for (int mt = wp; mt < MT; mt += NMAIN) {
+          double acc[4][2];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
+          const uint32_t wa = wl + (uint32_t)(mt * KS) * 256u;
+          // software pipeline: the operands of the next four k-steps are in flight while this group's mma issue
+          double a_cur[4], b_cur[4], a_nxt[4], b_nxt[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { a_cur[q] = lds64(wa + q * 256u); b_cur[q] = lds64(hb + (uint32_t)q * 4u * S8); }
+#pragma unroll 1
+          for (int ks = 0; ks < KS; ks += 4) {
+            const bool more = ks + 4 < KS;
+            if (more) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                a_nxt[q] = lds64(wa + (uint32_t)(ks + 4 + q) * 256u);
+                b_nxt[q] = lds64(hb + (uint32_t)(ks + 4 + q) * 4u * S8);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dmma_884(acc[q][0], acc[q][1], a_cur[q], b_cur[q]);
+            if (more) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { a_cur[q] = a_nxt[q]; b_cur[q] = b_nxt[q]; }
+            }
+          }
+          const int j = 8 * mt + g;
+          const double bj = j < N ? lds64(a_B + (uint32_t)j * 8u) : 0.0;
+          double y0 = bj + ((acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]));
+          double y1 = bj + ((acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]));
+          if (!last) { y0 = ilqr_act(act, y0); y1 = ilqr_act(act, y1); }
+          sts128(hout + (uint32_t)(8 * mt) * S8 + out_off, y0, y1);
+        }
+        sync_main();
+        if (l == 0) lapl(1); else lapl(last ? 2 : 3);
+        const uint32_t t2 = hin; hin = hout; hout = t2;
+      }
+    }
+    sync_ls();
+    lapl(4);
+    // mlp.py:235-236; y = b + (p0 + p1) + (p2 + p3) when the output layer was split over K
+    if (integrator) {
+      double y;
+      if (ksplit) y = u_bias + ((lds64(u_part) + lds64(u_part + 512u)) + (lds64(u_part + 1024u) + lds64(u_part + 1536u)));
+      else y = lds64(u_y);
+      sts64(u_x + nx8, lds64(u_x) + fma(y, u_std, u_mean));
+      u_x += nx8;
+    }
+    sync_ls();
+    lapl(5);
+  }
+  if (prof && tid == 0) for (int q = 0; q < 6; ++q) A->prof[8 + q] += lc[q];
+}
+
 // Backward Riccati pass (ilqr.py:159-187) by ONE warp with warp barriers only.  A lone warp retires a dependent
 // instruction every ~7-10 cycles, so the recursion costs what it executes: NX / NU > 0 fix the dimensions at compile time
 // (loops unroll, index arithmetic folds; the cartpole shape 4 / 1 is instantiated), 0 = run-time dimensions.  Each
@@ -588,11 +817,13 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
   const double *nb = RES ? s_var : P.net_blob;
   double *traj = RES ? s_var + net_d : P.traj;
   double *s_h = s_var + (RES ? net_d + tl.total : 0);
-  const size_t phase_d = RES ? (ls_scratch(mw, LS) > JAC_WARPS * jpw ? ls_scratch(mw, LS) : JAC_WARPS * jpw) : ls_scratch(mw, LS);
+  const size_t lss = P.ls_mma ? (size_t)P.ls_doubles : ls_scratch(mw, LS);
+  const size_t phase_d = RES ? (lss > JAC_WARPS * jpw ? lss : JAC_WARPS * jpw) : lss;
   double *jac_wk = (RES ? s_h : P.jac_work) + (size_t)(warp < JAC_WARPS ? warp : 0) * jpw;
   int *s_tab_n = reinterpret_cast<int *>(s_h + phase_d);                          // e -> (e / n) << 16 | e % n
   int *s_tab_x = s_tab_n + n * n;                                                                    // e -> (e / nx) << 16 | e % nx
   __shared__ int s_flag[4];          // [0]=line search failed, [1]=used idx, [2]=refresh jac
+  __shared__ LsArgs s_ls;
   __shared__ int s_piv[MAX_NU];
   __shared__ double s_lin, s_quad;
 
@@ -606,6 +837,23 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
   if (RES) {
     double *dst = s_var;
     for (int t = tid; t < net.total; t += NT) dst[t] = P.net_blob[t];
+  }
+  if (RES && P.ls_mma && tid == 0) {                   // arguments of the out-of-line line search (shared addresses)
+    LsArgs &A = s_ls;
+    A.nx = nx; A.nu = nu; A.H = H; A.S = P.ls_S; A.mwp = P.ls_mwp; A.L = net.n_layers; A.act = net.act; A.bounded = P.bounded;
+    A.profile = P.ls_profile;
+    const uint32_t a_nb = sh32(nb), a_scr = sh32(s_h);
+    for (int l = 0; l < net.n_layers; ++l) {
+      A.KS[l] = P.ls_kp[l] >> 2; A.MT[l] = P.ls_mt[l]; A.N[l] = net.dims[l + 1]; A.Kin[l] = net.dims[l]; A.ws[l] = net.wstride[l];
+      A.a_W[l] = a_nb + (uint32_t)net.woff[l] * 8u; A.a_B[l] = a_nb + (uint32_t)net.boff[l] * 8u;
+      A.a_Wf[l] = a_scr + (uint32_t)(2 * P.ls_mwp * P.ls_S + 8 * 64 + P.ls_wf[l]) * 8u;
+    }
+    A.a_xu_mean = a_nb + (uint32_t)net.xu_mean * 8u; A.a_xu_std = a_nb + (uint32_t)net.xu_std * 8u;
+    A.a_dy_mean = a_nb + (uint32_t)net.dy_mean * 8u; A.a_dy_std = a_nb + (uint32_t)net.dy_std * 8u;
+    A.a_scr = a_scr; A.a_states = sh32(states); A.a_ctrls = sh32(ctrls); A.a_Ks = sh32(Ks); A.a_ks = sh32(ks);
+    A.a_ls_states = sh32(ls_states); A.a_ls_ctrls = sh32(ls_ctrls); A.a_alphas = sh32(c_alphas); A.a_umin = sh32(c_umin);
+    A.a_umax = sh32(c_umax);
+    A.x0 = P.x0; A.prof = P.prof;
   }
   for (int t = tid; t < (int)cst_doubles(nx, nu, LS); t += NT) s_cst[t] = P.cst[t];
   for (int t = tid; t < n * n; t += NT) s_tab_n[t] = ((t / n) << 16) | (t % n);
@@ -677,26 +925,57 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
     for (int t = tid; t < H * nu; t += NT) ksq += ks[t] * ks[t];
     const double ks_norm = sqrt(block_sum(ksq, s_red, tid));
 
-    // ---- line-search rollouts (ilqr.py:190-205)
-    if (warp < LS_WARPS) {
-      double *part = s_h + (size_t)2 * mw * ls_cols(LS);
-      if (LS <= 10) ls_rollouts<10, 1>(P, nb, s_h, part, states, ctrls, Ks, ks, ls_states, ls_ctrls, c_alphas, c_umin, c_umax, tid);
-      else ls_rollouts<10, 2>(P, nb, s_h, part, states, ctrls, Ks, ks, ls_states, ls_ctrls, c_alphas, c_umin, c_umax, tid);
+    // ---- line-search rollouts (ilqr.py:190-205) and the objective of every step size (per-step costs in parallel, then
+    //      a sequential sum per step size)
+    auto objectives = [&](int a0, int na) {
+      for (int t = tid; t < na * (H + 1); t += NT) {
+        const int j = a0 + t / (H + 1), i = t % (H + 1);
+        step_cost[(H + 1) + j * (H + 1) + i] = step_cost_of(ls_states + (size_t)j * (H + 1) * nx, ls_ctrls + (size_t)j * H * nu, i);
+      }
+      __syncthreads();
+      if (tid < na) {
+        double o = 0.0;
+        for (int i = 0; i <= H; ++i) o += step_cost[(H + 1) + (a0 + tid) * (H + 1) + i];
+        s_obj[a0 + tid] = o;
+      }
+      __syncthreads();
+    };
+    if (P.ls_mma) {
+      // eight step sizes at a time; the acceptance rule below walks them in order and stops at the first one it takes
+      // (or at once when the step is tiny), so a later tile is rolled out only if the rule would get that far
+      for (int a0 = 0; a0 < LS; a0 += 8) {
+        const int na = LS - a0 < 8 ? LS - a0 : 8;
+        if (warp < LS_WARPS)
+        {
+          if (nx == 4) ls_rollouts_mma<4>(&s_ls, a0, na);
+          else ls_rollouts_mma<0>(&s_ls, a0, na);
+        }
+        __syncthreads();
+        lap(2);
+        objectives(a0, na);
+        if (tid == 0) {
+          int stop = 0;
+          for (int l = a0; l < a0 + na && !stop; ++l) {
+            const double alpha = c_alphas[l];
+            const double expect = alpha * lin_cost_reduce + alpha * alpha * quad_cost_reduce / 2;
+            if ((obj - s_obj[l]) / (-expect) > P.ls_cost_threshold || ks_norm < P.u_threshold) stop = 1;
+          }
+          s_flag[3] = stop;
+        }
+        __syncthreads();
+        lap(3);
+        if (s_flag[3]) break;
+      }
+    } else {
+      if (warp < LS_WARPS) {
+        double *part = s_h + (size_t)2 * mw * ls_cols(LS);
+        if (LS <= 10) ls_rollouts<10, 1>(P, nb, s_h, part, states, ctrls, Ks, ks, ls_states, ls_ctrls, c_alphas, c_umin, c_umax, tid);
+        else ls_rollouts<10, 2>(P, nb, s_h, part, states, ctrls, Ks, ks, ls_states, ls_ctrls, c_alphas, c_umin, c_umax, tid);
+      }
+      __syncthreads();
+      lap(2);
+      objectives(0, LS);
     }
-    __syncthreads();
-    lap(2);
-    // objective of every alpha: per-step costs in parallel, then a sequential sum per alpha
-    for (int t = tid; t < LS * (H + 1); t += NT) {
-      const int j = t / (H + 1), i = t - j * (H + 1);
-      step_cost[(H + 1) + t] = step_cost_of(ls_states + (size_t)j * (H + 1) * nx, ls_ctrls + (size_t)j * H * nu, i);
-    }
-    __syncthreads();
-    if (tid < LS) {
-      double o = 0.0;
-      for (int i = 0; i <= H; ++i) o += step_cost[(H + 1) + tid * (H + 1) + i];
-      s_obj[tid] = o;
-    }
-    __syncthreads();
     // ---- backtracking acceptance (ilqr.py:208-238), thread 0 decides
     if (tid == 0) {
       int best_idx = -1, used = -1, have_best = 0;
@@ -880,7 +1159,40 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
     size_t fixed = (size_t)n * n * 2 + (size_t)nx * nx * 3 + 2 * nx + (size_t)nx * n + n + (size_t)nu * nx + nu +
                    (size_t)nu * nu + NWARPS + LS + 4 + 1 + ((cst_doubles(nx, nu, LS) + 1) & ~(size_t)1);
     const size_t tabs = ((size_t)n * n + (size_t)nx * nx + 1) / 2 + 1;       // ints, in doubles
-    const size_t jacs = (size_t)JAC_WARPS * jpw, lss = ls_scratch(mw, LS);
+    // line search on mma.m8n8k4.f64 fragments: activations [padded rows][S] x 2 + the fragment-ordered weight image
+    size_t lss_mma = 0;
+    {
+      int mwp = 0, off = 0;
+      P.ls_S = 20;                                       // = 4 (mod 16) doubles: conflict-free operand loads
+      for (int l = 0; l < net.n_layers; ++l) {
+        P.ls_kp[l] = (net.dims[l] + 15) & ~15;           // k-steps come in groups of four (one per partial accumulator)
+        P.ls_mt[l] = (net.dims[l + 1] + 7) / 8;
+        P.ls_wf[l] = off;
+        off += P.ls_mt[l] * 8 * P.ls_kp[l];
+        mwp = std::max(mwp, std::max(P.ls_kp[l], P.ls_mt[l] * 8));
+      }
+      P.ls_mwp = mwp;
+      lss_mma = (size_t)2 * mwp * P.ls_S + 8 * 64 + off;  // + the K-split partials of the output layer
+      P.ls_doubles = (int)lss_mma;
+    }
+    const size_t jacs = (size_t)JAC_WARPS * jpw, lss_old = ls_scratch(mw, LS);
+    size_t fixed_probe = (size_t)n * n * 2 + (size_t)nx * nx * 3 + 2 * nx + (size_t)nx * n + n + (size_t)nu * nx + nu +
+                         (size_t)nu * nu + NWARPS + LS + 4 + 1 + ((cst_doubles(nx, nu, LS) + 1) & ~(size_t)1) +
+                         ((size_t)n * n + (size_t)nx * nx + 1) / 2 + 1;
+    int optin_probe = 0;
+    cudaDeviceGetAttribute(&optin_probe, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+    const size_t cap_probe = (size_t)optin_probe > 2048 ? ((size_t)optin_probe - 2048) / sizeof(double) : 0;
+    {
+      // taken in resident mode only (it addresses every array as shared memory), when everything still fits with its
+      // phase scratch
+      const size_t base = (((size_t)net.total + 1) & ~(size_t)1) + tl.total;
+      const bool res_old = fixed_probe + base + std::max(jacs, lss_old) <= cap_probe;
+      const bool res_mma = fixed_probe + base + std::max(jacs, lss_mma) <= cap_probe;
+      (void)res_old;
+      P.ls_profile = getenv("AMPC_ILQR_LS_PROFILE") ? 1 : 0;
+      P.ls_mma = (!getenv("AMPC_ILQR_NO_MMA") && !getenv("AMPC_ILQR_NO_SMEM") && res_mma && 8 * n <= NT) ? 1 : 0;
+    }
+    const size_t lss = P.ls_mma ? lss_mma : lss_old;
     const size_t var = (((size_t)net.total + 1) & ~(size_t)1) + tl.total + (jacs > lss ? jacs : lss);
     fixed += tabs;
     int max_optin = 0;
@@ -925,7 +1237,7 @@ extern "C" int ampc_ilqr_debug_profile(ampc_ilqr *h, unsigned long long *out8) {
   if (getenv("AMPC_ILQR_LS_PROFILE")) {   // the line-search phase split (thread 0): controls, main loops, barrier, combine, barrier, update
     unsigned long long v[16];
     AMPC_CUDA_CHECK(cudaMemcpy(v, h->d_prof, sizeof(v), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "ilqr line search (cycles): controls %llu, main loops %llu, barrier %llu, combine %llu, barrier %llu, update %llu\n",
+    fprintf(stderr, "ilqr line search (cycles of thread 0; ls_rollouts: controls, main loops, barrier, combine, barrier, update; ls_rollouts_mma: controls, layer 0, output layer, other layers, barrier, update): %llu %llu %llu %llu %llu %llu\n",
             v[8], v[9], v[10], v[11], v[12], v[13]);
   }
   AMPC_CUDA_CHECK(cudaMemcpy(out8, h->d_prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
