@@ -64,3 +64,47 @@ def test_ilqr_matches_oracle_multi_dim_ctrl(nx, nu, hidden, act, H):
     np.testing.assert_allclose(ctrls, r["ctrls"], rtol=0, atol=1e-7)
     np.testing.assert_allclose(Ks, r["Ks"], rtol=1e-6, atol=1e-7)
     ctl.close()
+
+
+def _solve(p, cost, umin, umax, dt, H, x0, **kw):
+    ctl = _ctl(p, cost, umin, umax, dt, H, **kw)
+    conv, states, ctrls, Ks, ks = ctl.compute_ilqr(x0)
+    info = dict(ctl.last_info)
+    ctl.close()
+    return conv, states, ctrls, Ks, ks, info
+
+
+def test_ilqr_line_search_paths_agree(monkeypatch):
+    """The line search on FP64 tensor-core fragments (step sizes in tiles of eight, evaluated until the acceptance rule
+    stops) against the CUDA-core line search that rolls all step sizes out: same decisions, same trajectories."""
+    mlp, cost, umin, umax, _, dt = load_cartpole()
+    z = np.load(os.path.join(GOLDEN, "ilqr_cartpole_H50.npz"))
+    x0 = z["p0_x0"]
+    monkeypatch.delenv("AMPC_ILQR_NO_MMA", raising=False)
+    a = _solve(mlp, cost, umin, umax, dt, 50, x0)
+    monkeypatch.setenv("AMPC_ILQR_NO_MMA", "1")
+    b = _solve(mlp, cost, umin, umax, dt, 50, x0)
+    assert a[0] == b[0] and a[5]["alpha_idx"] == b[5]["alpha_idx"] and a[5]["n_iter"] == b[5]["n_iter"]
+    np.testing.assert_allclose(a[1], b[1], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(a[2], b[2], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("ls_max_iter,thr", [(12, 0.97), (20, 0.999), (5, 0.3)])
+def test_ilqr_later_step_size_tiles_match_oracle(ls_max_iter, thr):
+    """A demanding acceptance threshold sends the rule past the first eight step sizes (second and third tile of the
+    tensor-core line search, and the best-so-far fallback when none is accepted); ls_max_iter < 8 is a partial tile."""
+    nx, nu, H = 6, 2, 12
+    rng = np.random.default_rng(4)
+    p = synthetic_mlp(nx, nu, [48, 40], act="relu", seed=9)
+    A = rng.normal(size=(nx, nx))
+    cost = QuadCostParams(np.eye(nx) + 0.1 * A @ A.T, 0.05 * np.eye(nu), 5 * np.eye(nx), goal=0.1 * rng.normal(size=nx))
+    umin, umax = -np.ones(nu), 1.5 * np.ones(nu)
+    x0 = rng.normal(size=nx)
+    r = ilqr_solve(p, cost, 0.05, x0, H, (umin, umax), ls_max_iter=ls_max_iter, ls_discount=0.6, ls_cost_threshold=thr)
+    conv, states, ctrls, Ks, ks, info = _solve(p, cost, umin, umax, 0.05, H, x0, ls_max_iter=ls_max_iter, ls_discount=0.6,
+                                               ls_cost_threshold=thr)
+    assert conv == r["converged"] and info["n_iter"] == r["n_iter"] and info["alpha_idx"] == r["alpha_idx"]
+    if ls_max_iter > 8:
+        assert max(info["alpha_idx"]) >= 8, "the case is meant to reach the second tile of step sizes"
+    np.testing.assert_allclose(states, r["states"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(ctrls, r["ctrls"], rtol=0, atol=1e-7)
