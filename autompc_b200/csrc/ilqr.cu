@@ -60,6 +60,7 @@ struct IlqrParams {
   double *states, *ctrls, *Ks, *ks;   // outputs (global)
   int *info, *alpha_idx;
   // line search on FP64 tensor-core fragments (ls_rollouts_mma): on when the fragment-ordered weight image fits
+  int jac_mma, jac_SP, ls_wf_total;   // Jacobian refresh on the tensor-core path: on, panel row stride, doubles of the Wf image
   int ls_profile;                  // != 0: ls_rollouts_mma reads the clock at its phase boundaries (AMPC_ILQR_LS_PROFILE)
   int ls_mma, ls_S, ls_mwp, ls_doubles;   // activation row stride (doubles), padded activation rows, phase scratch in doubles
   int ls_wf[MAXL], ls_kp[MAXL], ls_mt[MAXL];   // per layer: offset of its image inside the Wf region, padded K, 8-row tiles
@@ -449,6 +450,9 @@ struct LsArgs {
   uint32_t a_scr, a_states, a_ctrls, a_Ks, a_ks, a_ls_states, a_ls_ctrls, a_alphas, a_umin, a_umax;
   const double *x0;                                          // global
   unsigned long long *prof;                                  // global
+  // jac_batch_mma
+  uint32_t a_W0s, a_G, a_PA, a_PB, a_tab, a_Jacs;            // W0 / xu_std (row-major), act' per hidden layer, panels, column -> step table
+  int SP, ncols;                                             // panel row stride (doubles), 8 * (nx + nu) panel columns per chunk
 };
 
 // Line-search rollouts on the FP64 tensor-core path: same contract as ls_rollouts for the `na` (<= 8) step sizes
@@ -472,37 +476,21 @@ struct LsArgs {
 // NXT = nx at compile time (0: run time).
 // (scripts/dmma_microbench.cu, profiles/r02b_dmma_microbench.txt: 26 cycles latency, one mma per 16 cycles and SM
 // sub-partition = 64 multiply-adds per clock and SM, the DFMA rate -- the gain is in the operand traffic.)
+// The routine is two loops over the horizon that meet at the barriers, each compiled on its own (a combined body kept
+// ~120 values alive and spilled; with 227 KB of shared memory the L1 that backs local memory is a few KB, so a spill
+// costs an L2 round trip):
+//   ls_mma_io      warps 8..15: stage the inputs of step i (controls, centred state), integrate the state after it;
+//   ls_mma_layers  warps 0..7 : the layers of step i on mma fragments.
+// Barrier 1 (all 16 warps) separates staging | layers | update; barrier 2 (8 warps) the layers among themselves.
 template <int NXT>
-__device__ __noinline__ void ls_rollouts_mma(const LsArgs *A, int a0, int na) {
-  const int tid = threadIdx.x;
-  const int nx = NXT ? NXT : A->nx, nu = A->nu, n = nx + nu, H = A->H, S = A->S, L = A->L;
+__device__ __noinline__ void ls_mma_io(const LsArgs *A, int a0, int na) {
   constexpr int NTH = LS_WARPS * 32, NMAIN = 8;
-  const int lane = tid & 31, wp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+  const int tid = (int)threadIdx.x - NMAIN * 32;         // 0 .. 255 among the io warps
+  const int nx = NXT ? NXT : A->nx, nu = A->nu, n = nx + nu, H = A->H, S = A->S, L = A->L;
   const uint32_t S8 = (uint32_t)S * 8u;
   const uint32_t a_hA = A->a_scr, a_hB = a_hA + (uint32_t)A->mwp * S8, a_part = a_hB + (uint32_t)A->mwp * S8;
   auto sync_ls = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NTH) : "memory"); };
-  auto sync_main = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(NMAIN * 32) : "memory"); };
-  const bool prof = A->profile != 0;
-  long long tm = prof ? clock64() : 0;
-  unsigned long long lc[6] = {0, 0, 0, 0, 0, 0};         // thread 0: controls, layer 0, output layer, other layers, barrier, update
-  auto lapl = [&](int q) { if (prof) { const long long now = clock64(); lc[q] += (unsigned long long)(now - tm); tm = now; } };
-  // fragment-ordered weight image: Wf_l[(tile * KS + ks) * 32 + lane] = W_l[8 tile + lane / 4][4 ks + lane % 4], zero padded
-  for (int l = 0; l < L; ++l) {
-    const int Kin = A->Kin[l], N = A->N[l], ws = A->ws[l], KS = A->KS[l], cnt = A->MT[l] * KS * 32;
-    const uint32_t W = A->a_W[l], dst = A->a_Wf[l];
-    for (int e = tid; e < cnt; e += NTH) {
-      const int ln = e & 31, ks = (e >> 5) % KS, mt = (e >> 5) / KS, j = 8 * mt + (ln >> 2), k = 4 * ks + (ln & 3);
-      double w = (j < N && k < Kin) ? lds64(W + (uint32_t)(j * ws + k) * 8u) : 0.0;
-      if (l == 0 && k < Kin) w /= lds64(A->a_xu_std + (uint32_t)k * 8u);   // z = (v - mean) / std  ->  (v - mean) . (W / std)
-      sts64(dst + (uint32_t)e * 8u, w);
-    }
-  }
-  for (int t = tid; t < na * nx; t += NTH) {
-    const int j = t / nx, a = t - j * nx;
-    sts64(A->a_ls_states + (uint32_t)((a0 + j) * (H + 1) * nx + a) * 8u, A->x0[a]);
-  }
-  for (int t = tid; t < 2 * A->mwp * S; t += NTH) sts64(a_hA + (uint32_t)t * 8u, 0.0);
-  // ---- roles and addresses (the host takes this path only when 8 (nx + nu) <= NTH)
+  // roles and addresses (the host takes this path only when 8 (nx + nu) <= 256)
   const bool stager = tid < na * n;
   const int pj = stager ? tid / n : 0, pc = stager ? tid - pj * n : 0;
   const bool is_ctl = stager && pc >= nx;
@@ -520,13 +508,12 @@ __device__ __noinline__ void ls_rollouts_mma(const LsArgs *A, int a0, int na) {
   const double u_std = lds64(A->a_dy_std + (uint32_t)ua * 8u), u_mean = lds64(A->a_dy_mean + (uint32_t)ua * 8u),
                u_bias = lds64(A->a_B[L - 1] + (uint32_t)ua * 8u);
   uint32_t u_x = A->a_ls_states + (uint32_t)((a0 + uj) * (H + 1) * nx + ua) * 8u;
-  const bool ksplit = A->MT[L - 1] * 4 <= NMAIN;         // output layer split over K (see above)
+  const bool ksplit = A->MT[L - 1] * 4 <= NMAIN;
   const uint32_t u_part = a_part + (uint32_t)(((ua >> 3) * 4) * 64 + (ua & 7) * 8 + uj) * 8u;
   const uint32_t u_y = (((L & 1) ? a_hB : a_hA)) + (uint32_t)(ua * S + uj) * 8u;    // where the last layer's output lands
   const uint32_t nx8 = (uint32_t)nx * 8u, nu8 = (uint32_t)nu * 8u, knx8 = (uint32_t)(nu * nx) * 8u;
-  const int act = A->act;
-  const uint32_t hb_off = (uint32_t)(t4 * S + g) * 8u, out_off = (uint32_t)(g * S + 2 * t4) * 8u, lane8 = (uint32_t)lane * 8u;
-  sync_ls();
+  if (integrator) sts64(u_x, A->x0[ua]);                 // every alpha starts from x0
+  sync_ls();                                             // (pairs with the entry barrier of ls_mma_layers)
 #pragma unroll 1
   for (int i = 0; i < H; ++i) {
     // controls (ilqr.py:201-204) and the centred input, one thread per (alpha, input column)
@@ -554,71 +541,8 @@ __device__ __noinline__ void ls_rollouts_mma(const LsArgs *A, int a0, int na) {
       sts64(p_dst, v - p_mean);
       p_row += nx8; p_ref += nx8;
     }
-    sync_ls();
-    lapl(0);
-    if (wp < NMAIN) {
-      uint32_t hin = a_hA, hout = a_hB;
-#pragma unroll 1
-      for (int l = 0; l < L; ++l) {
-        const int KS = A->KS[l], MT = A->MT[l];
-        const bool last = (l == L - 1);
-        const uint32_t hb = hin + hb_off, wl = A->a_Wf[l] + lane8;
-        if (last && ksplit) {
-          // output layer, K split: this warp = (row tile, partial q); a chain of KS / 4 dependent mma
-          const int mt = wp >> 2, q = wp & 3;
-          if (mt < MT) {
-            double c0 = 0.0, c1 = 0.0;
-            const uint32_t wa = wl + (uint32_t)(mt * KS) * 256u;
-#pragma unroll 4
-            for (int ks = q; ks < KS; ks += 4) dmma_884(c0, c1, lds64(wa + (uint32_t)ks * 256u), lds64(hb + (uint32_t)ks * 4u * S8));
-            sts128(a_part + (uint32_t)((mt * 4 + q) * 64 + g * 8 + 2 * t4) * 8u, c0, c1);
-          }
-          lapl(2);
-          break;                                                    // the state update combines the partials behind sync_ls
-        }
-        const int N = A->N[l];
-        const uint32_t a_B = A->a_B[l];
-#pragma unroll 1
-        for (int mt = wp; mt < MT; mt += NMAIN) {
-          double acc[4][2];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
-          const uint32_t wa = wl + (uint32_t)(mt * KS) * 256u;
-          // software pipeline: the operands of the next four k-steps are in flight while this group's mma issue
-          double a_cur[4], b_cur[4], a_nxt[4], b_nxt[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) { a_cur[q] = lds64(wa + q * 256u); b_cur[q] = lds64(hb + (uint32_t)q * 4u * S8); }
-#pragma unroll 1
-          for (int ks = 0; ks < KS; ks += 4) {
-            const bool more = ks + 4 < KS;
-            if (more) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                a_nxt[q] = lds64(wa + (uint32_t)(ks + 4 + q) * 256u);
-                b_nxt[q] = lds64(hb + (uint32_t)(ks + 4 + q) * 4u * S8);
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) dmma_884(acc[q][0], acc[q][1], a_cur[q], b_cur[q]);
-            if (more) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) { a_cur[q] = a_nxt[q]; b_cur[q] = b_nxt[q]; }
-            }
-          }
-          const int j = 8 * mt + g;
-          const double bj = j < N ? lds64(a_B + (uint32_t)j * 8u) : 0.0;
-          double y0 = bj + ((acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]));
-          double y1 = bj + ((acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]));
-          if (!last) { y0 = ilqr_act(act, y0); y1 = ilqr_act(act, y1); }
-          sts128(hout + (uint32_t)(8 * mt) * S8 + out_off, y0, y1);
-        }
-        sync_main();
-        if (l == 0) lapl(1); else lapl(last ? 2 : 3);
-        const uint32_t t2 = hin; hin = hout; hout = t2;
-      }
-    }
-    sync_ls();
-    lapl(4);
+    sync_ls();                                           // inputs staged -> layers
+    sync_ls();                                           // layers done
     // mlp.py:235-236; y = b + (p0 + p1) + (p2 + p3) when the output layer was split over K
     if (integrator) {
       double y;
@@ -627,10 +551,268 @@ __device__ __noinline__ void ls_rollouts_mma(const LsArgs *A, int a0, int na) {
       sts64(u_x + nx8, lds64(u_x) + fma(y, u_std, u_mean));
       u_x += nx8;
     }
-    sync_ls();
+    sync_ls();                                           // state integrated
+  }
+}
+
+__device__ __noinline__ void ls_mma_layers(const LsArgs *A) {
+  constexpr int NTH = LS_WARPS * 32, NMAIN = 8;
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+  const int H = A->H, S = A->S, L = A->L;
+  const uint32_t S8 = (uint32_t)S * 8u;
+  const uint32_t a_hA = A->a_scr, a_hB = a_hA + (uint32_t)A->mwp * S8, a_part = a_hB + (uint32_t)A->mwp * S8;
+  auto sync_ls = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NTH) : "memory"); };
+  auto sync_main = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(NMAIN * 32) : "memory"); };
+  const bool prof = A->profile != 0;
+  long long tm = prof ? clock64() : 0;
+  unsigned long long lc[6] = {0, 0, 0, 0, 0, 0};         // thread 0: staging (io warps), layer 0, output layer, other layers, -, update (io warps)
+  auto lapl = [&](int q) { if (prof) { const long long now = clock64(); lc[q] += (unsigned long long)(now - tm); tm = now; } };
+  const bool ksplit = A->MT[L - 1] * 4 <= NMAIN;         // output layer split over K
+  const int act = A->act;
+  const uint32_t hb_off = (uint32_t)(t4 * S + g) * 8u, out_off = (uint32_t)(g * S + 2 * t4) * 8u, lane8 = (uint32_t)lane * 8u;
+  sync_ls();
+#pragma unroll 1
+  for (int i = 0; i < H; ++i) {
+    sync_ls();                                           // inputs staged
+    lapl(0);
+    uint32_t hin = a_hA, hout = a_hB;
+#pragma unroll 1
+    for (int l = 0; l < L; ++l) {
+      const int KS = A->KS[l], MT = A->MT[l];
+      const bool last = (l == L - 1);
+      const uint32_t hb = hin + hb_off, wl = A->a_Wf[l] + lane8;
+      if (last && ksplit) {
+        // output layer, K split: this warp = (row tile, partial q); a chain of KS / 4 dependent mma
+        const int mt = wp >> 2, q = wp & 3;
+        if (mt < MT) {
+          double c0 = 0.0, c1 = 0.0;
+          const uint32_t wa = wl + (uint32_t)(mt * KS) * 256u;
+#pragma unroll 4
+          for (int ks = q; ks < KS; ks += 4) dmma_884(c0, c1, lds64(wa + (uint32_t)ks * 256u), lds64(hb + (uint32_t)ks * 4u * S8));
+          sts128(a_part + (uint32_t)((mt * 4 + q) * 64 + g * 8 + 2 * t4) * 8u, c0, c1);
+        }
+        lapl(2);
+        break;                                                      // the state update combines the partials behind the barrier
+      }
+      const int N = A->N[l];
+      const uint32_t a_B = A->a_B[l];
+#pragma unroll 1
+      for (int mt = wp; mt < MT; mt += NMAIN) {
+        double acc[4][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
+        const uint32_t wa = wl + (uint32_t)(mt * KS) * 256u;
+        // software pipeline: the operands of the next four k-steps are in flight while this group's mma issue
+        double a_cur[4], b_cur[4], a_nxt[4], b_nxt[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { a_cur[q] = lds64(wa + q * 256u); b_cur[q] = lds64(hb + (uint32_t)q * 4u * S8); }
+#pragma unroll 1
+        for (int ks = 0; ks < KS; ks += 4) {
+          const bool more = ks + 4 < KS;
+          if (more) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              a_nxt[q] = lds64(wa + (uint32_t)(ks + 4 + q) * 256u);
+              b_nxt[q] = lds64(hb + (uint32_t)(ks + 4 + q) * 4u * S8);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dmma_884(acc[q][0], acc[q][1], a_cur[q], b_cur[q]);
+          if (more) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { a_cur[q] = a_nxt[q]; b_cur[q] = b_nxt[q]; }
+          }
+        }
+        const int j = 8 * mt + g;
+        const double bj = j < N ? lds64(a_B + (uint32_t)j * 8u) : 0.0;
+        double y0 = bj + ((acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]));
+        double y1 = bj + ((acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]));
+        if (!last) { y0 = ilqr_act(act, y0); y1 = ilqr_act(act, y1); }
+        sts128(hout + (uint32_t)(8 * mt) * S8 + out_off, y0, y1);
+      }
+      sync_main();
+      if (l == 0) lapl(1); else lapl(last ? 2 : 3);
+      const uint32_t t2 = hin; hin = hout; hout = t2;
+    }
+    sync_ls();                                           // layers done -> update
+    sync_ls();                                           // state integrated
     lapl(5);
   }
   if (prof && tid == 0) for (int q = 0; q < 6; ++q) A->prof[8 + q] += lc[q];
+}
+
+// Caller side: all LS_WARPS warps.  Builds the fragment-ordered weight image (the per-warp Jacobian panels or the tensor-
+// core Jacobian refresh have used the phase scratch since the last call) and hands the two halves of the CTA their loops.
+template <int NXT>
+__device__ __forceinline__ void ls_rollouts_mma(const LsArgs *A, int a0, int na) {
+  constexpr int NTH = LS_WARPS * 32;
+  const int tid = threadIdx.x;
+  // fragment-ordered weight image: Wf_l[(tile * KS + ks) * 32 + lane] = W_l[8 tile + lane / 4][4 ks + lane % 4], zero padded
+  for (int l = 0; l < A->L; ++l) {
+    const int Kin = A->Kin[l], N = A->N[l], ws = A->ws[l], KS = A->KS[l], cnt = A->MT[l] * KS * 32;
+    const uint32_t W = A->a_W[l], dst = A->a_Wf[l];
+    for (int e = tid; e < cnt; e += NTH) {
+      const int ln = e & 31, ks = (e >> 5) % KS, mt = (e >> 5) / KS, j = 8 * mt + (ln >> 2), k = 4 * ks + (ln & 3);
+      double w = (j < N && k < Kin) ? lds64(W + (uint32_t)(j * ws + k) * 8u) : 0.0;
+      if (l == 0 && k < Kin) w /= lds64(A->a_xu_std + (uint32_t)k * 8u);   // z = (v - mean) / std  ->  (v - mean) . (W / std)
+      sts64(dst + (uint32_t)e * 8u, w);
+    }
+  }
+  for (int t = tid; t < 2 * A->mwp * A->S; t += NTH) sts64(A->a_scr + (uint32_t)t * 8u, 0.0);
+  if (tid < 8 * 32) ls_mma_layers(A);
+  else ls_mma_io<NXT>(A, a0, na);
+}
+
+__device__ __noinline__ double ilqr_act_grad_other(int act, double y) { return ampc_act_grad<double>(act, y); }
+__device__ __forceinline__ double ilqr_act_grad(int act, double y) {
+  if (act == AMPC_ACT_RELU) return y > 0.0 ? 1.0 : 0.0;
+  return ilqr_act_grad_other(act, y);
+}
+
+// Jacobian refresh on the FP64 tensor-core path (same contract as jac_batch, resident mode only): the horizon steps are
+// independent here, so they are the COLUMNS of the products -- eight steps per chunk.  Per chunk:
+//   forward pass of the hidden layers for the 8 steps (one 8-column tile, as in ls_rollouts_mma) -> activations and the
+//     activation derivatives g_l[j][step];
+//   first panel  P_0[j][(step, c)] = W_0[j][c] / xu_std[c] * g_0[j][step]  (element-wise, mlp.py:298);
+//   P_l = g_l . (W_l P_{l-1})  for the layers above: (8 rows) x (8 columns) x (4 k) mma tiles over the 8 (nx + nu) panel
+//     columns, tile pairs dealt to the 16 warps; the weights are the line search's fragment-ordered image;
+//   Jacs[step][a][c] = P_last[a][(step, c)] dy_std[a] + [a == c].
+// FP64 floor of the refresh at the 5-64-64-4 network: ~18 k cycles (64 multiply-adds per clock); the one-warp-per-step
+// routine takes ~107 k (operand loads, as in the old line search).
+__device__ __noinline__ void jac_batch_mma(const LsArgs *A, uint32_t a_xs, uint32_t a_us) {
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+  const int nx = A->nx, nu = A->nu, nin = nx + nu, H = A->H, S = A->S, L = A->L, SP = A->SP, ncols = A->ncols;
+  constexpr int NTH = NT, NW = NT / 32;
+  const uint32_t S8 = (uint32_t)S * 8u, SP8 = (uint32_t)SP * 8u;
+  const uint32_t a_hA = A->a_scr, a_hB = a_hA + (uint32_t)A->mwp * S8;
+  const int act = A->act;
+  // fragment-ordered weight image (as in ls_rollouts_mma; layer 0 carries 1 / xu_std), zeroed buffers, column table
+  for (int l = 0; l < L; ++l) {
+    const int Kin = A->Kin[l], N = A->N[l], ws = A->ws[l], KS = A->KS[l], cnt = A->MT[l] * KS * 32;
+    const uint32_t W = A->a_W[l], dst = A->a_Wf[l];
+    for (int e = tid; e < cnt; e += NTH) {
+      const int ln = e & 31, ks = (e >> 5) % KS, mt = (e >> 5) / KS, j = 8 * mt + (ln >> 2), k = 4 * ks + (ln & 3);
+      double w = (j < N && k < Kin) ? lds64(W + (uint32_t)(j * ws + k) * 8u) : 0.0;
+      if (l == 0 && k < Kin) w /= lds64(A->a_xu_std + (uint32_t)k * 8u);
+      sts64(dst + (uint32_t)e * 8u, w);
+    }
+  }
+  for (int t = tid; t < 2 * A->mwp * S; t += NTH) sts64(a_hA + (uint32_t)t * 8u, 0.0);
+  for (int t = tid; t < 2 * A->mwp * SP; t += NTH) sts64(A->a_PA + (uint32_t)t * 8u, 0.0);   // PA and PB are adjacent
+  for (int t = tid; t < ncols; t += NTH) asm volatile("st.shared.u32 [%0], %1;" ::"r"(A->a_tab + (uint32_t)t * 4u), "r"(t / nin) : "memory");
+  __syncthreads();
+  const int NTP = (ncols + 7) >> 3;                      // column tiles of a panel
+#pragma unroll 1
+  for (int c0 = 0; c0 < H; c0 += 8) {
+    const int ns = H - c0 < 8 ? H - c0 : 8;
+    // centred inputs of the chunk's steps (columns beyond ns keep the previous chunk's finite values)
+    for (int t = tid; t < ns * nin; t += NTH) {
+      const int sI = t / nin, c = t - sI * nin;
+      const double v = c < nx ? lds64(a_xs + (uint32_t)((c0 + sI) * nx + c) * 8u) : lds64(a_us + (uint32_t)((c0 + sI) * nu + (c - nx)) * 8u);
+      sts64(a_hA + (uint32_t)(c * S + sI) * 8u, v - lds64(A->a_xu_mean + (uint32_t)c * 8u));
+    }
+    __syncthreads();
+    // ---- forward pass of the hidden layers: activations and derivatives
+    uint32_t hin = a_hA, hout = a_hB;
+#pragma unroll 1
+    for (int l = 0; l + 1 < L; ++l) {
+      const int KS = A->KS[l], MT = A->MT[l], N = A->N[l];
+      const uint32_t hb = hin + (uint32_t)(t4 * S + g) * 8u, a_G = A->a_G + (uint32_t)(l * A->mwp * 8) * 8u;
+#pragma unroll 1
+      for (int mt = wp; mt < MT; mt += NW) {
+        double acc[4][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
+        const uint32_t wa = A->a_Wf[l] + (uint32_t)(mt * KS * 32 + lane) * 8u;
+#pragma unroll 1
+        for (int ks = 0; ks < KS; ks += 4) {
+          double a4[4], b4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { a4[q] = lds64(wa + (uint32_t)(ks + q) * 256u); b4[q] = lds64(hb + (uint32_t)(ks + q) * 4u * S8); }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dmma_884(acc[q][0], acc[q][1], a4[q], b4[q]);
+        }
+        const int j = 8 * mt + g;
+        const double bj = j < N ? lds64(A->a_B[l] + (uint32_t)j * 8u) : 0.0;
+        const double y0 = bj + ((acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]));
+        const double y1 = bj + ((acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]));
+        sts128(hout + (uint32_t)(j * S + 2 * t4) * 8u, ilqr_act(act, y0), ilqr_act(act, y1));
+        sts128(a_G + (uint32_t)(j * 8 + 2 * t4) * 8u, ilqr_act_grad(act, y0), ilqr_act_grad(act, y1));
+      }
+      __syncthreads();
+      const uint32_t t2 = hin; hin = hout; hout = t2;
+    }
+    // ---- first panel (mlp.py:298)
+    {
+      const int N = A->N[0];
+      for (int col = lane; col < ncols; col += 32) {
+        int sI;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sI) : "r"(A->a_tab + (uint32_t)col * 4u) : "memory");
+        const int c = col - sI * nin;
+        for (int j = wp; j < N; j += NW)
+          sts64(A->a_PA + (uint32_t)(j * SP + col) * 8u,
+                lds64(A->a_W0s + (uint32_t)(j * nin + c) * 8u) * lds64(A->a_G + (uint32_t)(j * 8 + sI) * 8u));
+      }
+    }
+    __syncthreads();
+    // ---- panels of the layers above
+    uint32_t pin = A->a_PA, pout = A->a_PB;
+#pragma unroll 1
+    for (int l = 1; l < L; ++l) {
+      const int KS = A->KS[l], MT = A->MT[l];
+      const bool last = (l == L - 1);
+      const uint32_t a_G = A->a_G + (uint32_t)(l * A->mwp * 8) * 8u;
+#pragma unroll 1
+      for (int pr = wp; pr < MT * NTP; pr += NW) {
+        const int mt = pr % MT, nt = pr / MT;
+        double acc[4][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
+        const uint32_t wa = A->a_Wf[l] + (uint32_t)(mt * KS * 32 + lane) * 8u;
+        const uint32_t pb = pin + (uint32_t)(t4 * SP + 8 * nt + g) * 8u;
+        double a_cur[4], b_cur[4], a_nxt[4], b_nxt[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { a_cur[q] = lds64(wa + q * 256u); b_cur[q] = lds64(pb + (uint32_t)q * 4u * SP8); }
+#pragma unroll 1
+        for (int ks = 0; ks < KS; ks += 4) {
+          const bool more = ks + 4 < KS;
+          if (more) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              a_nxt[q] = lds64(wa + (uint32_t)(ks + 4 + q) * 256u);
+              b_nxt[q] = lds64(pb + (uint32_t)(ks + 4 + q) * 4u * SP8);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dmma_884(acc[q][0], acc[q][1], a_cur[q], b_cur[q]);
+          if (more) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { a_cur[q] = a_nxt[q]; b_cur[q] = b_nxt[q]; }
+          }
+        }
+        const int j = 8 * mt + g, col = 8 * nt + 2 * t4;
+        double v0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+        double v1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+        if (!last) {
+          int s0, s1;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(s0) : "r"(A->a_tab + (uint32_t)(col < ncols ? col : 0) * 4u) : "memory");
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(s1) : "r"(A->a_tab + (uint32_t)(col + 1 < ncols ? col + 1 : 0) * 4u) : "memory");
+          v0 *= lds64(a_G + (uint32_t)(j * 8 + s0) * 8u);
+          v1 *= lds64(a_G + (uint32_t)(j * 8 + s1) * 8u);
+        }
+        sts128(pout + (uint32_t)(j * SP + col) * 8u, v0, v1);
+      }
+      __syncthreads();
+      const uint32_t t2 = pin; pin = pout; pout = t2;
+    }
+    // ---- mlp.py:300-305: scale by dy_std, add the identity of x' = x + dy
+    for (int e = tid; e < ns * nx * nin; e += NTH) {
+      const int sI = e / (nx * nin), r = e - sI * nx * nin, a = r / nin, c = r - a * nin;
+      sts64(A->a_Jacs + (uint32_t)(((c0 + sI) * nx + a) * nin + c) * 8u,
+            lds64(pin + (uint32_t)(a * SP + sI * nin + c) * 8u) * lds64(A->a_dy_std + (uint32_t)a * 8u) + ((c == a) ? 1.0 : 0.0));
+    }
+    __syncthreads();
+  }
 }
 
 // Backward Riccati pass (ilqr.py:159-187) by ONE warp with warp barriers only.  A lone warp retires a dependent
@@ -854,6 +1036,14 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
     A.a_ls_states = sh32(ls_states); A.a_ls_ctrls = sh32(ls_ctrls); A.a_alphas = sh32(c_alphas); A.a_umin = sh32(c_umin);
     A.a_umax = sh32(c_umax);
     A.x0 = P.x0; A.prof = P.prof;
+    A.a_W0s = a_nb + (uint32_t)net.w0s * 8u;
+    const uint32_t a_after = a_scr + (uint32_t)(2 * P.ls_mwp * P.ls_S + 8 * 64 + P.ls_wf_total) * 8u;
+    A.SP = P.jac_SP; A.ncols = 8 * n;
+    A.a_G = a_after;
+    A.a_PA = A.a_G + (uint32_t)((net.n_layers - 1) * P.ls_mwp * 8) * 8u;
+    A.a_PB = A.a_PA + (uint32_t)(P.ls_mwp * P.jac_SP) * 8u;
+    A.a_tab = A.a_PB + (uint32_t)(P.ls_mwp * P.jac_SP) * 8u;
+    A.a_Jacs = sh32(Jacs);
   }
   for (int t = tid; t < (int)cst_doubles(nx, nu, LS); t += NT) s_cst[t] = P.cst[t];
   for (int t = tid; t < n * n; t += NT) s_tab_n[t] = ((t / n) << 16) | (t % n);
@@ -898,7 +1088,8 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
     }
   }
   __syncthreads();
-  jac_batch(P, nb, states, ctrls, Jacs, jac_wk, warp, lane);
+  if (RES && P.jac_mma) jac_batch_mma(&s_ls, sh32(states), sh32(ctrls));
+  else jac_batch(P, nb, states, ctrls, Jacs, jac_wk, warp, lane);
   for (int i = tid; i <= H; i += NT) step_cost[i] = step_cost_of(states, ctrls, i);
   __syncthreads();
   double obj = 0.0;       // every thread tracks the same scalars (uniform control flow)
@@ -1005,7 +1196,10 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
     if (s_flag[0]) { ls_fail = 1; break; }
     const int used = s_flag[1];
     const double *nxs = ls_states + (size_t)used * (H + 1) * nx, *nus = ls_ctrls + (size_t)used * H * nu;
-    if (s_flag[2]) jac_batch(P, nb, nxs, nus, Jacs, jac_wk, warp, lane);   // ilqr.py:232 (stale Jacobians otherwise, as in the reference)
+    if (s_flag[2]) {                                       // ilqr.py:232 (stale Jacobians otherwise, as in the reference)
+      if (RES && P.jac_mma) jac_batch_mma(&s_ls, sh32(nxs), sh32(nus));
+      else jac_batch(P, nb, nxs, nus, Jacs, jac_wk, warp, lane);
+    }
     lap(4);
     if (tid == 0) P.alpha_idx[itr] = used;
     double dsq = 0.0;
@@ -1160,7 +1354,7 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
                    (size_t)nu * nu + NWARPS + LS + 4 + 1 + ((cst_doubles(nx, nu, LS) + 1) & ~(size_t)1);
     const size_t tabs = ((size_t)n * n + (size_t)nx * nx + 1) / 2 + 1;       // ints, in doubles
     // line search on mma.m8n8k4.f64 fragments: activations [padded rows][S] x 2 + the fragment-ordered weight image
-    size_t lss_mma = 0;
+    size_t lss_mma = 0, jac_mma_doubles = 0;
     {
       int mwp = 0, off = 0;
       P.ls_S = 20;                                       // = 4 (mod 16) doubles: conflict-free operand loads
@@ -1172,7 +1366,12 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
         mwp = std::max(mwp, std::max(P.ls_kp[l], P.ls_mt[l] * 8));
       }
       P.ls_mwp = mwp;
+      P.ls_wf_total = off;
       lss_mma = (size_t)2 * mwp * P.ls_S + 8 * 64 + off;  // + the K-split partials of the output layer
+      // Jacobian refresh on the same fragments: + act' per hidden layer, two panels of 8 (nx + nu) columns, column table
+      const int ncols = 8 * n, ncp = (ncols + 7) & ~7;
+      P.jac_SP = ncp + ((ncp & 7) == 4 ? 0 : 4);         // = 4 (mod 8): conflict-free operand loads
+      jac_mma_doubles = lss_mma + (size_t)(net.n_layers - 1) * mwp * 8 + (size_t)2 * mwp * P.jac_SP + (ncols + 1) / 2 + 2;
       P.ls_doubles = (int)lss_mma;
     }
     const size_t jacs = (size_t)JAC_WARPS * jpw, lss_old = ls_scratch(mw, LS);
@@ -1190,8 +1389,10 @@ extern "C" int ampc_ilqr_create(ampc_ilqr **out, const ampc_ilqr_cfg *cfg, const
       const bool res_mma = fixed_probe + base + std::max(jacs, lss_mma) <= cap_probe;
       (void)res_old;
       P.ls_profile = getenv("AMPC_ILQR_LS_PROFILE") ? 1 : 0;
-      P.ls_mma = (!getenv("AMPC_ILQR_NO_MMA") && !getenv("AMPC_ILQR_NO_SMEM") && res_mma && 8 * n <= NT) ? 1 : 0;
+      P.ls_mma = (!getenv("AMPC_ILQR_NO_MMA") && !getenv("AMPC_ILQR_NO_SMEM") && res_mma && 8 * n <= NT / 2) ? 1 : 0;
     }
+    // the tensor-core Jacobian refresh lives in the phase scratch the per-warp routine would use
+    P.jac_mma = (P.ls_mma && !getenv("AMPC_ILQR_NO_JAC_MMA") && jac_mma_doubles <= std::max(jacs, lss_mma)) ? 1 : 0;
     const size_t lss = P.ls_mma ? lss_mma : lss_old;
     const size_t var = (((size_t)net.total + 1) & ~(size_t)1) + tl.total + (jacs > lss ? jacs : lss);
     fixed += tabs;
