@@ -453,6 +453,7 @@ struct LsArgs {
   // jac_batch_mma
   uint32_t a_W0s, a_G, a_PA, a_PB, a_tab, a_Jacs;            // W0 / xu_std (row-major), act' per hidden layer, panels, column -> step table
   int SP, ncols;                                             // panel row stride (doubles), 8 * (nx + nu) panel columns per chunk
+  int wf_persistent;                                         // the weight image is built once per solve (jac_batch_mma in use)
 };
 
 // Line-search rollouts on the FP64 tensor-core path: same contract as ls_rollouts for the `na` (<= 8) step sizes
@@ -643,11 +644,11 @@ __device__ __noinline__ void ls_mma_layers(const LsArgs *A) {
 
 // Caller side: all LS_WARPS warps.  Builds the fragment-ordered weight image (the per-warp Jacobian panels or the tensor-
 // core Jacobian refresh have used the phase scratch since the last call) and hands the two halves of the CTA their loops.
-template <int NXT>
-__device__ __forceinline__ void ls_rollouts_mma(const LsArgs *A, int a0, int na) {
-  constexpr int NTH = LS_WARPS * 32;
+// Fragment-ordered weight image of every layer: Wf_l[(tile * KS + ks) * 32 + lane] = W_l[8 tile + lane / 4][4 ks + lane % 4],
+// zero padded; layer 0 carries 1 / xu_std.  By the first NTH threads of the CTA.
+__device__ __forceinline__ void ls_build_wf(const LsArgs *A, int NTH) {
   const int tid = threadIdx.x;
-  // fragment-ordered weight image: Wf_l[(tile * KS + ks) * 32 + lane] = W_l[8 tile + lane / 4][4 ks + lane % 4], zero padded
+  if (tid >= NTH) return;
   for (int l = 0; l < A->L; ++l) {
     const int Kin = A->Kin[l], N = A->N[l], ws = A->ws[l], KS = A->KS[l], cnt = A->MT[l] * KS * 32;
     const uint32_t W = A->a_W[l], dst = A->a_Wf[l];
@@ -658,7 +659,16 @@ __device__ __forceinline__ void ls_rollouts_mma(const LsArgs *A, int a0, int na)
       sts64(dst + (uint32_t)e * 8u, w);
     }
   }
-  for (int t = tid; t < 2 * A->mwp * A->S; t += NTH) sts64(A->a_scr + (uint32_t)t * 8u, 0.0);
+}
+
+template <int NXT>
+__device__ __forceinline__ void ls_rollouts_mma(const LsArgs *A, int a0, int na) {
+  constexpr int NTH = LS_WARPS * 32;
+  const int tid = threadIdx.x;
+  if (!A->wf_persistent) {                               // the per-warp Jacobian panels have used the phase scratch since the last call
+    ls_build_wf(A, NTH);
+    for (int t = tid; t < 2 * A->mwp * A->S; t += NTH) sts64(A->a_scr + (uint32_t)t * 8u, 0.0);
+  }
   if (tid < 8 * 32) ls_mma_layers(A);
   else ls_mma_io<NXT>(A, a0, na);
 }
@@ -686,21 +696,8 @@ __device__ __noinline__ void jac_batch_mma(const LsArgs *A, uint32_t a_xs, uint3
   const uint32_t S8 = (uint32_t)S * 8u, SP8 = (uint32_t)SP * 8u;
   const uint32_t a_hA = A->a_scr, a_hB = a_hA + (uint32_t)A->mwp * S8;
   const int act = A->act;
-  // fragment-ordered weight image (as in ls_rollouts_mma; layer 0 carries 1 / xu_std), zeroed buffers, column table
-  for (int l = 0; l < L; ++l) {
-    const int Kin = A->Kin[l], N = A->N[l], ws = A->ws[l], KS = A->KS[l], cnt = A->MT[l] * KS * 32;
-    const uint32_t W = A->a_W[l], dst = A->a_Wf[l];
-    for (int e = tid; e < cnt; e += NTH) {
-      const int ln = e & 31, ks = (e >> 5) % KS, mt = (e >> 5) / KS, j = 8 * mt + (ln >> 2), k = 4 * ks + (ln & 3);
-      double w = (j < N && k < Kin) ? lds64(W + (uint32_t)(j * ws + k) * 8u) : 0.0;
-      if (l == 0 && k < Kin) w /= lds64(A->a_xu_std + (uint32_t)k * 8u);
-      sts64(dst + (uint32_t)e * 8u, w);
-    }
-  }
-  for (int t = tid; t < 2 * A->mwp * S; t += NTH) sts64(a_hA + (uint32_t)t * 8u, 0.0);
-  for (int t = tid; t < 2 * A->mwp * SP; t += NTH) sts64(A->a_PA + (uint32_t)t * 8u, 0.0);   // PA and PB are adjacent
-  for (int t = tid; t < ncols; t += NTH) asm volatile("st.shared.u32 [%0], %1;" ::"r"(A->a_tab + (uint32_t)t * 4u), "r"(t / nin) : "memory");
-  __syncthreads();
+  // (weight image, zeroed buffers and the column -> step table: set up once per solve by the kernel, they persist -- no
+  // phase between two calls writes that part of the phase scratch when this routine is in use)
   const int NTP = (ncols + 7) >> 3;                      // column tiles of a panel
 #pragma unroll 1
   for (int c0 = 0; c0 < H; c0 += 8) {
@@ -1044,6 +1041,7 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
     A.a_PB = A.a_PA + (uint32_t)(P.ls_mwp * P.jac_SP) * 8u;
     A.a_tab = A.a_PB + (uint32_t)(P.ls_mwp * P.jac_SP) * 8u;
     A.a_Jacs = sh32(Jacs);
+    A.wf_persistent = P.jac_mma;
   }
   for (int t = tid; t < (int)cst_doubles(nx, nu, LS); t += NT) s_cst[t] = P.cst[t];
   for (int t = tid; t < n * n; t += NT) s_tab_n[t] = ((t / n) << 16) | (t % n);
@@ -1072,6 +1070,13 @@ __global__ void __launch_bounds__(NT) ilqr_kernel(const IlqrParams P) {
     return quad_form(c_F, xs + (size_t)H * nx, c_goalF, nx);
   };
 
+  if (RES && P.jac_mma) {                                // tensor-core phases: zero their scratch, build the image and the table once
+    for (int t = tid; t < (int)phase_d; t += NT) s_h[t] = 0.0;
+    __syncthreads();
+    ls_build_wf(&s_ls, NT);
+    for (int t = tid; t < 8 * n; t += NT) asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_ls.a_tab + (uint32_t)t * 4u), "r"(t / n) : "memory");
+    __syncthreads();
+  }
   // ---- initial rollout (ilqr.py:141-147) by line-search group 0; Jacobians are evaluated in one batch afterwards
   if (grp == 0) {
     double *h0 = s_h, *h1 = s_h + mw;
