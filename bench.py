@@ -108,6 +108,19 @@ def measured_peaks():
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="B200_PROFILING.md fallback (of fallback)")
 
 
+def tc_build_note(ctl):
+    """Which build of the tensor-core kernel the handle runs (debug tap of the C ABI); '' for the fp32 kernel."""
+    try:
+        from autompc_b200 import _abi
+        mode = int(_abi.lib().ampc_mppi_debug_tc_mode(ctl._h))
+    except Exception:
+        return ""
+    if not mode:
+        return ""
+    return ", cta_group::%d%s" % (mode & 3, ", dz build (input layer fed by the output accumulator through kind::tf32)"
+                                  if mode & 16 else "")
+
+
 def ncu_traffic(workload_name, precision, world):
     """(bytes, source): dram__bytes_read.sum + dram__bytes_write.sum per launch of the rollout kernel.  NOT measured by
     this run (a number taken under a profiler never is a bench value): it is read from profiles/traffic.json, which
@@ -534,7 +547,9 @@ def gpu_arm_mppi(args, wl, d):
             value_note = ("weak scaling: %d x solves per second = solves of the base problem (K=%d) per second; one solve of "
                           "K=%d samples takes ms_per_step" % (world, wl["K"] // world, wl["K"]))
         flops = mlp_flops_per_solve(w, wl["K"], wl["H"])
-        traffic, traffic_src = ncu_traffic(wl["name"], ctl.precision, world)
+        # captures are per kernel build: "<precision>" = the dz build, "<precision>-nodz" = the build without it
+        traffic, traffic_src = ncu_traffic(wl["name"], ctl.precision + ("" if "dz build" in tc_build_note(ctl) or ctl.precision == "fp32"
+                                                                        else "-nodz"), world)
         fused = world > 1 and ctl.exchange == "nvlink"
         # dominant kernel = the rollout kernel; at N=1 it is the whole step.  Its average duration over
         # the timed region is ms_per_step minus the (tiny) merge kernel at N>1, which we do not subtract.
@@ -549,9 +564,11 @@ def gpu_arm_mppi(args, wl, d):
                        "precision_note": {"fp16": "tcgen05 kind::f16 with IEEE-half operands (11-bit significands = the "
                                                   "operand precision of tf32), fp32 accumulate/state/cost; deviation of "
                                                   "the updated action sequence from the float64 oracle at this size: "
-                                                  "2.1e-4 (profiles/r02_precision.jsonl)",
+                                                  "2.3e-4 with the dz build, 2.1e-4 without (profiles/r02_precision_dz.jsonl, "
+                                                  "r02_precision.jsonl)",
                                           "bf16": "tcgen05 kind::f16 with bf16 operands; deviation from the float64 "
-                                                  "oracle at this size: 2.1e-3 (profiles/r02_precision.jsonl)",
+                                                  "oracle at this size: 3.4e-3 with the dz build, 2.1e-3 without "
+                                                  "(profiles/r02_precision_dz.jsonl, r02_precision.jsonl)",
                                           "fp32": "CUDA-core fp32 FMA; deviation from the float64 oracle: 1.3e-5"}[ctl.precision],
                        "parallelism": ("%d samples sharded over %d GPU(s) (%s scaling), %d-float softmax record exchanged by %s"
                                        % (wl["K"], world, args.scaling, 2 + wl["H"] * nu,
@@ -575,7 +592,7 @@ def gpu_arm_mppi(args, wl, d):
                          "flop_per_launch": flops / world, "peak_source": "bf16 dense burst (kind::f16 runs fp16 and bf16 "
                          "operands at the same rate), " + peaks["source"],
                          "frac_of_sustained": achieved / peaks["bf16_sustained"],
-                         "kernel": "mppi_rollout (%s)" % ctl.precision},
+                         "kernel": "mppi_rollout (%s)%s" % (ctl.precision, tc_build_note(ctl))},
         }
         if parity is not None:
             line["parity"] = parity
