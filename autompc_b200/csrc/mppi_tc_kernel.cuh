@@ -32,6 +32,13 @@
 // Work that does not depend on the state (next step's noise, clipping, control cost) runs in the
 // shadow of the layer-1 MMAs.
 //
+// DZ build (template flag; ReLU networks with >= 2 hidden layers): the state update is linear, z_{i+1} = z_i + dz_i, so the
+// input layer of step i+1 is issued as  W0 [z_i | u_{i+1} | 1]  (16-bit operands the owners stored one layer earlier, in
+// tensor-memory columns the last hidden GEMM does not read)  +  W0x dz_i  (kind::tf32 MMAs whose A operand is the output
+// layer's fp32 accumulator, read in place): no epilogue hop between the output layer and the next input layer, and the
+// owners integrate z off the critical path.  The layer loop of the epilogue warps is rolled in that build
+// (mppi_tc_hidden_layer.inc is its body in both builds).
+//
 // The clipped noise (mppi.py:139) of every (step, control, sample) is written to an L2-resident
 // scratch and re-read once the softmax weights are known (mppi.py:115-117); per-CTA partial records
 // (min, sum w, sum w*eps) are merged by the last CTA to finish, exactly like the fp32 kernel.
