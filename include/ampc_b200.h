@@ -50,6 +50,10 @@ enum {
                          outside that range (AMPC_ERR_UNSUPPORTED).  The reference network is
                          float64 (autompc/sysid/mlp.py:165); this is the fp32-class tensor-core mode */
 };
+/* Both tensor-core modes run the "dz" build of the kernel for ReLU networks with two or more hidden layers when its
+ * extra image fits in shared memory: the input layer of step i+1 is the 16-bit GEMM on [z_i | u_{i+1} | 1] plus a
+ * kind::tf32 GEMM on the output layer's fp32 accumulator (the increment of the normalised state), see DESIGN.md 3.1.
+ * Same stated tolerances; AMPC_TC_DZ=0 in the environment at create() keeps the build without it. */
 
 #define AMPC_MAX_LAYERS 5 /* <= 4 hidden + output, autompc/sysid/mlp.py:110-111 */
 #define AMPC_MAX_WIDTH 256 /* hidden_size upper bound, autompc/sysid/mlp.py:112-119 */
