@@ -180,7 +180,21 @@ struct AmpcMppiParams {
   // host-buffer entry point: the observation rides in the kernel parameters (no H2D copy on the stream) ...
   int x0_inline;          // != 0: use x0_val instead of x0
   float x0_val[32];       // nx <= 32 on this path
+  // ... and the last CTA publishes "control written" in mapped pinned host memory, so that the host can return as
+  // soon as the result has landed instead of waiting for the stream to drain (null: off)
+  unsigned int *host_flag;
+  unsigned int host_seq;
 };
+
+// Called by every thread of the CTA that finished the solve, after the control has been written.
+__device__ __forceinline__ void ampc_publish_host_flag(const AmpcMppiParams &p) {
+  if (p.host_flag == nullptr) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned int *>(p.host_flag) = p.host_seq;
+  }
+}
 
 // Merge softmax partial records [m, s, W(HN)] (block level or rank level) and either
 // apply the update (mppi.py:115-118) or emit the merged record.  Called by one CTA.

@@ -69,7 +69,8 @@ struct ampc_mppi {
   float *d_wpack = nullptr, *d_consts = nullptr, *d_act = nullptr, *d_costs = nullptr, *d_term = nullptr;
   float *d_partials = nullptr, *d_x0 = nullptr, *d_u = nullptr, *d_eps = nullptr;
   unsigned int *d_ticket = nullptr;
-  float *h_pin = nullptr;          // pinned staging: x0 (nx) | u (nu)
+  float *h_pin = nullptr;          // pinned staging: x0 (nx) | u (nu) | "control written" sequence number (one word)
+  unsigned int host_seq = 0;       // sequence number of the last host-buffer solve
   float *d_pin = nullptr;          // the same buffer as the device sees it (mapped): the control is written straight to it
   float *h_eps = nullptr;          // pinned staging for external eps (lazily)
   size_t eps_elems = 0;
@@ -201,8 +202,10 @@ void free_handle(ampc_mppi *h) {
 // fused = true: the multi-GPU exchange runs in the kernel's tail (ampc_mppi_connect_peers_* done before)
 int launch_rollout(ampc_mppi *h, const float *dev_x0, const float *dev_eps, uint64_t seed, uint64_t counter,
                    float *dev_u, float *dev_record, cudaStream_t stream, const float *inline_x0 = nullptr,
-                   bool fused = false) {
+                   bool fused = false, unsigned int *host_flag = nullptr, unsigned int host_seq = 0) {
   AmpcMppiParams p = h->p;
+  p.host_flag = host_flag;
+  p.host_seq = host_seq;
   p.x0_inline = 0;
   if (inline_x0) {
     p.x0_inline = 1;
@@ -259,9 +262,31 @@ int solve_host_impl(ampc_mppi *h, const double *host_x0, const double *host_eps,
     // The only host traffic besides (optional) external noise is the observation in (nx floats) and the control out
     // (nu floats).  The observation rides in the kernel parameters and the last CTA writes the control straight into
     // the mapped pinned buffer: one launch + one synchronise instead of copy -> launch -> copy on the stream.
-    int rc = launch_rollout(h, h->d_x0, d_eps, seed, counter, h->d_pin + nx, nullptr, h->stream, h->h_pin, fused);
+    // The kernel's last CTA also publishes a sequence number behind the control (system-scope fence in between); the
+    // host spins on it and returns when the result has landed -- cudaStreamSynchronize would also wait for the
+    // kernel's teardown and costs a driver round trip.  The stream is polled now and then so that a failed launch
+    // surfaces as an error instead of a hang.  (AMPC_NO_SPIN=1: synchronise the stream instead.)
+    static const bool spin = !getenv("AMPC_NO_SPIN");
+    volatile unsigned int *flag = reinterpret_cast<volatile unsigned int *>(h->h_pin + nx + nu);
+    const unsigned int seq = ++h->host_seq ? h->host_seq : ++h->host_seq;     // never 0
+    int rc = launch_rollout(h, h->d_x0, d_eps, seed, counter, h->d_pin + nx, nullptr, h->stream, h->h_pin, fused,
+                            spin ? reinterpret_cast<unsigned int *>(h->d_pin + nx + nu) : nullptr, seq);
     if (rc) return rc;
-    AMPC_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (spin) {
+      for (unsigned int it = 1;; ++it) {
+        if (*flag == seq) break;
+        if ((it & 0x3FFFu) == 0u) {
+          const cudaError_t q = cudaStreamQuery(h->stream);
+          if (q == cudaSuccess) { if (*flag != seq) AMPC_CUDA_CHECK(cudaStreamSynchronize(h->stream)); break; }
+          if (q != cudaErrorNotReady) AMPC_CUDA_CHECK(q);
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+      }
+    } else {
+      AMPC_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    }
     for (int j = 0; j < nu; ++j) host_u[j] = h->h_pin[nx + j];
     return AMPC_OK;
   }
@@ -369,7 +394,8 @@ extern "C" int ampc_mppi_create(ampc_mppi **out, const ampc_mppi_cfg *cfg, const
   AMPC_CREATE_CHECK(cudaMalloc(&h->d_u, nu * sizeof(float)));
   AMPC_CREATE_CHECK(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
   AMPC_CREATE_CHECK(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
-  AMPC_CREATE_CHECK(cudaHostAlloc(&h->h_pin, (nx + nu) * sizeof(float), cudaHostAllocMapped));
+  AMPC_CREATE_CHECK(cudaHostAlloc(&h->h_pin, (nx + nu + 1) * sizeof(float), cudaHostAllocMapped));
+  memset(h->h_pin, 0, (nx + nu + 1) * sizeof(float));
   AMPC_CREATE_CHECK(cudaHostGetDevicePointer((void **)&h->d_pin, h->h_pin, 0));
   p.consts = h->d_consts; p.act_seq = h->d_act; p.costs = h->d_costs; p.term_out = h->d_term;
   p.ticket = h->d_ticket;

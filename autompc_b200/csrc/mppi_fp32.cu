@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(NTHR) mppi_rollout_fp32_kernel(const AmpcMppiP
                        p.record_out, s_misc);
     if (p.peer_mail != nullptr) ampc_peer_exchange_merge(p, p.record_out, HN, s_act, c_scale, s_misc);
     if (tid == 0) *p.ticket = 0u;
+    ampc_publish_host_flag(p);
   }
 }
 

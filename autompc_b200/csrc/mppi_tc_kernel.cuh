@@ -887,6 +887,7 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
     }
     if (p.peer_mail != nullptr) ampc_peer_exchange_merge(p, p.record_out, HN, s_act, c_scale, s_misc);
     if (tid == 0) *p.ticket = 0u;
+    ampc_publish_host_flag(p);
   }
   // ---- teardown
   trace(-1, 0xA4);                                      // ticket taken / merge done (if this was the last CTA)

@@ -586,8 +586,9 @@ def gpu_arm_mppi(args, wl, d):
                     "h2d_bytes_per_step": 4 * nx,
                     "d2h_bytes_per_step": 4 * nu, "api": "autompc_b200.MPPI.run(state, new_obs) with NumPy float64 buffers",
                     "transfer": "host observation -> pinned float32 -> kernel parameters (H2D with the launch); control "
-                                "written by the kernel's last CTA into mapped pinned host memory (D2H), one stream "
-                                "synchronise per step" if (world == 1 or fused) else "pinned H2D / D2H copies on the stream"},
+                                "written by the kernel's last CTA into mapped pinned host memory (D2H) with a sequence "
+                                "number behind it that the host spins on (no stream synchronise)"
+                                if (world == 1 or fused) else "pinned H2D / D2H copies on the stream"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_burst"], "traffic": traffic, "traffic_source": traffic_src,
