@@ -187,6 +187,7 @@ int validate(const ampc_mppi_cfg *cfg, const ampc_mlp_desc *mlp, const ampc_quad
 void free_handle(ampc_mppi *h) {
   if (!h) return;
   DeviceGuard g(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);   // a host-buffer solve returns before its kernel has torn down
   if (h->tc) ampc_mppi_tc_destroy(h->tc);
   cudaFree(h->d_wpack); cudaFree(h->d_consts); cudaFree(h->d_act); cudaFree(h->d_costs); cudaFree(h->d_term);
   cudaFree(h->d_partials); cudaFree(h->d_x0); cudaFree(h->d_u); cudaFree(h->d_eps); cudaFree(h->d_ticket);
