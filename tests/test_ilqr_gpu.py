@@ -108,3 +108,24 @@ def test_ilqr_later_step_size_tiles_match_oracle(ls_max_iter, thr):
         assert max(info["alpha_idx"]) >= 8, "the case is meant to reach the second tile of step sizes"
     np.testing.assert_allclose(states, r["states"], rtol=0, atol=1e-7)
     np.testing.assert_allclose(ctrls, r["ctrls"], rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("env", [{"AMPC_ILQR_NO_JAC_MMA": "1"}, {"AMPC_ILQR_NO_SMEM": "1"}])
+def test_ilqr_fallback_paths_match_reference_fixture(env, monkeypatch):
+    """The other routes through the solve kernel -- tensor-core line search with the one-warp-per-step Jacobian refresh
+    (the phase scratch is shared: the weight image is rebuilt per call), and the kernel on global scratch (nothing
+    resident, CUDA-core line search) -- against the unmodified-reference fixture."""
+    for k in ("AMPC_ILQR_NO_MMA", "AMPC_ILQR_NO_JAC_MMA", "AMPC_ILQR_NO_SMEM"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    z = np.load(os.path.join(GOLDEN, "ilqr_cartpole_H10.npz"))
+    mlp, cost, umin, umax, _, dt = load_cartpole()
+    ctl = _ctl(mlp, cost, umin, umax, dt, int(z["H"]))
+    conv, states, ctrls, Ks, ks = ctl.compute_ilqr(z["p0_x0"])
+    info = ctl.last_info
+    assert conv == bool(z["p0_converged"]) and info["n_iter"] == int(z["p0_n_iter"])
+    assert info["alpha_idx"] == [int(a) for a in z["p0_alpha_idx"]]
+    np.testing.assert_allclose(states, z["p0_states"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(ctrls, z["p0_ctrls"], rtol=0, atol=1e-7)
+    ctl.close()
