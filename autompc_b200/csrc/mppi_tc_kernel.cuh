@@ -557,8 +557,9 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
           //                                                         of that layer's epilogue: "early" part E)
           //                              + W0x dz_i               (kind::tf32; A = the output layer's fp32 accumulator, read
           //                                                         in place at YCOL of the same buffer, no epilogue hop: T).
-          // Order  E(h0) | wait bar_y | T(h0) commit0  E(h1) T(h1) commit1 :  E(h0) executes while this thread waits for
-          // the output layer's commit (T reads what other MMAs wrote: not a pair the tensor pipe orders by itself).
+          // Order  E(h0) E(h1) | wait bar_y | T(h0) commit0  T(h1) commit1 :  E executes while this thread waits for the
+          // output layer's commit (T reads what other MMAs wrote: not a pair the tensor pipe orders by itself).  (With
+          // E(h1) behind commit0 instead: 0.2361 vs 0.2343 ms on one box.)
           const uint32_t d_addr = (n & 1u) * TMEM_BUF, a_addr = ((n + 1u) & 1u) * TMEM_BUF;
 #pragma unroll
           for (int h = 0; h < MAXG; ++h) {
@@ -568,14 +569,18 @@ __global__ void __launch_bounds__(NTHR, 1) mppi_rollout_tc_kernel(const AmpcMppi
               for (int ks = 0; ks < 4; ++ks)
                 if (ks < nks0)
                   umma_ts<CG>(dh, a_addr + ecol + (uint32_t)(ks * 8), e_lo[h] + (uint32_t)(ks * 2), id_l[0], ks > 0 ? 1u : 0u);
-              if (h == 0) {
-                trace(i, 0x61);                         // E(h0) issued
-                if (a.dz != 2) {                        // (dz == 2: measurement only -- rely on the pipe's issue order)
-                  if (!mbar_test_wait(bar_y, (uint32_t)i & 1u)) mbar_wait(bar_y, (uint32_t)i & 1u);
-                  tc_fence_after();
-                }
-                trace(i, 0x60);                         // output-layer accumulator of step i complete (issuer)
-              }
+            }
+          }
+          trace(i, 0x61);                               // E issued
+          if (a.dz != 2) {                              // (dz == 2: measurement only -- rely on the pipe's issue order)
+            if (!mbar_test_wait(bar_y, (uint32_t)i & 1u)) mbar_wait(bar_y, (uint32_t)i & 1u);
+            tc_fence_after();
+          }
+          trace(i, 0x60);                               // output-layer accumulator of step i complete (issuer)
+#pragma unroll
+          for (int h = 0; h < MAXG; ++h) {
+            if (h < nh0) {
+              const uint32_t dh = d_addr + (uint32_t)h * hw0;
 #pragma unroll
               for (int ks = 0; ks < NKX; ++ks)
                 umma_ts_tf32<CG>(dh, a_addr + (uint32_t)(YCOL + ks * 8), x_lo[h] + (uint32_t)(ks * 2), idx, 1u);
