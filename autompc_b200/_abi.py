@@ -74,6 +74,7 @@ EXPORTS = {
     "ampc_mlp_pred_diff_batch": [C.c_void_p, C.c_int32, _dp, _dp, _dp, _dp, _dp],
     "ampc_mlp_nmpc_constraint": [C.c_void_p, C.c_int32, _dp, _dp],
     "ampc_mlp_nmpc_jacobian": [C.c_void_p, C.c_int32, _dp, _dp],
+    "ampc_mlp_debug_last_kernel_ms": [C.c_void_p, C.POINTER(C.c_float)],
     "ampc_linear_create": [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _dp, _dp, C.c_int32],
     "ampc_linear_destroy": [C.c_void_p],
     "ampc_linear_pred_batch": [C.c_void_p, C.c_int32, _dp, _dp, _dp],

@@ -7,9 +7,11 @@
 //   J_0 = W_0 diag(1/xu_std),  J_l = W_l (act'(pre_{l-1}) * J_{l-1}),  J = diag(dy_std) J_L,
 // which is the closed form of the reference's eye(nx) back-propagation.
 //
-// One CTA per sample; activations and the two Jacobian panels live in shared
+// One CTA per sample (eight samples per CTA for pred_batch / k-step rollouts on batches
+// beyond one wave, ampc_mlp_blocked); activations and the two Jacobian panels live in shared
 // memory; weights are stored in-major ([in][out]) so neighbouring threads read
 // neighbouring outputs.  The same device routines are reused by the iLQR kernel.
+#include <cstdlib>
 #include <vector>
 
 #include "ampc_common.cuh"
@@ -19,7 +21,10 @@ struct ampc_mlp {
   AmpcMlpF64 net;
   int device = 0;
   double *d_blob = nullptr;
-  size_t smem_pred = 0, smem_diff = 0;
+  size_t smem_pred = 0, smem_batch = 0, smem_diff = 0;
+  double *d_scratch = nullptr;       // grow-only staging for the host-buffer entry points (no cudaMalloc per call)
+  size_t scratch_doubles = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around the last launch (ampc_mlp_debug_last_kernel_ms)
 };
 
 namespace {
@@ -39,6 +44,7 @@ __device__ __forceinline__ double ampc_box_cost_f64(const double *box, int n_box
   return c;
 }
 
+// One sample per CTA: the batches of the reference's callers (1, H, a few hundred) leave SMs idle anyway.
 __global__ void __launch_bounds__(NT) pred_batch_kernel(const AmpcMlpF64 net, int batch, const double *X,
                                                         const double *U, double *Xn) {
   extern __shared__ double sm_d[];
@@ -54,6 +60,33 @@ __global__ void __launch_bounds__(NT) pred_batch_kernel(const AmpcMlpF64 net, in
   const double *out = ampc_mlp_f64_forward(net, h0, h1, nullptr, threadIdx.x, NT);
   for (int j = threadIdx.x; j < nx; j += NT)
     Xn[(size_t)s * nx + j] = X[(size_t)s * nx + j] + (out[j] * net.dy_std[j] + net.dy_mean[j]);
+}
+
+// Batches beyond one wave of one-sample CTAs (ampc_mlp_blocked): a CTA owns AMPC_MLP_SB consecutive samples
+// (mlp_f64.cuh: ampc_mlp_f64_forward_blocked), so the 1.1 MB of float64 weights is read from L2 once per eight samples
+// instead of once per sample; same arithmetic per sample, bit-identical results (4.57 -> 1.91 ms at batch 65536, C3 net).
+__global__ void __launch_bounds__(NT) pred_batch_blocked_kernel(const AmpcMlpF64 net, int batch, const double *X,
+                                                                const double *U, double *Xn) {
+  extern __shared__ double sm_d[];
+  constexpr int SB = AMPC_MLP_SB;
+  const int s0 = blockIdx.x * SB;
+  const int nx = net.nx, nu = net.nu, nin = nx + nu, W = net.max_width;
+  double *h0 = sm_d, *h1 = sm_d + SB * W;
+  for (int t = threadIdx.x; t < SB * nin; t += NT) {
+    const int q = t / nin, j = t - q * nin, s = s0 + q;
+    double z = 0.0;
+    if (s < batch) {
+      const double v = j < nx ? X[(size_t)s * nx + j] : U[(size_t)s * nu + (j - nx)];
+      z = (v - net.xu_mean[j]) / net.xu_std[j];
+    }
+    h0[q * W + j] = z;
+  }
+  __syncthreads();
+  const double *out = ampc_mlp_f64_forward_blocked(net, h0, h1, W, threadIdx.x, NT);
+  for (int t = threadIdx.x; t < SB * nx; t += NT) {
+    const int q = t / nx, j = t - q * nx, s = s0 + q;
+    if (s < batch) Xn[(size_t)s * nx + j] = X[(size_t)s * nx + j] + (out[q * W + j] * net.dy_std[j] + net.dy_mean[j]);
+  }
 }
 
 __global__ void __launch_bounds__(NTJ) pred_diff_kernel(const AmpcMlpF64 net, int batch, const double *X,
@@ -142,6 +175,43 @@ __global__ void __launch_bounds__(NT) rollout_batch_kernel(const AmpcMlpF64 net,
     __syncthreads();
   }
   for (int j = threadIdx.x; j < nx; j += NT) Xh[(size_t)s * nx + j] = x[j];
+}
+
+// sample-blocked form (see pred_batch_blocked_kernel): 13.4 -> 7.1 ms at batch 8192, horizon 20
+__global__ void __launch_bounds__(NT) rollout_batch_blocked_kernel(const AmpcMlpF64 net, int batch, int horizon,
+                                                                   const double *X0, const double *U, double *Xh) {
+  extern __shared__ double sm_d[];
+  constexpr int SB = AMPC_MLP_SB;
+  const int s0 = blockIdx.x * SB;
+  const int nx = net.nx, nu = net.nu, nin = nx + nu, W = net.max_width;
+  double *h0 = sm_d, *h1 = h0 + SB * W, *x = h1 + SB * W;   // x: [SB][nx]
+  for (int t = threadIdx.x; t < SB * nx; t += NT) {
+    const int q = t / nx, j = t - q * nx, s = s0 + q;
+    x[t] = s < batch ? X0[(size_t)s * nx + j] : 0.0;
+  }
+  __syncthreads();
+  for (int k = 0; k < horizon; ++k) {
+    for (int t = threadIdx.x; t < SB * nin; t += NT) {
+      const int q = t / nin, j = t - q * nin, s = s0 + q;
+      double z = 0.0;
+      if (s < batch) {
+        const double v = j < nx ? x[q * nx + j] : U[((size_t)k * batch + s) * nu + (j - nx)];
+        z = (v - net.xu_mean[j]) / net.xu_std[j];
+      }
+      h0[q * W + j] = z;
+    }
+    __syncthreads();
+    const double *out = ampc_mlp_f64_forward_blocked(net, h0, h1, W, threadIdx.x, NT);
+    for (int t = threadIdx.x; t < SB * nx; t += NT) {
+      const int q = t / nx, j = t - q * nx;
+      x[t] = x[t] + (out[q * W + j] * net.dy_std[j] + net.dy_mean[j]);
+    }
+    __syncthreads();
+  }
+  for (int t = threadIdx.x; t < SB * nx; t += NT) {
+    const int q = t / nx, j = t - q * nx, s = s0 + q;
+    if (s < batch) Xh[(size_t)s * nx + j] = x[t];
+  }
 }
 
 // One closed-loop plant step on the device: x <- sim.pred(x, u) (mlp.py:219-227, float64), plus the float32 copy the
@@ -286,7 +356,8 @@ extern "C" int ampc_mlp_create(ampc_mlp **out, const ampc_mlp_desc *mlp, int32_t
   m->device = device;
   int rc = ampc_mlp_f64_upload(mlp, nx, nu, &m->net, &m->d_blob);
   if (rc) { delete m; return rc; }
-  m->smem_pred = 2 * (size_t)m->net.max_width * sizeof(double);
+  m->smem_pred = 2 * (size_t)m->net.max_width * sizeof(double);                     // one sample (sim_step_kernel)
+  m->smem_batch = 2 * (size_t)AMPC_MLP_SB * m->net.max_width * sizeof(double);      // AMPC_MLP_SB samples per CTA
   m->smem_diff = (3 * (size_t)m->net.max_width + 2 * (size_t)m->net.max_width * (nx + nu)) * sizeof(double);
   cudaError_t e = ampc_raise_smem_limit((const void *)pred_diff_kernel, m->smem_diff);
   if (e == cudaSuccess) e = ampc_raise_smem_limit((const void *)nmpc_knot_kernel<true>, m->smem_diff);
@@ -305,8 +376,43 @@ extern "C" int ampc_mlp_destroy(ampc_mlp *m) {
   if (!m) return AMPC_OK;
   cudaSetDevice(m->device);
   cudaFree(m->d_blob);
+  cudaFree(m->d_scratch);
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
   delete m;
   return AMPC_OK;
+}
+
+// Device staging of `n` doubles on the handle; grown (never shrunk) when a call needs more.
+static int mlp_scratch(ampc_mlp *m, size_t n, double **out) {
+  if (n > m->scratch_doubles) {
+    cudaFree(m->d_scratch);
+    m->d_scratch = nullptr;
+    m->scratch_doubles = 0;
+    AMPC_CUDA_CHECK(cudaMalloc(&m->d_scratch, n * sizeof(double)));
+    m->scratch_doubles = n;
+  }
+  if (!m->ev0) {
+    AMPC_CUDA_CHECK(cudaEventCreate(&m->ev0));
+    AMPC_CUDA_CHECK(cudaEventCreate(&m->ev1));
+  }
+  *out = m->d_scratch;
+  return AMPC_OK;
+}
+
+extern "C" int ampc_mlp_debug_last_kernel_ms(ampc_mlp *m, float *ms) {
+  AMPC_REQUIRE(m && ms && m->ev0, AMPC_ERR_INVALID, "no launch recorded on this handle");
+  AMPC_CUDA_CHECK(cudaSetDevice(m->device));
+  AMPC_CUDA_CHECK(cudaEventElapsedTime(ms, m->ev0, m->ev1));
+  return AMPC_OK;
+}
+
+// Sample-blocked kernels once the one-sample CTAs would no longer fit in one wave (8 CTAs of NT threads on each of the
+// 148 SMs); below that the one-sample grid has more parallelism (kernel 0.126 vs 0.146 ms at batch 512; 0.625 vs 0.337 at 8192).
+// AMPC_MLP_BLOCKED=0|1 forces one or the other (tests run both on the same inputs).
+static bool ampc_mlp_blocked(int batch) {
+  if (const char *f = getenv("AMPC_MLP_BLOCKED")) return f[0] == '1';
+  return batch > 148 * 8;
 }
 
 static int run_mlp(ampc_mlp *m, int batch, const double *X, const double *U, double *Xn, double *Jx, double *Ju) {
@@ -317,20 +423,23 @@ static int run_mlp(ampc_mlp *m, int batch, const double *X, const double *U, dou
   const size_t nX = (size_t)batch * nx, nU = (size_t)batch * nu;
   const size_t nJx = Jx ? nX * nx : 0, nJu = Jx ? nX * nu : 0;
   double *d = nullptr;
-  AMPC_CUDA_CHECK(cudaMalloc(&d, (2 * nX + nU + nJx + nJu) * sizeof(double)));
+  if (int rc = mlp_scratch(m, 2 * nX + nU + nJx + nJu, &d)) return rc;
   double *dX = d, *dU = dX + nX, *dXn = dU + nU, *dJx = dXn + nX, *dJu = dJx + nJx;
   cudaError_t e = cudaMemcpy(dX, X, nX * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(dU, U, nU * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
+    cudaEventRecord(m->ev0);
     if (Jx) pred_diff_kernel<<<batch, NTJ, m->smem_diff>>>(m->net, batch, dX, dU, dXn, dJx, dJu);
+    else if (ampc_mlp_blocked(batch))
+      pred_batch_blocked_kernel<<<(batch + AMPC_MLP_SB - 1) / AMPC_MLP_SB, NT, m->smem_batch>>>(m->net, batch, dX, dU, dXn);
     else pred_batch_kernel<<<batch, NT, m->smem_pred>>>(m->net, batch, dX, dU, dXn);
+    cudaEventRecord(m->ev1);
     ampc_count_launch();
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(Xn, dXn, nX * sizeof(double), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && Jx) e = cudaMemcpy(Jx, dJx, nJx * sizeof(double), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && Jx) e = cudaMemcpy(Ju, dJu, nJu * sizeof(double), cudaMemcpyDeviceToHost);
-  cudaFree(d);
   AMPC_CUDA_CHECK(e);
   return AMPC_OK;
 }
@@ -353,17 +462,23 @@ extern "C" int ampc_mlp_rollout_batch(ampc_mlp *m, int32_t batch, int32_t horizo
   const int nx = m->net.nx, nu = m->net.nu;
   const size_t nX = (size_t)batch * nx, nU = (size_t)horizon * batch * nu;
   double *d = nullptr;
-  AMPC_CUDA_CHECK(cudaMalloc(&d, (2 * nX + nU) * sizeof(double)));
+  if (int rc = mlp_scratch(m, 2 * nX + nU, &d)) return rc;
   double *dX = d, *dU = dX + nX, *dXh = dU + nU;
   cudaError_t e = cudaMemcpy(dX, X0, nX * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(dU, U, nU * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    rollout_batch_kernel<<<batch, NT, m->smem_pred + nx * sizeof(double)>>>(m->net, batch, horizon, dX, dU, dXh);
+    cudaEventRecord(m->ev0);
+    if (ampc_mlp_blocked(batch))
+      rollout_batch_blocked_kernel<<<(batch + AMPC_MLP_SB - 1) / AMPC_MLP_SB, NT,
+                                     m->smem_batch + (size_t)AMPC_MLP_SB * nx * sizeof(double)>>>(m->net, batch, horizon, dX,
+                                                                                                  dU, dXh);
+    else
+      rollout_batch_kernel<<<batch, NT, m->smem_pred + nx * sizeof(double)>>>(m->net, batch, horizon, dX, dU, dXh);
+    cudaEventRecord(m->ev1);
     ampc_count_launch();
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(Xh, dXh, nX * sizeof(double), cudaMemcpyDeviceToHost);
-  cudaFree(d);
   AMPC_CUDA_CHECK(e);
   return AMPC_OK;
 }
@@ -375,16 +490,17 @@ static int run_nmpc(ampc_mlp *m, int32_t H, const double *x, double *out, bool j
   const size_t n_in = (size_t)(H + 1) * nx + (size_t)H * nu;
   const size_t n_out = jac ? (size_t)H * (nx * nx + nx * nu + nx) : (size_t)H * nx;
   double *d = nullptr;
-  AMPC_CUDA_CHECK(cudaMalloc(&d, (n_in + n_out) * sizeof(double)));
+  if (int rc = mlp_scratch(m, n_in + n_out, &d)) return rc;
   cudaError_t e = cudaMemcpy(d, x, n_in * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
+    cudaEventRecord(m->ev0);
     if (jac) nmpc_knot_kernel<true><<<H, NTJ, m->smem_diff>>>(m->net, H, d, d + n_in);
     else nmpc_knot_kernel<false><<<H, NTJ, m->smem_diff>>>(m->net, H, d, d + n_in);
+    cudaEventRecord(m->ev1);
     ampc_count_launch();
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(out, d + n_in, n_out * sizeof(double), cudaMemcpyDeviceToHost);
-  cudaFree(d);
   AMPC_CUDA_CHECK(e);
   return AMPC_OK;
 }

@@ -202,6 +202,9 @@ int ampc_mlp_pred_diff_batch(ampc_mlp *m, int32_t batch, const double *X, const 
  *               get_jacobian(x, True) (nmpc.py:148-169) is index arithmetic and stays on the host.                */
 int ampc_mlp_nmpc_constraint(ampc_mlp *m, int32_t H, const double *x, double *c);
 int ampc_mlp_nmpc_jacobian(ampc_mlp *m, int32_t H, const double *x, double *jac);
+/* Measurement tap: device time (CUDA events) of the kernel the last call above launched on this handle, without the
+ * host <-> device copies around it.  No reference counterpart. */
+int ampc_mlp_debug_last_kernel_ms(ampc_mlp *m, float *ms);
 
 /* ------------------------------------------------------- linear models --- */
 /* Replaces ARX.pred / pred_batch (autompc/sysid/arx.py:146-154) and Koopman.pred / pred_batch

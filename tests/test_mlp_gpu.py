@@ -56,6 +56,34 @@ def test_mlp_kernels_match_oracle_large(act):
         np.testing.assert_allclose(ju, rju, rtol=0, atol=1e-11)
 
 
+@pytest.mark.parametrize("dims", [(17, 6, [256, 256, 256], "relu"), (4, 1, [64, 64], "tanh"), (5, 2, [33], "sigmoid")])
+def test_sample_blocked_kernels_equal_one_sample_kernels(dims, monkeypatch):
+    """pred_batch / k-step rollouts: the eight-samples-per-CTA kernels (batches beyond one wave) and the
+    one-sample-per-CTA kernels do the same arithmetic per sample -> identical bits, and both meet the oracle.
+    Batch sizes: one sample, a ragged last CTA, the dispatch threshold's two sides."""
+    nx, nu, hidden, act = dims
+    p = synthetic_mlp(nx, nu, hidden, act=act, seed=11)
+    m = _model(p)
+    rng = np.random.default_rng(3)
+    for batch in (1, 7, 8, 9, 1184, 1185, 2051):
+        X, U = rng.normal(size=(batch, nx)), 0.3 * rng.normal(size=(3, batch, nu))
+        got = {}
+        for forced in ("0", "1", None):
+            if forced is None:
+                monkeypatch.delenv("AMPC_MLP_BLOCKED", raising=False)
+            else:
+                monkeypatch.setenv("AMPC_MLP_BLOCKED", forced)
+            got[forced] = (m.pred_batch(X, U[0]), m.rollout_batch(X, U))
+        for forced in ("1", None):
+            np.testing.assert_array_equal(got[forced][0], got["0"][0])
+            np.testing.assert_array_equal(got[forced][1], got["0"][1])
+        np.testing.assert_allclose(got["1"][0], mlp_pred_batch(p, X, U[0]), rtol=0, atol=1e-12)
+        chained = X
+        for k in range(3):
+            chained = mlp_pred_batch(p, chained, U[k])
+        np.testing.assert_allclose(got["1"][1], chained, rtol=0, atol=1e-11)
+
+
 def test_mlp_parameter_round_trip_and_errors():
     p = synthetic_mlp(4, 1, [64, 64], seed=8)
     m = _model(p)
