@@ -15,6 +15,8 @@
 struct ampc_linear {
   int ns = 0, nu = 0, device = 0;
   double *d_At = nullptr;   // [ns + nu][ns]: rows 0..ns-1 = A^T, rows ns.. = B^T
+  double *d_scratch = nullptr;   // grow-only staging of X | U | Xn (no cudaMalloc per call)
+  size_t scratch_doubles = 0;
 };
 
 namespace {
@@ -83,6 +85,7 @@ extern "C" int ampc_linear_destroy(ampc_linear *h) {
   if (!h) return AMPC_OK;
   cudaSetDevice(h->device);
   cudaFree(h->d_At);
+  cudaFree(h->d_scratch);
   delete h;
   return AMPC_OK;
 }
@@ -92,8 +95,14 @@ extern "C" int ampc_linear_pred_batch(ampc_linear *h, int32_t batch, const doubl
   if (batch == 0) return AMPC_OK;
   AMPC_CUDA_CHECK(cudaSetDevice(h->device));
   const size_t nX = (size_t)batch * h->ns, nU = (size_t)batch * h->nu;
-  double *d = nullptr;
-  AMPC_CUDA_CHECK(cudaMalloc(&d, (2 * nX + nU) * sizeof(double)));
+  if (2 * nX + nU > h->scratch_doubles) {
+    cudaFree(h->d_scratch);
+    h->d_scratch = nullptr;
+    h->scratch_doubles = 0;
+    AMPC_CUDA_CHECK(cudaMalloc(&h->d_scratch, (2 * nX + nU) * sizeof(double)));
+    h->scratch_doubles = 2 * nX + nU;
+  }
+  double *d = h->d_scratch;
   double *dX = d, *dU = dX + nX, *dXn = dU + nU;
   cudaError_t e = cudaMemcpy(dX, X, nX * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(dU, U, nU * sizeof(double), cudaMemcpyHostToDevice);
@@ -104,7 +113,6 @@ extern "C" int ampc_linear_pred_batch(ampc_linear *h, int32_t batch, const doubl
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(Xn, dXn, nX * sizeof(double), cudaMemcpyDeviceToHost);
-  cudaFree(d);
   AMPC_CUDA_CHECK(e);
   return AMPC_OK;
 }

@@ -127,25 +127,53 @@ __device__ __forceinline__ const double *ampc_mlp_f64_forward_jac_batch(const Am
       g[(size_t)s * hstride + j] = last ? 1.0 : ampc_act_grad<double>(net.act, y);
     }
     __syncthreads();
-    const int per = N * nin;
-    for (int t = tid; t < m * per; t += nthr) {
-      const int s = t / per, r = t - s * per;
-      const int c = r / N, j = r - c * N;   // j fastest: coalesced weight reads
-      const double *jp = Jp + (size_t)s * jstride;
-      double v;
-      if (l == 0) {
-        v = __ldg(net.Wt[0] + (size_t)c * N + j) / __ldg(net.xu_std + c);
-      } else {
-        double p0 = 0.0, p1 = 0.0;
+    if (l == 0) {
+      const int per = N * nin;
+      for (int t = tid; t < m * per; t += nthr) {
+        const int s = t / per, r = t - s * per;
+        const int c = r / N, j = r - c * N;   // j fastest: coalesced weight reads
+        const double v = __ldg(net.Wt[0] + (size_t)c * N + j) / __ldg(net.xu_std + c);
+        Jn[(size_t)s * jstride + (size_t)j * nin + c] = v * g[(size_t)s * hstride + j];
+      }
+    } else {
+      // J_l[j][c] = g[j] * sum_k W_l[k][j] J_{l-1}[k][c]: a thread owns output neuron j for FOUR input columns, so a
+      // weight read feeds four multiply-adds and eight accumulators are in flight (even / odd k per column -- the
+      // summation order per element is the one-column loop's: sum over even k, sum over odd k, tail into the even one,
+      // even + odd).  A ragged last group recomputes the last column and drops the duplicates at the store.
+      constexpr int CB = 4;
+      const int ncg = (nin + CB - 1) / CB, per = N * ncg;
+      const double *__restrict__ Wt = net.Wt[l];
+      for (int t = tid; t < m * per; t += nthr) {
+        const int s = t / per, r = t - s * per;
+        const int cg = r / N, j = r - cg * N;   // j fastest: coalesced weight reads, broadcast panel reads
+        const double *jp = Jp + (size_t)s * jstride;
+        int cq[CB];
+#pragma unroll
+        for (int q = 0; q < CB; ++q) cq[q] = min(cg * CB + q, nin - 1);
+        double p0[CB], p1[CB];
+#pragma unroll
+        for (int q = 0; q < CB; ++q) p0[q] = p1[q] = 0.0;
         int k = 0;
         for (; k + 2 <= Kin; k += 2) {
-          p0 = fma(__ldg(net.Wt[l] + (size_t)k * N + j), jp[(size_t)k * nin + c], p0);
-          p1 = fma(__ldg(net.Wt[l] + (size_t)(k + 1) * N + j), jp[(size_t)(k + 1) * nin + c], p1);
+          const double w0 = __ldg(Wt + (size_t)k * N + j), w1 = __ldg(Wt + (size_t)(k + 1) * N + j);
+          const double *r0 = jp + (size_t)k * nin, *r1 = r0 + nin;
+#pragma unroll
+          for (int q = 0; q < CB; ++q) {
+            p0[q] = fma(w0, r0[cq[q]], p0[q]);
+            p1[q] = fma(w1, r1[cq[q]], p1[q]);
+          }
         }
-        if (k < Kin) p0 = fma(__ldg(net.Wt[l] + (size_t)k * N + j), jp[(size_t)k * nin + c], p0);
-        v = p0 + p1;
+        if (k < Kin) {
+          const double w0 = __ldg(Wt + (size_t)k * N + j);
+#pragma unroll
+          for (int q = 0; q < CB; ++q) p0[q] = fma(w0, jp[(size_t)k * nin + cq[q]], p0[q]);
+        }
+        const double gj = g[(size_t)s * hstride + j];
+        double *o = Jn + (size_t)s * jstride + (size_t)j * nin;
+#pragma unroll
+        for (int q = 0; q < CB; ++q)
+          if (cg * CB + q < nin) o[cg * CB + q] = (p0[q] + p1[q]) * gj;
       }
-      Jn[(size_t)s * jstride + (size_t)j * nin + c] = v * g[(size_t)s * hstride + j];
     }
     __syncthreads();
     double *t2 = hin; hin = hout; hout = t2;

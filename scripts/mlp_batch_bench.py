@@ -33,3 +33,20 @@ for batch, horizon in ((1, 1), (512, 1), (8192, 1), (65536, 1), (512, 20), (8192
     k = float(np.median(kms)) if kms else float("nan")
     print("batch %6d horizon %2d: %9.3f ms per call, kernel %8.4f ms = %6.2f TFLOP/s fp64  checksum %.17g"
           % (batch, horizon, dt * 1e3, k, fl / (k * 1e-3) / 1e12, float(np.sum(out))))
+
+# Jacobian kernels (one sample / knot per CTA): pred_diff_batch and the direct-transcription callbacks at batch H
+for batch in (1, 7, 50, 400):
+    X = rng.normal(size=(batch, 17)); U = 0.3 * rng.normal(size=(batch, 6))
+    m.pred_diff_batch(X, U)
+    kms, ms = [], ctypes.c_float()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        xn, jx, ju = m.pred_diff_batch(X, U)
+        if hasattr(_abi.lib(), "ampc_mlp_debug_last_kernel_ms"):
+            _abi.check(_abi.lib().ampc_mlp_debug_last_kernel_ms(m._h, ctypes.byref(ms)))
+            kms.append(ms.value)
+    dt = (time.perf_counter() - t0) / 10
+    fl = 2.0 * (141312 + 23 * (256 * 256 * 2 + 256 * 17)) * batch
+    k = float(np.median(kms)) if kms else float("nan")
+    print("pred_diff_batch %4d: %9.3f ms per call, kernel %8.4f ms = %6.2f TFLOP/s fp64  checksum %.17g"
+          % (batch, dt * 1e3, k, fl / (k * 1e-3) / 1e12, float(np.sum(jx) + np.sum(ju))))

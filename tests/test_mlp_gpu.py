@@ -84,6 +84,24 @@ def test_sample_blocked_kernels_equal_one_sample_kernels(dims, monkeypatch):
         np.testing.assert_allclose(got["1"][1], chained, rtol=0, atol=1e-11)
 
 
+@pytest.mark.parametrize("dims", [(5, 2, [33, 17], "tanh"), (3, 1, [7], "relu"), (9, 4, [64, 31, 50, 12], "selu"),
+                                  (32, 20, [256, 128], "sigmoid")])
+def test_jacobian_kernels_odd_widths_and_ragged_column_groups(dims):
+    """Forward-mode Jacobians with odd layer widths (the even / odd-k partial sums' tail) and input widths that are
+    not a multiple of the four-column groups a thread owns (nin = 7, 4, 13, 52)."""
+    nx, nu, hidden, act = dims
+    p = synthetic_mlp(nx, nu, hidden, act=act, seed=21)
+    m = _model(p)
+    rng = np.random.default_rng(5)
+    for batch in (1, 6):
+        X, U = rng.normal(size=(batch, nx)), rng.normal(size=(batch, nu))
+        xn, jx, ju = m.pred_diff_batch(X, U)
+        rxn, rjx, rju = mlp_pred_diff_batch(p, X, U)
+        np.testing.assert_allclose(xn, rxn, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(jx, rjx, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(ju, rju, rtol=0, atol=1e-11)
+
+
 def test_mlp_parameter_round_trip_and_errors():
     p = synthetic_mlp(4, 1, [64, 64], seed=8)
     m = _model(p)
