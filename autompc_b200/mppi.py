@@ -18,9 +18,10 @@ Engine-only keyword arguments (all optional):
                softmax) | ``"auto"`` (default: fp16 when the shape and the weight range
                allow it, else bf16, else fp32).  The reference computes in float64
                (``autompc/sysid/mlp.py:165``); measured deviation of the updated,
-               normalised action sequence from it at the C3 configuration: fp32 ~1e-4,
-               fp16 ~1e-3 (11-bit significands = the operand precision of tf32),
-               bf16 ~1e-2.  Ask for ``"fp32"`` when parity matters more than speed.
+               normalised action sequence from it at the C3 configuration: fp32 1e-5,
+               fp16 2.3e-4 (11-bit significands = the operand precision of tf32),
+               bf16 3.4e-3; worst parity case 1.2e-3 / 1.1e-2 (tests state 2e-3 / 2e-2).
+               Ask for ``"fp32"`` when parity matters more than speed.
 ``terminal``   ``"reference"`` (default: last sample's terminal cost added to
                all samples, ``mppi.py:79-82``) or ``"per_sample"``.
 ``device``     CUDA ordinal.
