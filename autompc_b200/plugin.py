@@ -232,6 +232,8 @@ except Exception:  # pragma: no cover
             self.system = system
             self._ctrl_bounds = np.zeros((system.ctrl_dim, 2))
             self._ctrl_bounds[:, 0], self._ctrl_bounds[:, 1] = -np.inf, np.inf
+            self._obs_bounds = np.zeros((system.obs_dim, 2))            # tasks/task.py:21-24
+            self._obs_bounds[:, 0], self._obs_bounds[:, 1] = -np.inf, np.inf
             self._init_obs = None
             self._num_steps = None
 
@@ -240,6 +242,19 @@ except Exception:  # pragma: no cover
 
         def get_cost(self):
             return self.cost
+
+        def set_obs_bound(self, obs_label, lower, upper):       # tasks/task.py:149-165
+            i = self.system.observations.index(obs_label)
+            self._obs_bounds[i, :] = [lower, upper]
+
+        def set_obs_bounds(self, lowers, uppers):               # tasks/task.py:167-180
+            self._obs_bounds[:, 0], self._obs_bounds[:, 1] = lowers, uppers
+
+        def get_obs_bounds(self):                               # tasks/task.py:245-255
+            return self._obs_bounds.copy()
+
+        def are_obs_bounded(self):                              # tasks/task.py:215-228
+            return bool(np.any(self._obs_bounds[:, 0] != -np.inf) or np.any(self._obs_bounds[:, 1] != np.inf))
 
         def set_ctrl_bound(self, ctrl_label, lower, upper):
             i = self.system.controls.index(ctrl_label)
