@@ -9,6 +9,8 @@ What runs, in a subprocess (so that ``autompc_b200.plugin`` binds to the referen
   controller through the reference's ``ControllerFactory.__call__`` (controller.py:30-33);
 * ``autompc.utils.simulation.simulate(controller, init_obs, sim_model=model, max_steps=T)`` (simulation.py:11-64)
   driving ``controller.traj_to_state`` / ``run``;
+* ``get_configuration_space()`` of ``MPPIFactory`` and ``IterativeLQRFactory`` against the reference factories'
+  (names, types, ranges, defaults), and the iLQR factory's sorting into the reference ``Pipeline``;
 * the same closed loop with the reference's OWN ``autompc.control.mppi.MPPI`` built by the same pipeline recipe, from
   the same NumPy seed: the two trajectories must agree (the engine draws the noise in the reference's order,
   mppi.py:99, :126).
@@ -101,6 +103,21 @@ np.random.seed(7)
 with ref_loader.quiet():
     ctl_r.reset()
 np.testing.assert_allclose(a, ctl_r.act_sequence, rtol=0, atol=1e-7)
+
+# ---- both factories declare the reference's hyper-parameters: same names, types, ranges and defaults
+# (mppi.py:26-64, ilqr.py:36-41), and the iLQR factory sorts into the reference pipeline as a controller factory
+RefILQRFactory = importlib.import_module("autompc.control.ilqr").IterativeLQRFactory
+def hp_table(cs):
+    return sorted((h.name, type(h).__name__, h.lower, h.upper, h.default_value) for h in cs.get_hyperparameters())
+assert hp_table(autompc_b200.MPPIFactory(system).get_configuration_space()) == \
+    hp_table(RefMPPIFactory(system).get_configuration_space())
+assert hp_table(autompc_b200.IterativeLQRFactory(system).get_configuration_space()) == \
+    hp_table(RefILQRFactory(system).get_configuration_space())
+pipe_i = Pipeline(system, model, QuadCostFactory(system), autompc_b200.IterativeLQRFactory(system))
+pipe_ir = Pipeline(system, model, QuadCostFactory(system), RefILQRFactory(system))
+assert isinstance(pipe_i.controller_factory, autompc_b200.IterativeLQRFactory)
+assert sorted(pipe_i.get_configuration_space().get_hyperparameter_names()) == \
+    sorted(pipe_ir.get_configuration_space().get_hyperparameter_names())
 print("dropin ok", float(np.abs(traj.obs - traj_r.obs).max()))
 '''
 
