@@ -126,3 +126,67 @@ print("dropin ok", float(np.abs(traj.obs - traj_r.obs).max()))
 def test_engine_controller_under_reference_pipeline_and_simulate():
     out = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], capture_output=True, text=True, cwd=ROOT)
     assert out.returncode == 0 and "dropin ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+LINEAR_SCRIPT = r'''
+import sys, os
+sys.path.insert(0, %(root)r)
+import numpy as np
+from oracle import ref_loader
+from oracle.make_golden import gen_trajs, make_cartpole
+from oracle.make_golden_r2 import load_extra
+ns = load_extra(ref_loader.load())
+import autompc_b200
+from autompc_b200 import plugin
+assert plugin.HAVE_AUTOMPC
+system, task = make_cartpole(ns)
+trajs = gen_trajs(ns, system, 8, 60, seed=9)
+with ref_loader.quiet():
+    arx = ns.ARX(system, history=3)
+    arx.train(trajs)
+    # (the reference only sets `product_terms` when it arrives as a string, koopman.py:98-99)
+    koop = ns.Koopman(system, method="lstsq", poly_basis=True, poly_degree=3, product_terms="false")
+    koop.train(trajs)
+z = np.load(os.path.join(%(root)r, "tests", "golden", "linear_models.npz"))
+assert np.array_equal(arx.A, z["arx_A"]) and np.array_equal(arx.B, z["arx_B"])   # the fixture's model, trained again
+for ref in (arx, koop):
+    m = autompc_b200.B200Linear.from_model(ref)
+    assert isinstance(m, ns.Model) and m.base is ref and m.state_dim == ref.state_dim
+    A, B = ref.to_linear()
+    assert np.array_equal(m.A, A) and np.array_equal(m.B, B) and m.A.flags.c_contiguous
+    for cut in (1, 2, 7, 30):                                  # shorter than the history, equal, longer
+        np.testing.assert_array_equal(m.traj_to_state(trajs[1][:cut]), ref.traj_to_state(trajs[1][:cut]))
+    st = ref.traj_to_state(trajs[0][:7])
+    np.testing.assert_array_equal(m.update_state(st, trajs[0][6].ctrl, trajs[0][7].obs),
+                                  ref.update_state(st, trajs[0][6].ctrl, trajs[0][7].obs))
+    pa, pb = m.get_parameters()["A"], m.get_parameters()["B"]
+    assert np.array_equal(pa, A) and np.array_equal(pb, B)
+    # the direct-transcription problem on the model's (stacked / lifted) state: sizes and bounds as the reference's
+    task.set_obs_bound("theta", -3.0, 3.5)
+    prob = autompc_b200.NonLinearMPCProblem(system, m, task, 5)
+    with ref_loader.quiet():
+        np.random.seed(0)
+        prob_r = ns.NonLinearMPCProblem(system, ref, task, 5)
+    assert (prob.dimx, prob.dimc, prob.nnz) == (prob_r.dimx, prob_r.dimc, prob_r.nnz)
+    for a, b in zip(prob.get_variable_bounds(), prob_r.get_variable_bounds()):
+        assert np.array_equal(a, b)
+    r, c = prob.get_jacobian(None, True)
+    rr, cr = prob_r.get_jacobian(prob_r._x, True)
+    assert np.array_equal(r, rr) and np.array_equal(c, cr)
+    x = np.random.default_rng(1).normal(size=prob.dimx)
+    np.testing.assert_allclose(prob.get_cost(x), prob_r.get_cost(x), rtol=1e-12)
+    np.testing.assert_allclose(prob.get_gradient(x), prob_r.get_gradient(x), rtol=1e-12, atol=1e-13)
+    # constant Jacobian values of a linear model, in the reference's sparse order (nmpc.py:170-187)
+    np.testing.assert_array_equal(prob.get_jacobian(x, False), prob_r.get_jacobian(x, False))
+print("linear ok")
+'''
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree only exists in the build container")
+def test_linear_models_and_transcription_host_side_under_reference_objects():
+    """``B200Linear.from_model(<reference ARX / Koopman>)``: matrices, ``traj_to_state`` / ``update_state`` (history
+    stacking, basis lifting: arx.py:64-103, koopman.py:100-118) and the direct-transcription problem's sizes, bounds,
+    pattern, cost, gradient and (constant) Jacobian values built on it, against the live unmodified reference objects.
+    Host code only: ``pred_batch`` on the device is tests/test_linear_nmpc_gpu.py's."""
+    out = subprocess.run([sys.executable, "-c", LINEAR_SCRIPT % {"root": ROOT}], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0 and "linear ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
