@@ -1,0 +1,72 @@
+"""BASELINE.md section 3, rows (i) / (ii) for the configurations the UNMODIFIED reference can run (ctrl_dim = 1):
+its own ``MPPI.run`` (autompc/control/mppi.py:154-168, ``MLP.pred_batch`` on torch CPU float64, Python loop over the K
+samples in ``cost_eqn``) timed in the BUILD CONTAINER (the reference tree does not exist on the GPU box), next to the
+float64 NumPy port that ``bench.py`` times as ``cpu_baseline`` on the GPU box -- so that the port can be related to the
+real thing on one host.  C1 = cartpole K=256 H=20, C2 = cartpole K=4096 H=30, the trained cartpole MLP 2x64.
+
+    python scripts/reference_cpu_timing.py > profiles/r02c_reference_cpu_c1_c2.json
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import bench
+from oracle import ref_loader
+from oracle.make_golden import CART_X0, make_cartpole
+from oracle.make_golden_f import reference_mlp_from_npz
+
+
+def time_reference(ns, system, task, mlp, K, H, threads, n_warm, n_steps):
+    torch.set_num_threads(threads)
+    np.random.seed(0)
+    with ref_loader.quiet():
+        ctl = ns.MPPI(system, task, mlp, horizon=H, num_path=K, sigma=1.0, lmda=1.0)
+        x = CART_X0.copy()
+        constate = np.concatenate([x, np.zeros(1)])
+        ts = []
+        for i in range(n_warm + n_steps):
+            t0 = time.perf_counter()
+            u, constate = ctl.run(constate, x)
+            ts.append(time.perf_counter() - t0)
+    ts = np.array(ts[n_warm:])
+    return {"ms_per_step_mean": 1e3 * float(ts.mean()), "ms_per_step_median": 1e3 * float(np.median(ts)),
+            "steps_per_s": float(1.0 / ts.mean()), "steps_timed": int(n_steps), "warmup": int(n_warm),
+            "torch_threads": int(threads)}
+
+
+def main():
+    ns = ref_loader.load()
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cartpole_mlp.npz"))
+    system, task = make_cartpole(ns)
+    mlp = reference_mlp_from_npz(ns, system, z)
+    ncpu = os.cpu_count() or 1
+    out = {"host": bench.cpu_info(), "torch": torch.__version__, "numpy": np.__version__,
+           "what": "unmodified reference autompc.control.mppi.MPPI.run vs the float64 NumPy port (oracle/mppi_oracle.py), "
+                   "same host, trained cartpole MLP[5-64-64-4], QuadCost of examples/3_Controllers_and_Tasks.ipynb cell 6",
+           "configs": []}
+    for name, K, H, n_warm, n_steps in (("C1", 256, 20, 5, 40), ("C2", 4096, 30, 1, 5)):
+        rows = []
+        for threads in (1, ncpu):
+            r = time_reference(ns, system, task, mlp, K, H, threads, n_warm, n_steps)
+            r.update(variant="unmodified reference MPPI.run", kind="reference")
+            rows.append(r)
+        torch.set_num_threads(ncpu)
+        wl = bench.workload("c2")
+        wl.update(weights=bench.trained_cartpole_weights(), K=K, H=H)
+        for variant, threads, faithful in (("port, vectorised, all threads", None, False), ("port, vectorised, 1 thread", 1, False),
+                                           ("port, reference-faithful Python K-loop, 1 thread", 1, True)):
+            rate, cores, sample = bench.cpu_port_rate(wl, 6.0, threads=threads, faithful=faithful)
+            rows.append({"variant": variant, "kind": "port", "steps_per_s": rate, "ms_per_step_mean": 1e3 / rate,
+                         "cores": cores, "sample": sample})
+        out["configs"].append({"config": "%s cartpole MPPI K=%d H=%d" % (name, K, H), "rows": rows})
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
