@@ -4,7 +4,10 @@ samples in ``cost_eqn``) timed in the BUILD CONTAINER (the reference tree does n
 float64 NumPy port that ``bench.py`` times as ``cpu_baseline`` on the GPU box -- so that the port can be related to the
 real thing on one host.  C1 = cartpole K=256 H=20, C2 = cartpole K=4096 H=30, the trained cartpole MLP 2x64.
 
-    python scripts/reference_cpu_timing.py > profiles/r02c_reference_cpu_c1_c2.json
+C4 = cartpole IterativeLQR H=50 (``compute_ilqr_default``, autompc/control/ilqr.py:100-265) from the task's initial
+observation, next to the float64 NumPy port ``bench.py --workload c4`` reports.
+
+    python scripts/reference_cpu_timing.py > profiles/r02c_reference_cpu_c1_c2_c4.json
 """
 import json
 import os
@@ -65,6 +68,26 @@ def main():
             rows.append({"variant": variant, "kind": "port", "steps_per_s": rate, "ms_per_step_mean": 1e3 / rate,
                          "cores": cores, "sample": sample})
         out["configs"].append({"config": "%s cartpole MPPI K=%d H=%d" % (name, K, H), "rows": rows})
+    # --- C4: the unmodified reference's iLQR solve vs the port
+    wl = bench.workload("c4")
+    rows = []
+    for threads in (1, ncpu):
+        torch.set_num_threads(threads)
+        with ref_loader.quiet():
+            ctl = ns.IterativeLQR(system, task, mlp, horizon=wl["H"])
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                conv, states, ctrls, Ks, ks = ctl.compute_ilqr_default(CART_X0.copy(), np.zeros((wl["H"], 1)), silent=True)
+                ts.append(time.perf_counter() - t0)
+        rows.append({"variant": "unmodified reference compute_ilqr_default", "kind": "reference", "torch_threads": threads,
+                     "ms_per_step_mean": 1e3 * float(np.mean(ts[1:])), "steps_per_s": float(1.0 / np.mean(ts[1:])),
+                     "steps_timed": 2, "warmup": 1, "converged": bool(conv)})
+    torch.set_num_threads(ncpu)
+    rate, cores, sample = bench.cpu_ilqr_rate(wl, 6.0)
+    rows.append({"variant": "port, 1 thread", "kind": "port", "steps_per_s": rate, "ms_per_step_mean": 1e3 / rate,
+                 "cores": cores, "sample": sample})
+    out["configs"].append({"config": "C4 cartpole IterativeLQR H=50 (one solve = one step)", "rows": rows})
     print(json.dumps(out, indent=1))
 
 
