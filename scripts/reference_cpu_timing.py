@@ -7,7 +7,9 @@ real thing on one host.  C1 = cartpole K=256 H=20, C2 = cartpole K=4096 H=30, th
 C4 = cartpole IterativeLQR H=50 (``compute_ilqr_default``, autompc/control/ilqr.py:100-265) from the task's initial
 observation, next to the float64 NumPy port ``bench.py --workload c4`` reports.
 
-    python scripts/reference_cpu_timing.py > profiles/r02c_reference_cpu_c1_c2_c4.json
+C5 = the tuning batch on a bounded sample.
+
+    python scripts/reference_cpu_timing.py > profiles/r02c_reference_cpu.json
 """
 import json
 import os
@@ -88,6 +90,42 @@ def main():
     rows.append({"variant": "port, 1 thread", "kind": "port", "steps_per_s": rate, "ms_per_step_mean": 1e3 / rate,
                  "cores": cores, "sample": sample})
     out["configs"].append({"config": "C4 cartpole IterativeLQR H=50 (one solve = one step)", "rows": rows})
+    # --- C5: the tuner's inner loop (tuning/pipeline_tuner.py:213-239) on a bounded sample: the reference's own
+    # simulate() driving its own MPPI for the first candidates, 5 closed-loop steps each; scaled to the whole job by
+    # the share of sample-steps done (the same scaling as bench.cpu_c5_rate), next to that port
+    import importlib
+    with ref_loader.quiet():
+        simulate = importlib.import_module("autompc.utils.simulation").simulate
+    wl = bench.workload("c5")
+    cands, _ = bench.c5_candidates(wl)
+    work_total = float(sum(kw["num_path"] * kw["horizon"] for kw, _ in cands)) * wl["T"]
+    torch.set_num_threads(1)
+    work_done, steps, t0 = 0.0, 0, time.perf_counter()
+    for kw, etask in cands:
+        Q, R, F = etask.get_cost().get_cost_matrices()
+        rtask = ns.Task(system)
+        rtask.set_ctrl_bound("u", -20.0, 20.0)
+        rtask.set_cost(ns.QuadCost(system, Q, R, F, goal=np.zeros(4)))
+        np.random.seed(kw["seed"])
+        with ref_loader.quiet():
+            ctl = ns.MPPI(system, rtask, mlp, horizon=kw["horizon"], num_path=kw["num_path"], sigma=kw["sigma"],
+                          lmda=kw["lmda"])
+            simulate(ctl, CART_X0.copy(), sim_model=mlp, max_steps=5, silent=True)
+        steps += 5
+        work_done += 5.0 * kw["num_path"] * kw["horizon"]
+        if time.perf_counter() - t0 > 20.0:
+            break
+    dt = time.perf_counter() - t0
+    rows = [{"variant": "unmodified reference simulate() + MPPI.run", "kind": "reference", "torch_threads": 1,
+             "steps_per_s": (wl["n_cand"] * wl["T"]) / (dt * work_total / work_done),
+             "ms_per_step_mean": 1e3 * (dt * work_total / work_done) / (wl["n_cand"] * wl["T"]),
+             "sample": "%d closed-loop steps (5 per candidate) in %.1f s = %.4g of the job's sample-steps"
+                       % (steps, dt, work_done / work_total)}]
+    torch.set_num_threads(ncpu)
+    rate, cores, sample = bench.cpu_c5_rate(wl, 10.0)
+    rows.append({"variant": "port, all threads", "kind": "port", "steps_per_s": rate, "ms_per_step_mean": 1e3 / rate,
+                 "cores": cores, "sample": sample})
+    out["configs"].append({"config": "C5 64 candidates x 200 closed-loop steps (MPC steps/s of the whole job)", "rows": rows})
     print(json.dumps(out, indent=1))
 
 
